@@ -1,0 +1,85 @@
+/* sqeazy_b200 device-pointer extension of the sqeazy C API (new; not in the reference).
+ *
+ * The reference's boundary (include/sqeazy.h) takes HOST buffers, so every call pays two PCIe
+ * crossings. These entry points take DEVICE pointers and a CUDA stream handle (cudaStream_t passed
+ * as void*; NULL = legacy default stream) so that callers holding data in HBM — and the roofline
+ * measurements in bench.py — reach the same kernels without the copies. Plain C ABI: pointers and
+ * sizes only. The SQY_* host entry points are thin wrappers over these.
+ *
+ * Return value: 0 on success, non-zero on failure (same convention as sqeazy.h).
+ * All functions synchronise `stream` before returning unless stated otherwise.
+ */
+#ifndef SQEAZY_B200_EXT_H
+#define SQEAZY_B200_EXT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- whole pipelines (replace dynamic_pipeline::encode/decode, dynamic_pipeline.hpp:560-690,740-846) ---- */
+
+/* d_src: shape-product uint16 voxels in device memory. d_dst: device buffer of dst_capacity bytes
+ * (>= SQY_Pipeline_Max_Compressed_Length_UI16). Writes [header][payload]; *dst_bytes = blob bytes. */
+int sqyx_encode_device_UI16(const char* pipeline, const void* d_src, const long* shape, unsigned shape_size, void* d_dst,
+                            long dst_capacity, long* dst_bytes, void* stream);
+
+/* as above; d_global_hist (device, 65536 x uint32) replaces the local histogram of a `quantiser` stage.
+ * Multi-GPU: every rank fills its histogram with sqyx_histogram_UI16, all-reduces it (NCCL, sum) and
+ * passes the result here, so all ranks derive the identical LUT. NULL = histogram d_src locally. */
+int sqyx_encode_device_ex_UI16(const char* pipeline, const void* d_src, const long* shape, unsigned shape_size, void* d_dst,
+                               long dst_capacity, long* dst_bytes, const void* d_global_hist, void* stream);
+
+/* d_blob: [header][payload] in device memory; d_dst: device buffer of dst_capacity bytes (>= raw bytes). */
+int sqyx_decode_device_UI16(const void* d_blob, long blob_bytes, void* d_dst, long dst_capacity, void* stream);
+
+/* ---- single stages (what the parity tests drive) ---- */
+
+/* bitswapN, w in {1,2,4,8}; threshold > 0 fuses remove_background(threshold) into the load.
+ * reference: encoders/bitswap_scheme_impl.hpp:97-197 */
+int sqyx_bitswap_encode_UI16(int w, const void* d_src, void* d_dst, long n, int threshold, void* stream);
+int sqyx_bitswap_decode_UI16(int w, const void* d_src, void* d_dst, long n, void* stream);
+
+/* out = in > t ? in - t : 0. reference: encoders/remove_background_scheme_impl.hpp:73-95 */
+int sqyx_remove_background_UI16(const void* d_src, void* d_dst, long n, int threshold, void* stream);
+
+/* rmestbkrd threshold: four 99 % supports (z=0 face, z=Z-1 face, rows y=0 / y=Y-1 at z in {1,Z/2,Z-2}) and
+ * threshold = (uint16)min. l2_bytes < 0 = use this host's L2 size the way the reference does (SQY_L2_BYTES
+ * overrides). reference: encoders/background_scheme_utils.hpp:35-105, remove_estimated_background_scheme_impl.hpp:71-112 */
+int sqyx_estimate_background_UI16(const void* d_src, const long* shape3, long l2_bytes, float* supports4, int* threshold,
+                                  void* stream);
+
+/* 65536-bin uint32 histogram, ACCUMULATED into d_hist (zero it first). Does not synchronise.
+ * reference: encoders/histogram_utils.hpp:41-55,98-154 */
+int sqyx_histogram_UI16(const void* d_src, long n, void* d_hist, void* stream);
+
+/* host-side LUT construction from a histogram (host pointers): enc 65536 x u8, dec 256 x u16.
+ * reference: encoders/quantiser_utils.hpp:227-306,386-418 */
+int sqyx_quantiser_luts(const unsigned* hist, unsigned char* enc, unsigned short* dec);
+
+/* LUT gathers; the tables are HOST pointers (copied to the device inside).
+ * reference: encoders/quantiser_scheme_impl.hpp:206-223 (apply), :245-282 (decode) */
+int sqyx_lut_apply_UI16(const void* d_src, void* d_codes, long n, const unsigned char* enc_host, void* stream);
+int sqyx_lut_decode_UI16(const void* d_codes, void* d_dst, long n, const unsigned short* dec_host, void* stream);
+
+/* LZ4 frames. sqyx_lz4_bound(n) = capacity the encoder may need for n input bytes.
+ * reference: encoders/lz4.hpp:214-242 (encode), :257-339 (decode), :166-188 (bound) */
+long sqyx_lz4_bound(long nbytes);
+int sqyx_lz4_encode(const void* d_src, long nbytes, void* d_dst, long dst_capacity, long* payload_bytes, void* stream);
+int sqyx_lz4_decode(const void* d_src, long nbytes, void* d_dst, long dst_bytes, long* decoded_bytes, void* stream);
+
+/* ---- bookkeeping ---- */
+int sqyx_device_count(void);
+/* cumulative number of CUDA kernels launched by this library in this process */
+long sqyx_kernel_launches(void);
+/* block statistics of the most recent LZ4 encode on this thread's device:
+ * out[0] general-path blocks, out[1] constant (closed-form) blocks, out[2] stored blocks, out[3] payload bytes */
+int sqyx_last_lz4_stats(long* out4);
+/* value of compass-style L2 probe used by rmestbkrd on this host */
+long sqyx_host_l2_bytes(void);
+/* releases the cached device scratch of the current device */
+int sqyx_release_scratch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

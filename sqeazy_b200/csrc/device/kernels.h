@@ -1,0 +1,37 @@
+// Internal launch interface of the sm_100a kernels (device pointers, explicit stream).
+// Every function enqueues work on `st` and returns 0 or a cudaError_t / negative library code.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <atomic>
+
+namespace sqyb {
+
+// cumulative count of kernels launched by this library (reported as gpu_launches by bench.py)
+extern std::atomic<long> g_kernel_launches;
+#define SQYB_COUNT_LAUNCH(n) ::sqyb::g_kernel_launches.fetch_add((n), std::memory_order_relaxed)
+
+// bitswap.cu
+int k_bitswap_encode(int w, const uint16_t* in, uint16_t* out, uint64_t n, int threshold, cudaStream_t st);
+int k_bitswap_decode(int w, const uint16_t* in, uint16_t* out, uint64_t n, cudaStream_t st);
+int k_remove_background(const uint16_t* in, uint16_t* out, uint64_t n, int threshold, cudaStream_t st);
+
+// quantise.cu
+int k_histogram_u16(const uint16_t* in, uint64_t n, uint32_t* hist /* 65536 x u32, accumulated into */, cudaStream_t st);
+int k_lut_apply(const uint16_t* in, uint8_t* out, uint64_t n, const uint8_t* lut_dev /* 65536 */, cudaStream_t st);
+int k_lut_decode(const uint8_t* in, uint16_t* out, uint64_t n, const uint16_t* lut_dev /* 256 */, cudaStream_t st);
+
+// lz4_encode.cu
+size_t k_lz4_encode_workspace_bytes(uint64_t raw_bytes);
+// workspace[0..8) receives the payload size (u64) when the stream has drained; [16,28) block-kind counters
+int k_lz4_encode(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, cudaStream_t st);
+
+// lz4_decode.cu
+size_t k_lz4_decode_workspace_bytes(uint64_t dst_bytes);
+int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, int measure_all,
+                 cudaStream_t st);
+int k_lz4_decode_status(void* workspace, uint32_t* error, uint64_t* total_decoded, cudaStream_t st);
+
+}  // namespace sqyb

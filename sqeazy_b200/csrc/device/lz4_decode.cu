@@ -1,0 +1,480 @@
+// LZ4 frame decoder for sm_100a: decodes any concatenation of LZ4 frames (what the reference's
+// sequential loop accepts, encoders/lz4.hpp:257-339): frames written by this library (independent
+// 16 KiB blocks + block index in a skippable frame), by the reference's parallel mode (one frame
+// per chunk, encoders/lz4_utils.hpp:193-274) and by its serial mode / the sqy CLI default (one frame
+// of block-LINKED 256 KiB blocks, encoders/lz4_utils.hpp:99-173).
+//
+// Stages (all on the GPU, no host round trip):
+//   directory : one CTA parses the stream. Our index frame -> block table by a parallel prefix sum;
+//               foreign frames -> thread 0 walks the 4-byte block headers.
+//   sizes     : only for foreign blocks whose decoded size is not implied (last block of a frame):
+//               a warp per block parses tokens without copying.
+//   offsets   : one CTA prefix-sums decoded sizes into output offsets and validates the total.
+//   decode    : persistent grid, a warp per block; tokens/lengths parsed warp-uniformly, literals and
+//               matches copied 32 lanes wide; linked blocks wait on their predecessor's flag only when
+//               a match reaches in front of the block.
+#include "common.cuh"
+#include "kernels.h"
+#include "lz4_format.h"
+
+namespace sqyb {
+namespace {
+
+constexpr uint32_t kNoLink = 0xFFFFFFFFu;
+
+enum DecErr : uint32_t {
+  kErrNone = 0,
+  kErrBadMagic = 1,
+  kErrTruncated = 2,
+  kErrTooManyBlocks = 3,
+  kErrBadBlock = 4,
+  kErrSizeMismatch = 5,
+  kErrBadHeader = 6,
+};
+
+struct DecCtl {          // lives at the start of the workspace
+  uint32_t nblocks;
+  uint32_t error;
+  uint32_t ticket_size;
+  uint32_t ticket_decode;
+  uint32_t need_sizes;   // number of blocks whose decoded size must be measured
+  uint32_t pad[3];
+  unsigned long long total_decoded;
+};
+
+struct DecTables {
+  unsigned long long* src_off;   // offset of block data in the stream
+  unsigned long long* dst_off;   // offset in the output
+  uint32_t* word;                // block header word (bit31 = stored)
+  uint32_t* dsize;               // decoded size (0 = unknown until the size pass)
+  uint32_t* link;                // previous block of the same linked frame or kNoLink
+  uint32_t* done;                // completion flags for linked frames
+};
+
+__device__ __forceinline__ uint32_t rd32(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__device__ __forceinline__ unsigned long long rd64(const uint8_t* p) {
+  return (unsigned long long)rd32(p) | ((unsigned long long)rd32(p + 4) << 32);
+}
+
+// inclusive block scan of one value per thread (1024 threads); returns inclusive sum, total via smem
+__device__ __forceinline__ unsigned long long block_scan_incl(unsigned long long v, unsigned long long* warp_sums,
+                                                              unsigned long long& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += t;
+  }
+  __syncthreads();
+  if (lane == 31) warp_sums[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = warp_sums[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += t;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  total = warp_sums[31];
+  return v + (warp > 0 ? warp_sums[warp - 1] : 0ull);
+}
+
+constexpr int kDirThreads = 1024;
+constexpr int kPerThread = 8;
+
+__global__ void __launch_bounds__(kDirThreads) lz4_directory_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
+                                                                    DecCtl* ctl, DecTables T, uint32_t capacity,
+                                                                    int measure_all) {
+  __shared__ unsigned long long warp_sums[32];
+  __shared__ unsigned long long sh_pos;
+  __shared__ uint32_t sh_nb, sh_err, sh_mode, sh_need;
+  __shared__ unsigned long long sh_args[4];
+  const int tid = threadIdx.x;
+  if (tid == 0) { sh_pos = 0; sh_nb = 0; sh_err = 0; sh_need = 0; }
+  __syncthreads();
+  while (true) {
+    // ---- thread 0 classifies what starts at pos ----
+    if (tid == 0) {
+      sh_mode = 0;  // 0 stop, 1 our indexed frame (parallel), 2 handled serially / continue
+      const unsigned long long pos = sh_pos;
+      if (sh_err == 0 && pos + 4 <= src_bytes) {
+        const uint32_t magic = rd32(src + pos);
+        if ((magic & 0xFFFFFFF0u) == kLz4SkippableMagicBase) {
+          if (pos + 8 > src_bytes) { sh_err = kErrTruncated; }
+          else {
+            const unsigned long long size = rd32(src + pos + 4);
+            const unsigned long long body = pos + 8;
+            bool ours = false;
+            if (magic == kSqybSkippableMagic && size >= sizeof(SqybIndexHeader) && body + size <= src_bytes &&
+                rd32(src + body) == kSqybIndexMagic && rd32(src + body + 4) == 1u) {
+              const uint32_t bb = rd32(src + body + 8), nblk = rd32(src + body + 12);
+              const unsigned long long raw = rd64(src + body + 16), fbytes = rd64(src + body + 24);
+              const unsigned long long fstart = body + size;
+              if (size == sizeof(SqybIndexHeader) + 4ull * nblk && bb > 0 && fstart + fbytes <= src_bytes &&
+                  fbytes >= kLz4FrameHeaderBytes + kLz4EndMarkBytes && rd32(src + fstart) == kLz4FrameMagic &&
+                  (src[fstart + 4] & 0x1D) == 0 /* no checksums, no content size, no dict */ &&
+                  (unsigned long long)nblk * bb >= raw && (nblk == 0 || (unsigned long long)(nblk - 1) * bb < raw)) {
+                ours = true;
+                if ((unsigned long long)sh_nb + nblk > capacity) sh_err = kErrTooManyBlocks;
+                else {
+                  sh_args[0] = body + sizeof(SqybIndexHeader);   // index words
+                  sh_args[1] = fstart + kLz4FrameHeaderBytes;    // first block header
+                  sh_args[2] = ((unsigned long long)bb << 32) | nblk;
+                  sh_args[3] = raw;
+                  sh_pos = fstart + fbytes;
+                  sh_mode = 1;
+                }
+              }
+            }
+            if (!ours && sh_err == 0) {
+              if (body + size > src_bytes) sh_err = kErrTruncated;
+              else { sh_pos = body + size; sh_mode = 2; }
+            }
+          }
+        } else if (magic == kLz4FrameMagic) {
+          // ---- foreign frame: serial walk of the block headers ----
+          if (pos + 7 > src_bytes) sh_err = kErrTruncated;
+          else {
+            const uint32_t flg = src[pos + 4], bd = src[pos + 5];
+            const bool indep = (flg >> 5) & 1, bchk = (flg >> 4) & 1, csz = (flg >> 3) & 1, cchk = (flg >> 2) & 1, dict = flg & 1;
+            const uint32_t bsid = (bd >> 4) & 7;
+            if ((flg >> 6) != 1 || bsid < 4) sh_err = kErrBadHeader;
+            else {
+              const uint32_t maxblock = 1u << (8 + 2 * bsid);
+              unsigned long long p = pos + 7 + (csz ? 8 : 0) + (dict ? 4 : 0);
+              uint32_t nb = sh_nb;
+              const uint32_t first_of_frame = nb;
+              while (true) {
+                if (p + 4 > src_bytes) { sh_err = kErrTruncated; break; }
+                const uint32_t word = rd32(src + p);
+                if (word == 0) { p += 4; break; }
+                const uint32_t sz = word & 0x7FFFFFFFu;
+                if (sz > maxblock || p + 4 + sz > src_bytes) { sh_err = kErrBadBlock; break; }
+                if (nb >= capacity) { sh_err = kErrTooManyBlocks; break; }
+                T.src_off[nb] = p + 4;
+                T.word[nb] = word;
+                // non-final blocks of liblz4 frames are full; measure_all drops that assumption
+                T.dsize[nb] = (word & kLz4StoredFlag) ? sz : (measure_all ? 0u : maxblock);
+                if (measure_all && !(word & kLz4StoredFlag)) sh_need++;
+                T.link[nb] = (!indep && nb > first_of_frame) ? nb - 1 : kNoLink;
+                nb++;
+                p += 4ull + sz + (bchk ? 4 : 0);
+              }
+              if (sh_err == 0) {
+                if (cchk) p += 4;
+                // the last block of a frame may be short: its size has to be measured
+                if (!measure_all && nb > first_of_frame && !(T.word[nb - 1] & kLz4StoredFlag)) { T.dsize[nb - 1] = 0; sh_need++; }
+                sh_nb = nb;
+                sh_pos = p;
+                sh_mode = 2;
+              }
+            }
+          }
+        } else {
+          sh_err = kErrBadMagic;
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t mode = sh_mode;
+    if (mode == 0) break;
+    if (mode == 1) {
+      // ---- our frame: block table by parallel prefix sum over the index words ----
+      const uint8_t* idx = src + sh_args[0];
+      const unsigned long long first_hdr = sh_args[1];
+      const uint32_t nblk = (uint32_t)(sh_args[2] & 0xFFFFFFFFu), bb = (uint32_t)(sh_args[2] >> 32);
+      const unsigned long long raw = sh_args[3];
+      const uint32_t nb0 = sh_nb;
+      unsigned long long running = 0;
+      for (uint32_t base = 0; base < nblk; base += kDirThreads * kPerThread) {
+        uint32_t w[kPerThread];
+        unsigned long long local = 0;
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) {
+          const uint32_t i = base + tid * kPerThread + k;
+          w[k] = i < nblk ? rd32(idx + 4ull * i) : 0u;
+          local += i < nblk ? 4ull + (w[k] & 0x7FFFFFFFu) : 0ull;
+        }
+        unsigned long long total;
+        const unsigned long long incl = block_scan_incl(local, warp_sums, total);
+        unsigned long long off = running + incl - local;
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) {
+          const uint32_t i = base + tid * kPerThread + k;
+          if (i < nblk) {
+            T.src_off[nb0 + i] = first_hdr + off + 4;
+            T.word[nb0 + i] = w[k];
+            const unsigned long long rem = raw - (unsigned long long)i * bb;
+            T.dsize[nb0 + i] = (uint32_t)(rem < bb ? rem : bb);
+            T.link[nb0 + i] = kNoLink;
+            off += 4ull + (w[k] & 0x7FFFFFFFu);
+          }
+        }
+        running += total;
+        __syncthreads();
+      }
+      if (tid == 0) sh_nb = nb0 + nblk;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    ctl->nblocks = sh_nb;
+    ctl->error = sh_err;
+    ctl->need_sizes = sh_need;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp-level block decode
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t read_ext(const uint8_t* __restrict__ src, uint32_t& ip, uint32_t csize, int lane) {
+  uint32_t add = 0;
+  while (true) {
+    const uint32_t idx = ip + lane;
+    const uint32_t bval = idx < csize ? (uint32_t)__ldg(src + idx) : 0u;
+    const uint32_t nz = __ballot_sync(0xffffffffu, bval != 255u);
+    if (nz) {
+      const int f = __ffs(nz) - 1;
+      add += 255u * f + __shfl_sync(0xffffffffu, bval, f);
+      ip += f + 1;
+      return add;
+    }
+    add += 255u * 32u;
+    ip += 32;
+  }
+}
+
+// copy n bytes src -> dst (src read-only stream, arbitrary alignment), warp-cooperative
+__device__ __forceinline__ void warp_copy_from_stream(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n,
+                                                      int lane) {
+  if (n >= 256 && (((uintptr_t)dst) & 15) == 0) {
+    // 16-byte stores; source words fetched 4-byte aligned and funnel-shifted
+    const uint32_t sh = ((uintptr_t)src & 3) * 8;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>((uintptr_t)src & ~(uintptr_t)3);
+    const uint32_t nvec = (n - 8) >> 4;  // keep the 5-word read inside [src, src+n)
+    for (uint32_t v = lane; v < nvec; v += 32) {
+      const uint32_t* p = sw + v * 4;
+      const uint32_t x0 = __ldg(p), x1 = __ldg(p + 1), x2 = __ldg(p + 2), x3 = __ldg(p + 3), x4 = __ldg(p + 4);
+      uint4 o;
+      o.x = __funnelshift_r(x0, x1, sh);
+      o.y = __funnelshift_r(x1, x2, sh);
+      o.z = __funnelshift_r(x2, x3, sh);
+      o.w = __funnelshift_r(x3, x4, sh);
+      reinterpret_cast<uint4*>(dst)[v] = o;
+    }
+    const uint32_t done = nvec << 4;
+    for (uint32_t k = done + lane; k < n; k += 32) dst[k] = __ldg(src + k);
+  } else {
+    for (uint32_t k = lane; k < n; k += 32) dst[k] = __ldg(src + k);
+  }
+}
+
+template <bool kSizeOnly>
+__device__ __forceinline__ uint32_t decode_block_warp(const uint8_t* __restrict__ src, uint32_t csize, uint8_t* dst,
+                                                      uint32_t dcap, unsigned long long before, uint32_t link,
+                                                      const uint32_t* done, bool& waited, uint32_t& err, int lane) {
+  uint32_t ip = 0, op = 0;
+  while (ip < csize) {
+    const uint32_t token = __ldg(src + ip);
+    ip++;
+    uint32_t lit = token >> 4;
+    if (lit == 15) lit += read_ext(src, ip, csize, lane);
+    if (lit) {
+      if (ip + lit > csize || op + lit > dcap) { err = kErrBadBlock; return op; }
+      if (!kSizeOnly) {
+        if (lit <= 32) { if ((uint32_t)lane < lit) dst[op + lane] = __ldg(src + ip + lane); }
+        else warp_copy_from_stream(dst + op, src + ip, lit, lane);
+      }
+      ip += lit;
+      op += lit;
+    }
+    if (ip >= csize) break;
+    if (ip + 2 > csize) { err = kErrBadBlock; return op; }
+    const uint32_t offset = (uint32_t)__ldg(src + ip) | ((uint32_t)__ldg(src + ip + 1) << 8);
+    ip += 2;
+    uint32_t mlen = token & 15u;
+    if (mlen == 15) mlen += read_ext(src, ip, csize, lane);
+    mlen += 4;
+    if (offset == 0 || op + mlen > dcap) { err = kErrBadBlock; return op; }
+    if (!kSizeOnly) {
+      if (offset > op) {
+        // reaches in front of this block: only legal inside a linked frame
+        if (link == kNoLink || (unsigned long long)(offset - op) > before) { err = kErrBadBlock; return op; }
+        if (!waited) {
+          if (lane == 0) {
+            while (atomicAdd(const_cast<uint32_t*>(done) + link, 0u) == 0u) __nanosleep(100);
+            __threadfence();
+          }
+          waited = true;
+        }
+      }
+      __syncwarp();
+      uint8_t* o = dst + op;
+      if (offset >= 32) {
+        // 32 bytes per step never overlap their own source; later steps may read earlier ones
+        const bool overlap = mlen > offset;
+        for (uint32_t kb = 0; kb < mlen; kb += 32) {
+          const uint32_t k = kb + lane;
+          if (k < mlen) o[k] = o[(long long)k - offset];
+          if (overlap) __syncwarp();
+        }
+      } else if (offset == 1) {
+        const uint8_t v = *(o - 1);
+        for (uint32_t k = lane; k < mlen; k += 32) o[k] = v;
+      } else {
+        const uint8_t* base = o - offset;
+        for (uint32_t k = lane; k < mlen; k += 32) o[k] = base[k % offset];
+      }
+      __syncwarp();
+    }
+    op += mlen;
+  }
+  return op;
+}
+
+constexpr int kDecThreads = 128;
+
+// measures the decoded size of the blocks the directory could not infer
+__global__ void __launch_bounds__(kDecThreads) lz4_sizes_kernel(const uint8_t* __restrict__ src, DecCtl* ctl, DecTables T) {
+  if (ctl->error || ctl->need_sizes == 0) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t nblocks = ctl->nblocks;
+  while (true) {
+    uint32_t b = 0;
+    if (lane == 0) b = atomicAdd(&ctl->ticket_size, 1u);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= nblocks) return;
+    if (T.dsize[b] != 0 || (T.word[b] & kLz4StoredFlag)) continue;
+    bool waited = false;
+    uint32_t err = 0;
+    const uint32_t sz = decode_block_warp<true>(src + T.src_off[b], T.word[b] & 0x7FFFFFFFu, nullptr, 0xFFFFFFFFu, 0, kNoLink,
+                                               nullptr, waited, err, lane);
+    if (lane == 0) {
+      T.dsize[b] = sz;
+      if (err) atomicMax(&ctl->error, err);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kDirThreads) lz4_offsets_kernel(DecCtl* ctl, DecTables T, uint64_t dst_bytes) {
+  __shared__ unsigned long long warp_sums[32];
+  if (ctl->error) return;
+  const uint32_t nblk = ctl->nblocks;
+  const int tid = threadIdx.x;
+  unsigned long long running = 0;
+  for (uint32_t base = 0; base < nblk; base += kDirThreads * kPerThread) {
+    uint32_t d[kPerThread];
+    unsigned long long local = 0;
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) {
+      const uint32_t i = base + tid * kPerThread + k;
+      d[k] = i < nblk ? T.dsize[i] : 0u;
+      local += d[k];
+    }
+    unsigned long long total;
+    const unsigned long long incl = block_scan_incl(local, warp_sums, total);
+    unsigned long long off = running + incl - local;
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) {
+      const uint32_t i = base + tid * kPerThread + k;
+      if (i < nblk) { T.dst_off[i] = off; T.done[i] = 0; off += d[k]; }
+    }
+    running += total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    ctl->total_decoded = running;
+    // the reference accepts 0 < decoded <= expected (encoders/lz4.hpp:334-338); we refuse overruns
+    if (running > dst_bytes || (running == 0 && dst_bytes != 0)) ctl->error = kErrSizeMismatch;
+  }
+}
+
+__global__ void __launch_bounds__(kDecThreads) lz4_decode_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                 DecCtl* ctl, DecTables T) {
+  if (ctl->error) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t nblocks = ctl->nblocks;
+  while (true) {
+    uint32_t b = 0;
+    if (lane == 0) b = atomicAdd(&ctl->ticket_decode, 1u);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= nblocks) return;
+    const uint32_t word = T.word[b];
+    const uint32_t csize = word & 0x7FFFFFFFu;
+    const uint32_t dsize = T.dsize[b];
+    const unsigned long long doff = T.dst_off[b];
+    const uint32_t link = T.link[b];
+    const uint8_t* s = src + T.src_off[b];
+    uint8_t* d = dst + doff;
+    bool waited = false;
+    uint32_t err = 0;
+    if (word & kLz4StoredFlag) {
+      if (csize != dsize) err = kErrSizeMismatch;
+      else warp_copy_from_stream(d, s, csize, lane);
+    } else {
+      // bytes of the same linked frame in front of this block (at most the 64 KiB window matters)
+      const unsigned long long before = link != kNoLink ? doff : 0ull;
+      const uint32_t got = decode_block_warp<false>(s, csize, d, dsize, before, link, T.done, waited, err, lane);
+      if (!err && got != dsize) err = kErrSizeMismatch;
+    }
+    if (err && lane == 0) atomicMax(&ctl->error, err);
+    // publish completion (linked frames): a block is done when it and its predecessor are done
+    __syncwarp();
+    if (lane == 0) {
+      if (link != kNoLink && !waited) {
+        while (atomicAdd(T.done + link, 0u) == 0u) __nanosleep(100);
+      }
+      __threadfence();
+      atomicExch(T.done + b, 1u);
+    }
+  }
+}
+
+}  // namespace
+
+size_t k_lz4_decode_capacity(uint64_t dst_bytes) { return (size_t)(dst_bytes / kLz4BlockBytes + 1024); }
+
+size_t k_lz4_decode_workspace_bytes(uint64_t dst_bytes) {
+  const size_t cap = k_lz4_decode_capacity(dst_bytes);
+  return 256 + cap * (8 + 8 + 4 + 4 + 4 + 4) + 256;
+}
+
+// Enqueues the whole decode; the status lands in workspace (see k_lz4_decode_status).
+int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, int measure_all,
+                 cudaStream_t st) {
+  const size_t cap = k_lz4_decode_capacity(dst_bytes);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  DecCtl* ctl = reinterpret_cast<DecCtl*>(ws);
+  DecTables T;
+  uint8_t* p = ws + 256;
+  T.src_off = reinterpret_cast<unsigned long long*>(p); p += 8 * cap;
+  T.dst_off = reinterpret_cast<unsigned long long*>(p); p += 8 * cap;
+  T.word = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
+  T.dsize = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
+  T.link = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
+  T.done = reinterpret_cast<uint32_t*>(p);
+  SQYB_CUDA_OK(cudaMemsetAsync(ctl, 0, sizeof(DecCtl), st));
+  lz4_directory_kernel<<<1, kDirThreads, 0, st>>>(src, src_bytes, ctl, T, (uint32_t)cap, measure_all);
+  lz4_sizes_kernel<<<kNumSMs * 4, kDecThreads, 0, st>>>(src, ctl, T);
+  lz4_offsets_kernel<<<1, kDirThreads, 0, st>>>(ctl, T, dst_bytes);
+  lz4_decode_kernel<<<kNumSMs * 16, kDecThreads, 0, st>>>(src, dst, ctl, T);
+  SQYB_COUNT_LAUNCH(4);
+  return (int)cudaGetLastError();
+}
+
+// copies {error, total_decoded} back (synchronises the stream)
+int k_lz4_decode_status(void* workspace, uint32_t* error, uint64_t* total_decoded, cudaStream_t st) {
+  DecCtl h;
+  SQYB_CUDA_OK(cudaMemcpyAsync(&h, workspace, sizeof(DecCtl), cudaMemcpyDeviceToHost, st));
+  SQYB_CUDA_OK(cudaStreamSynchronize(st));
+  *error = h.error;
+  *total_decoded = h.total_decoded;
+  return 0;
+}
+
+}  // namespace sqyb

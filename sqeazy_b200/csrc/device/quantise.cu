@@ -1,0 +1,146 @@
+// Quantiser device kernels: the 65536-bin uint32 histogram and the two LUT gathers.
+//   histogram : encoders/histogram_utils.hpp:41-55,98-154 (serial/parallel::fill_histogram),
+//               called single-threaded by quantiser::computeHistogram (quantiser_utils.hpp:144-151)
+//   LUT apply : quantiser_scheme_impl.hpp:206-223 (u16 -> 8-bit code, 65536-entry table)
+//   LUT decode: quantiser_scheme_impl.hpp:258-279, quantiser_utils.hpp:26-42 (8-bit -> u16, 256 entries;
+//               unsigned index — the reference's signed-char index is UB for codes >= 128)
+//
+// Histogram layout: 65536 x u32 does not fit one SM's shared memory (256 KiB > 227 KB), so each CTA
+// privatises the low kSmemBins = 49152 bins (192 KiB, shared-memory atomics) and sends the rare values
+// above that straight to global atomics; one CTA per SM, flushed once at the end. Counts are exact
+// uint32 (mod 2^32, like the reference's bins).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sqyb {
+namespace {
+
+constexpr int kSmemBins = 49152;
+constexpr int kHistThreads = 1024;
+
+__global__ void __launch_bounds__(kHistThreads, 1) histogram_u16_kernel(const uint16_t* __restrict__ in, uint64_t n,
+                                                                        uint32_t* __restrict__ hist) {
+  extern __shared__ uint32_t sh[];
+  for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // head (unaligned) elements are handled by the scalar loop at the end via [0, lead)
+  const uintptr_t addr = (uintptr_t)in;
+  uint64_t lead = ((16 - (addr & 15)) & 15) / 2;
+  if (lead > n) lead = n;
+  const uint4* vin = reinterpret_cast<const uint4*>(in + lead);
+  const uint64_t nv = (n - lead) / 8;
+  auto add = [&](uint32_t v) {
+    if (v < (uint32_t)kSmemBins) atomicAdd(&sh[v], 1u);
+    else atomicAdd(&hist[v], 1u);
+  };
+  for (uint64_t i = tid; i < nv; i += stride) {
+    const uint4 v = ld_stream(vin + i);
+    add(v.x & 0xffff); add(v.x >> 16);
+    add(v.y & 0xffff); add(v.y >> 16);
+    add(v.z & 0xffff); add(v.z >> 16);
+    add(v.w & 0xffff); add(v.w >> 16);
+  }
+  for (uint64_t i = tid; i < lead; i += stride) add(in[i]);
+  for (uint64_t i = lead + nv * 8 + tid; i < n; i += stride) add(in[i]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x) {
+    const uint32_t c = sh[i];
+    if (c) atomicAdd(&hist[i], c);
+  }
+}
+
+// small ranges (rmestbkrd faces/rows): plain global atomics
+__global__ void histogram_u16_small_kernel(const uint16_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ hist) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(&hist[in[i]], 1u);
+}
+
+// u16 -> u8 through a 65536-entry table staged in shared memory (64 KiB)
+__global__ void __launch_bounds__(512) lut_apply_kernel(const uint16_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                        uint64_t n, const uint8_t* __restrict__ lut) {
+  extern __shared__ uint32_t shw[];
+  uint8_t* s = reinterpret_cast<uint8_t*>(shw);
+  {
+    const uint4* l4 = reinterpret_cast<const uint4*>(lut);
+    uint4* s4 = reinterpret_cast<uint4*>(shw);
+    for (int i = threadIdx.x; i < 65536 / 16; i += blockDim.x) s4[i] = l4[i];
+  }
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool aligned = ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 7) == 0;
+  const uint64_t nv = aligned ? n / 8 : 0;
+  for (uint64_t i = tid; i < nv; i += stride) {
+    const uint4 v = ld_stream(reinterpret_cast<const uint4*>(in) + i);
+    uint2 o;
+    o.x = s[v.x & 0xffff] | (s[v.x >> 16] << 8) | (s[v.y & 0xffff] << 16) | (s[v.y >> 16] << 24);
+    o.y = s[v.z & 0xffff] | (s[v.z >> 16] << 8) | (s[v.w & 0xffff] << 16) | (s[v.w >> 16] << 24);
+    st_stream(reinterpret_cast<uint2*>(out) + i, o);
+  }
+  for (uint64_t i = nv * 8 + tid; i < n; i += stride) out[i] = s[in[i]];
+}
+
+// u8 -> u16 through a 256-entry table
+__global__ void __launch_bounds__(512) lut_decode_kernel(const uint8_t* __restrict__ in, uint16_t* __restrict__ out,
+                                                         uint64_t n, const uint16_t* __restrict__ lut) {
+  __shared__ uint16_t s[256];
+  if (threadIdx.x < 256) s[threadIdx.x] = lut[threadIdx.x];
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool aligned = ((uintptr_t)in & 7) == 0 && ((uintptr_t)out & 15) == 0;
+  const uint64_t nv = aligned ? n / 8 : 0;
+  for (uint64_t i = tid; i < nv; i += stride) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(in) + i);
+    uint4 o;
+    o.x = s[v.x & 0xff] | ((uint32_t)s[(v.x >> 8) & 0xff] << 16);
+    o.y = s[(v.x >> 16) & 0xff] | ((uint32_t)s[v.x >> 24] << 16);
+    o.z = s[v.y & 0xff] | ((uint32_t)s[(v.y >> 8) & 0xff] << 16);
+    o.w = s[(v.y >> 16) & 0xff] | ((uint32_t)s[v.y >> 24] << 16);
+    st_stream(reinterpret_cast<uint4*>(out) + i, o);
+  }
+  for (uint64_t i = nv * 8 + tid; i < n; i += stride) out[i] = s[in[i]];
+}
+
+}  // namespace
+
+int k_histogram_u16(const uint16_t* in, uint64_t n, uint32_t* hist, cudaStream_t st) {
+  if (n == 0) return 0;
+  if (n < (1u << 20)) {
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    histogram_u16_small_kernel<<<blocks, 256, 0, st>>>(in, n, hist);
+    SQYB_COUNT_LAUNCH(1);
+    return (int)cudaGetLastError();
+  }
+  const size_t smem = kSmemBins * sizeof(uint32_t);
+  SQYB_CUDA_OK(cudaFuncSetAttribute(histogram_u16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  histogram_u16_kernel<<<kNumSMs, kHistThreads, smem, st>>>(in, n, hist);
+  SQYB_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+int k_lut_apply(const uint16_t* in, uint8_t* out, uint64_t n, const uint8_t* lut_dev, cudaStream_t st) {
+  if (n == 0) return 0;
+  SQYB_CUDA_OK(cudaFuncSetAttribute(lut_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  uint64_t blocks = (n / 8 + 511) / 512;
+  if (blocks > (uint64_t)kNumSMs * 3) blocks = kNumSMs * 3;  // 3 CTAs (64 KiB each) per SM, grid-stride
+  if (blocks < 1) blocks = 1;
+  lut_apply_kernel<<<(int)blocks, 512, 65536, st>>>(in, out, n, lut_dev);
+  SQYB_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+int k_lut_decode(const uint8_t* in, uint16_t* out, uint64_t n, const uint16_t* lut_dev, cudaStream_t st) {
+  if (n == 0) return 0;
+  uint64_t blocks = (n / 8 + 511) / 512;
+  if (blocks > (uint64_t)kNumSMs * 16) blocks = kNumSMs * 16;
+  if (blocks < 1) blocks = 1;
+  lut_decode_kernel<<<(int)blocks, 512, 0, st>>>(in, out, n, lut_dev);
+  SQYB_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace sqyb
