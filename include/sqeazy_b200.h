@@ -69,11 +69,19 @@ int sqyx_lz4_decode(const void* d_src, long nbytes, void* d_dst, long dst_bytes,
 
 /* ---- bookkeeping ---- */
 int sqyx_device_count(void);
+/* makes `device` current for the calling thread inside this library's CUDA runtime instance (one process
+ * per GPU callers set it once; all sqyx_ and SQY_ calls then use that device) */
+int sqyx_set_device(int device);
 /* cumulative number of CUDA kernels launched by this library in this process */
 long sqyx_kernel_launches(void);
 /* block statistics of the most recent LZ4 encode on this thread's device:
  * out[0] general-path blocks, out[1] constant (closed-form) blocks, out[2] stored blocks, out[3] payload bytes */
 int sqyx_last_lz4_stats(long* out4);
+/* per-stage device time (CUDA events on the caller's stream, accumulated over calls while enabled):
+ * out7 = {filter+bitswap encode, lz4 encode, histogram, LUT apply, lz4 decode, LUT decode, bitswap decode} in ms.
+ * Enabling adds an event synchronisation per stage; leave it off for throughput runs. */
+int sqyx_enable_stage_timing(int on);
+int sqyx_stage_ms(float* out7, int reset);
 /* value of compass-style L2 probe used by rmestbkrd on this host */
 long sqyx_host_l2_bytes(void);
 /* releases the cached device scratch of the current device */

@@ -1,0 +1,319 @@
+"""sqeazy_b200 — B200-native sqeazy volume pipeline (bitswapN, remove_background/rmestbkrd, quantiser, LZ4).
+
+This package is a thin ctypes mirror of the C ABI in include/sqeazy.h (the reference's boundary,
+src/cpp/inc/sqeazy.h) and include/sqeazy_b200.h (device-pointer extension). All compute happens in
+the hand-written sm_100a kernels inside sqeazy_b200/libsqeazy.so; there is no Python or CPU
+fallback: if the shared library is missing, importing `lib()` raises.
+
+Host-buffer calls (numpy) map 1:1 to SQY_*; device-buffer calls (torch CUDA tensors) map to sqyx_*.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_bool, c_char_p, c_float, c_int, c_long, c_uint, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsqeazy.so")
+
+# every symbol declared in include/sqeazy.h and include/sqeazy_b200.h
+SQY_SYMBOLS = [
+    "SQY_Header_Size", "SQY_Decompressed_NDims", "SQY_Decompressed_Shape", "SQY_Decompressed_Sizeof",
+    "SQY_Decompressed_Length", "SQY_Version_Triple", "SQY_PipelineEncode_UI16", "SQY_PipelineEncode_UI8",
+    "SQY_Pipeline_Max_Compressed_Length_UI16", "SQY_Pipeline_Max_Compressed_Length_UI8",
+    "SQY_Pipeline_Max_Compressed_Length_3D_UI16", "SQY_Pipeline_Max_Compressed_Length_3D_UI8",
+    "SQY_Pipeline_Possible_UI16", "SQY_Pipeline_Possible_UI8", "SQY_Pipeline_Possible", "SQY_Decode_UI16",
+    "SQY_PipelineDecode_UI16", "SQY_Decode_UI8", "SQY_h5_query_sizeof", "SQY_h5_query_dtype", "SQY_h5_query_ndims",
+    "SQY_h5_query_shape", "SQY_h5_read_UI16", "SQY_h5_write_UI16", "SQY_h5_write", "SQY_h5_link",
+]
+SQYX_SYMBOLS = [
+    "sqyx_encode_device_UI16", "sqyx_encode_device_ex_UI16", "sqyx_decode_device_UI16", "sqyx_bitswap_encode_UI16",
+    "sqyx_bitswap_decode_UI16", "sqyx_remove_background_UI16", "sqyx_estimate_background_UI16", "sqyx_histogram_UI16",
+    "sqyx_quantiser_luts", "sqyx_lut_apply_UI16", "sqyx_lut_decode_UI16", "sqyx_lz4_bound", "sqyx_lz4_encode",
+    "sqyx_lz4_decode", "sqyx_device_count", "sqyx_kernel_launches", "sqyx_last_lz4_stats", "sqyx_host_l2_bytes",
+    "sqyx_release_scratch", "sqyx_set_device", "sqyx_enable_stage_timing", "sqyx_stage_ms",
+]
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Loads libsqeazy.so (built by `make` / __graft_entry__.build()). Fails loudly when absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `make` (or __graft_entry__.build()). sqeazy_b200 has no fallback path.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.SQY_Pipeline_Possible_UI16.restype = c_bool
+        L.SQY_Pipeline_Possible_UI8.restype = c_bool
+        L.SQY_Pipeline_Possible.restype = c_bool
+        for name in ("sqyx_lz4_bound", "sqyx_kernel_launches", "sqyx_host_l2_bytes"):
+            getattr(L, name).restype = c_long
+        _lib = L
+    return _lib
+
+
+class SqeazyError(RuntimeError):
+    pass
+
+
+def _vp(a: np.ndarray):
+    return a.ctypes.data_as(c_void_p)
+
+
+# ------------------------------------------------------------------------------------------------
+# SQY_* : host buffers (numpy)
+# ------------------------------------------------------------------------------------------------
+def pipeline_possible(pipeline: str, sizeof_pixel: int = 2) -> bool:
+    return bool(lib().SQY_Pipeline_Possible(pipeline.encode("latin-1"), c_int(sizeof_pixel)))
+
+
+def max_compressed_length(pipeline: str, raw_bytes: int) -> int:
+    p = pipeline.encode("latin-1")
+    n = c_long(raw_bytes)
+    if lib().SQY_Pipeline_Max_Compressed_Length_UI16(p, c_long(len(p)), ctypes.byref(n)) != 0:
+        raise SqeazyError(f"invalid pipeline {pipeline!r}")
+    return n.value
+
+
+def max_compressed_length_3d(pipeline: str, shape) -> int:
+    p = pipeline.encode("latin-1")
+    shp = (c_long * len(shape))(*shape)
+    n = c_long(len(p))
+    if lib().SQY_Pipeline_Max_Compressed_Length_3D_UI16(p, shp, c_uint(len(shape)), ctypes.byref(n)) != 0:
+        raise SqeazyError(f"invalid pipeline {pipeline!r}")
+    return n.value
+
+
+def encode(pipeline: str, volume: np.ndarray, nthreads: int = 1, out: np.ndarray | None = None) -> np.ndarray:
+    """SQY_PipelineEncode_UI16: uint16 volume (any rank, C order) -> blob bytes (uint8 array)."""
+    vol = np.ascontiguousarray(volume, dtype=np.uint16)
+    cap = max_compressed_length(pipeline, vol.nbytes)
+    if out is None or out.size < cap:
+        out = np.empty(cap, dtype=np.uint8)
+    shp = (c_long * vol.ndim)(*vol.shape)
+    n = c_long(0)
+    rc = lib().SQY_PipelineEncode_UI16(pipeline.encode("latin-1"), _vp(vol), shp, c_uint(vol.ndim), _vp(out), ctypes.byref(n),
+                                       c_int(nthreads))
+    if rc != 0:
+        raise SqeazyError(f"SQY_PipelineEncode_UI16({pipeline!r}) returned {rc}")
+    return out[: n.value]
+
+
+def header_size(blob: np.ndarray) -> int:
+    n = c_long(blob.size)
+    lib().SQY_Header_Size(_vp(blob), ctypes.byref(n))
+    return n.value
+
+
+def decompressed_shape(blob: np.ndarray):
+    nd = c_long(blob.size)
+    lib().SQY_Decompressed_NDims(_vp(blob), ctypes.byref(nd))
+    shp = (c_long * max(nd.value, 1))()
+    shp[0] = blob.size
+    lib().SQY_Decompressed_Shape(_vp(blob), shp)
+    return tuple(shp[i] for i in range(nd.value))
+
+
+def decompressed_length(blob: np.ndarray) -> int:
+    n = c_long(blob.size)
+    lib().SQY_Decompressed_Length(_vp(blob), ctypes.byref(n))
+    return n.value
+
+
+def decompressed_sizeof(blob: np.ndarray) -> int:
+    n = c_long(blob.size)
+    lib().SQY_Decompressed_Sizeof(_vp(blob), ctypes.byref(n))
+    return n.value
+
+
+def version_triple():
+    v = (c_int * 3)()
+    lib().SQY_Version_Triple(v)
+    return tuple(v)
+
+
+def decode(blob: np.ndarray, nthreads: int = 1, out: np.ndarray | None = None) -> np.ndarray:
+    """SQY_Decode_UI16: blob -> uint16 volume of the shape stored in the header."""
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    shape = decompressed_shape(blob)
+    nbytes = decompressed_length(blob)
+    if out is None:
+        out = np.empty(nbytes // 2, dtype=np.uint16)
+    rc = lib().SQY_Decode_UI16(_vp(blob), c_long(blob.size), _vp(out), c_int(nthreads))
+    if rc != 0:
+        raise SqeazyError(f"SQY_Decode_UI16 returned {rc}")
+    return out.reshape(shape) if shape else out
+
+
+# ------------------------------------------------------------------------------------------------
+# sqyx_* : device buffers (torch CUDA tensors). torch is plumbing only: memory, streams, distributed.
+# ------------------------------------------------------------------------------------------------
+def _stream_handle(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return c_void_p(s.cuda_stream)
+
+
+def _dp(t):
+    return c_void_p(t.data_ptr())
+
+
+def set_device(index: int):
+    """binds the library's CUDA runtime to `index` for this thread (torch.cuda.set_device does not reach it)"""
+    if lib().sqyx_set_device(c_int(index)) != 0:
+        raise SqeazyError(f"sqyx_set_device({index}) failed")
+
+
+def encode_device(pipeline: str, volume, out=None, global_hist=None, stream=None):
+    """sqyx_encode_device[_ex]_UI16. volume: CUDA tensor of 16-bit voxels (any rank); returns a uint8 CUDA view of the blob."""
+    import torch
+    assert volume.is_cuda and volume.element_size() == 2 and volume.is_contiguous()
+    cap = max_compressed_length(pipeline, volume.numel() * 2)
+    if out is None or out.numel() < cap:
+        out = torch.empty(cap, dtype=torch.uint8, device=volume.device)
+    shp = (c_long * volume.dim())(*volume.shape)
+    n = c_long(0)
+    gh = _dp(global_hist) if global_hist is not None else c_void_p(0)
+    with torch.cuda.device(volume.device):
+        rc = lib().sqyx_encode_device_ex_UI16(pipeline.encode("latin-1"), _dp(volume), shp, c_uint(volume.dim()), _dp(out),
+                                              c_long(out.numel()), ctypes.byref(n), gh, _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError(f"sqyx_encode_device_UI16({pipeline!r}) returned {rc}")
+    return out[: n.value]
+
+
+def decode_device(blob, out, stream=None):
+    """sqyx_decode_device_UI16. blob: uint8 CUDA tensor; out: CUDA tensor with room for the raw volume."""
+    import torch
+    assert blob.is_cuda and out.is_cuda and blob.is_contiguous() and out.is_contiguous()
+    with torch.cuda.device(blob.device):
+        rc = lib().sqyx_decode_device_UI16(_dp(blob), c_long(blob.numel()), _dp(out), c_long(out.numel() * out.element_size()),
+                                           _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError(f"sqyx_decode_device_UI16 returned {rc}")
+    return out
+
+
+def bitswap_encode_device(w: int, src, dst, threshold: int = 0, stream=None):
+    rc = lib().sqyx_bitswap_encode_UI16(c_int(w), _dp(src), _dp(dst), c_long(src.numel()), c_int(threshold), _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError("sqyx_bitswap_encode_UI16 failed")
+    return dst
+
+
+def bitswap_decode_device(w: int, src, dst, stream=None):
+    rc = lib().sqyx_bitswap_decode_UI16(c_int(w), _dp(src), _dp(dst), c_long(src.numel()), _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError("sqyx_bitswap_decode_UI16 failed")
+    return dst
+
+
+def remove_background_device(src, dst, threshold: int, stream=None):
+    rc = lib().sqyx_remove_background_UI16(_dp(src), _dp(dst), c_long(src.numel()), c_int(threshold), _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError("sqyx_remove_background_UI16 failed")
+    return dst
+
+
+def estimate_background_device(volume, l2_bytes: int = -1, stream=None):
+    """returns (supports[4] float32, threshold) of rmestbkrd for a rank-3 CUDA volume"""
+    shp = (c_long * 3)(*volume.shape)
+    sup = (c_float * 4)()
+    t = c_int(0)
+    rc = lib().sqyx_estimate_background_UI16(_dp(volume), shp, c_long(l2_bytes), sup, ctypes.byref(t), _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError("sqyx_estimate_background_UI16 failed")
+    return np.array(list(sup), dtype=np.float32), t.value
+
+
+def histogram_device(src, hist, stream=None):
+    """accumulates the 65536-bin histogram of src into hist (int32/uint32 CUDA tensor of 65536); asynchronous"""
+    rc = lib().sqyx_histogram_UI16(_dp(src), c_long(src.numel()), _dp(hist), _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError("sqyx_histogram_UI16 failed")
+    return hist
+
+
+def quantiser_luts(hist: np.ndarray):
+    hist = np.ascontiguousarray(hist, dtype=np.uint32)
+    enc = np.zeros(65536, dtype=np.uint8)
+    dec = np.zeros(256, dtype=np.uint16)
+    if lib().sqyx_quantiser_luts(_vp(hist), _vp(enc), _vp(dec)) != 0:
+        raise SqeazyError("sqyx_quantiser_luts failed")
+    return enc, dec
+
+
+def lut_apply_device(src, codes, enc: np.ndarray, stream=None):
+    enc = np.ascontiguousarray(enc, dtype=np.uint8)
+    rc = lib().sqyx_lut_apply_UI16(_dp(src), _dp(codes), c_long(src.numel()), _vp(enc), _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError("sqyx_lut_apply_UI16 failed")
+    return codes
+
+
+def lut_decode_device(codes, dst, dec: np.ndarray, stream=None):
+    dec = np.ascontiguousarray(dec, dtype=np.uint16)
+    rc = lib().sqyx_lut_decode_UI16(_dp(codes), _dp(dst), c_long(codes.numel()), _vp(dec), _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError("sqyx_lut_decode_UI16 failed")
+    return dst
+
+
+def lz4_bound(nbytes: int) -> int:
+    return int(lib().sqyx_lz4_bound(c_long(nbytes)))
+
+
+def lz4_encode_device(src, out=None, stream=None):
+    """src: CUDA tensor (any dtype, contiguous) -> uint8 CUDA view of the LZ4 frame stream"""
+    import torch
+    nbytes = src.numel() * src.element_size()
+    cap = lz4_bound(nbytes)
+    if out is None or out.numel() < cap:
+        out = torch.empty(cap, dtype=torch.uint8, device=src.device)
+    n = c_long(0)
+    rc = lib().sqyx_lz4_encode(_dp(src), c_long(nbytes), _dp(out), c_long(out.numel()), ctypes.byref(n), _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError("sqyx_lz4_encode failed")
+    return out[: n.value]
+
+
+def lz4_decode_device(payload, out, stream=None):
+    """payload: uint8 CUDA tensor of LZ4 frames; out: CUDA tensor receiving the decoded bytes. Returns decoded byte count."""
+    n = c_long(0)
+    rc = lib().sqyx_lz4_decode(_dp(payload), c_long(payload.numel()), _dp(out), c_long(out.numel() * out.element_size()),
+                               ctypes.byref(n), _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError("sqyx_lz4_decode failed")
+    return n.value
+
+
+def kernel_launches() -> int:
+    return int(lib().sqyx_kernel_launches())
+
+
+def last_lz4_stats():
+    o = (c_long * 4)()
+    lib().sqyx_last_lz4_stats(o)
+    return {"general_blocks": o[0], "constant_blocks": o[1], "stored_blocks": o[2], "payload_bytes": o[3]}
+
+
+def host_l2_bytes() -> int:
+    return int(lib().sqyx_host_l2_bytes())
+
+
+STAGE_NAMES = ("filter_bitswap_encode", "lz4_encode", "histogram", "lut_apply", "lz4_decode", "lut_decode", "bitswap_decode")
+
+
+def enable_stage_timing(on: bool = True):
+    lib().sqyx_enable_stage_timing(c_int(1 if on else 0))
+
+
+def stage_ms(reset: bool = True):
+    """accumulated device milliseconds per stage since the last reset (needs enable_stage_timing(True))"""
+    o = (c_float * 7)()
+    lib().sqyx_stage_ms(o, c_int(1 if reset else 0))
+    return dict(zip(STAGE_NAMES, [float(v) for v in o]))

@@ -85,6 +85,38 @@ struct Arena {
 std::mutex g_mu;
 Arena g_arena[16];
 
+// ---- optional per-stage CUDA-event timing (sqyx_enable_stage_timing) ----
+enum StageTimer { kTFilterSwap = 0, kTLz4Enc, kTHist, kTLutApply, kTLz4Dec, kTLutDec, kTSwapDec, kNumTimers };
+std::atomic<int> g_timing{0};
+float g_stage_ms[kNumTimers] = {0};
+
+struct ScopedStageTimer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t st;
+  int slot;
+  bool on;
+  ScopedStageTimer(int slot_, cudaStream_t st_) : st(st_), slot(slot_), on(g_timing.load() != 0) {
+    if (on) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, st);
+    }
+  }
+  void stop() {
+    if (on && a) {
+      cudaEventRecord(b, st);
+      cudaEventSynchronize(b);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, a, b);
+      g_stage_ms[slot] += ms;
+      cudaEventDestroy(a);
+      cudaEventDestroy(b);
+      a = b = nullptr;
+    }
+  }
+  ~ScopedStageTimer() { stop(); }
+};
+
 int current_arena(Arena** a) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
@@ -172,6 +204,7 @@ int encode_device_impl(Arena& A, const Pipeline& pl_in, const uint16_t* d_src, c
   for (size_t i = 0; i < pl.head.size(); ++i) {
     const Stage& s = pl.head[i];
     uint16_t* out = nullptr;
+    ScopedStageTimer tm(kTFilterSwap, st);
     if (s.kind == StageKind::RemoveBackground || s.kind == StageKind::RmEstBkrd) {
       int t = s.threshold;
       if (s.kind == StageKind::RmEstBkrd) {
@@ -205,7 +238,10 @@ int encode_device_impl(Arena& A, const Pipeline& pl_in, const uint16_t* d_src, c
     }
     void* ws = nullptr;
     if (A.get(kSlotWs, k_lz4_encode_workspace_bytes(nbytes), &ws)) return 1;
-    CKK(k_lz4_encode(src, nbytes, payload, ws, st));
+    {
+      ScopedStageTimer tm(kTLz4Enc, st);
+      CKK(k_lz4_encode(src, nbytes, payload, ws, st));
+    }
     unsigned long long hres[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(hres, ws, 32, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -241,7 +277,9 @@ int encode_device_impl(Arena& A, const Pipeline& pl_in, const uint16_t* d_src, c
         CK(cudaMemcpyAsync(h.data(), d_global_hist, 65536 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
       } else {
         CK(cudaMemsetAsync(d_hist, 0, 65536 * sizeof(uint32_t), st));
+        ScopedStageTimer tm(kTHist, st);
         CKK(k_histogram_u16(cur, N, d_hist, st));
+        tm.stop();
         CK(cudaMemcpyAsync(h.data(), d_hist, 65536 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
       }
       CK(cudaStreamSynchronize(st));
@@ -256,7 +294,10 @@ int encode_device_impl(Arena& A, const Pipeline& pl_in, const uint16_t* d_src, c
       uint16_t* codes16 = nullptr;
       if (next_buf(&codes16)) return 1;
       uint8_t* codes = reinterpret_cast<uint8_t*>(codes16);
-      CKK(k_lut_apply(cur, codes, N, d_lut, st));
+      {
+        ScopedStageTimer tm(kTLutApply, st);
+        CKK(k_lut_apply(cur, codes, N, d_lut, st));
+      }
       if (lz4_into_payload(codes, N)) return 1;
     } else {
       if (payload_cap < N) return 1;
@@ -286,7 +327,10 @@ int lz4_decode_checked(Arena& A, const uint8_t* src, uint64_t nbytes, uint8_t* d
   void* ws = nullptr;
   if (A.get(kSlotWs, k_lz4_decode_workspace_bytes(dst_bytes), &ws)) return 1;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    CKK(k_lz4_decode(src, nbytes, dst, dst_bytes, ws, attempt, st));
+    {
+      ScopedStageTimer tm(kTLz4Dec, st);
+      CKK(k_lz4_decode(src, nbytes, dst, dst_bytes, ws, attempt, st));
+    }
     uint32_t err = 0;
     uint64_t total = 0;
     if (k_lz4_decode_status(ws, &err, &total, st)) return 1;
@@ -370,7 +414,10 @@ int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const ui
       if (A.get(kSlotSmall, 4 * 65536 * sizeof(uint32_t) + 4096, &sp)) return 1;
       uint16_t* d_lut = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(sp) + 4 * 65536 * sizeof(uint32_t));
       CK(cudaMemcpyAsync(d_lut, pl.sink.decode_lut, 512, cudaMemcpyHostToDevice, st));
-      CKK(k_lut_decode(codes, out, N, d_lut, st));
+      {
+        ScopedStageTimer tm(kTLutDec, st);
+        CKK(k_lut_decode(codes, out, N, d_lut, st));
+      }
       CK(cudaStreamSynchronize(st));
     }
     cur = out;
@@ -390,7 +437,10 @@ int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const ui
       // pick the scratch buffer that does not hold `cur`
       if (scratch(cur == bufs[0] ? 1 : 0, &out)) return 1;
     }
-    if (k_bitswap_decode(swaps[k], cur, out, N, st)) return 100 + 1;
+    {
+      ScopedStageTimer tm(kTSwapDec, st);
+      if (k_bitswap_decode(swaps[k], cur, out, N, st)) return 100 + 1;
+    }
     cur = out;
   }
   CK(cudaStreamSynchronize(st));
@@ -430,7 +480,23 @@ int sqyx_device_count(void) {
   return n;
 }
 
+int sqyx_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? 0 : 1; }
+
 long sqyx_kernel_launches(void) { return sqyb::g_kernel_launches.load(); }
+
+int sqyx_enable_stage_timing(int on) {
+  g_timing.store(on ? 1 : 0);
+  return 0;
+}
+
+int sqyx_stage_ms(float* out7, int reset) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (int i = 0; i < kNumTimers; ++i) {
+    if (out7) out7[i] = g_stage_ms[i];
+    if (reset) g_stage_ms[i] = 0;
+  }
+  return 0;
+}
 
 long sqyx_host_l2_bytes(void) { return (long)host_l2_cache_bytes(); }
 
