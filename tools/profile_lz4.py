@@ -1,0 +1,22 @@
+"""Small driver for ncu: bitswap a cfg1-sized synthetic stack, then LZ4-encode and -decode it a few times."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import sqeazy_b200 as sq
+from sqeazy_b200.synth import torch_volume
+
+shape = (256, 512, 512) if len(sys.argv) < 2 else tuple(int(v) for v in sys.argv[1].split("x"))
+reps = 3 if len(sys.argv) < 3 else int(sys.argv[2])
+torch.cuda.set_device(0)
+sq.set_device(0)
+vol = torch_volume(shape, "scmos")
+planes = torch.empty_like(vol)
+sq.bitswap_encode_device(1, vol.view(-1), planes.view(-1))
+out = torch.empty_like(vol)
+payload = None
+for _ in range(reps):
+    payload = sq.lz4_encode_device(planes)
+    sq.lz4_decode_device(payload, out)
+torch.cuda.synchronize()
+assert torch.equal(out, planes)
+print("payload", payload.numel(), sq.last_lz4_stats())
