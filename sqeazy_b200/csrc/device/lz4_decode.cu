@@ -38,7 +38,9 @@ struct DecCtl {          // lives at the start of the workspace
   uint32_t ticket_size;
   uint32_t ticket_decode;
   uint32_t need_sizes;   // number of blocks whose decoded size must be measured
-  uint32_t pad[3];
+  uint32_t ticket_small;
+  uint32_t n_small;      // blocks that take the shared-memory path
+  uint32_t n_generic;    // blocks that take the global-memory path
   unsigned long long total_decoded;
 };
 
@@ -339,6 +341,179 @@ __device__ __forceinline__ uint32_t decode_block_warp(const uint8_t* __restrict_
 
 constexpr int kDecThreads = 128;
 
+// ------------------------------------------------------------------------------------------------
+// shared-memory path: independent blocks of at most 16 KiB (everything this library writes)
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kSmallBlock = kLz4BlockBytes;
+constexpr uint32_t kRing = 1024;  // two 512-byte chunks of the compressed stream per warp
+constexpr int kSmallWarps = 4;
+constexpr size_t kSmallWarpSmem = kSmallBlock + 64 + kRing;
+
+__device__ __forceinline__ bool small_block_eligible(uint32_t word, uint32_t dsize, uint32_t link) {
+  return link == kNoLink && dsize <= kSmallBlock && dsize > 0 && (word & 0x7FFFFFFFu) <= kSmallBlock + 64;
+}
+
+__device__ __forceinline__ uint4 load_stream_piece(const uint8_t* addr, const uint8_t* sbeg, const uint8_t* send) {
+  if (addr >= sbeg && addr + 16 <= send) return __ldg(reinterpret_cast<const uint4*>(addr));
+  uint32_t w[4] = {0, 0, 0, 0};
+  for (int k = 0; k < 16; ++k) {
+    const uint8_t* p = addr + k;
+    if (p >= sbeg && p < send) w[k >> 2] |= (uint32_t)__ldg(p) << (8 * (k & 3));
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Decodes one block into out8 (shared memory). The compressed stream is windowed through a 1 KiB ring
+// (chunk c of the 16-byte aligned stream lives in ring half c & 1; chunk cur+2 waits in registers).
+__device__ __forceinline__ uint32_t decode_block_smem(const uint8_t* __restrict__ s, uint32_t csize, uint8_t* out8, uint32_t dcap,
+                                                      uint8_t* ring8, const uint8_t* sbeg, const uint8_t* send, uint32_t& err,
+                                                      int lane) {
+  const uint8_t* A = reinterpret_cast<const uint8_t*>((uintptr_t)s & ~(uintptr_t)15);
+  const uint32_t shift = (uint32_t)(s - A);
+  uint4* ring4 = reinterpret_cast<uint4*>(ring8);
+  uint32_t cur = 0;
+  ring4[lane] = load_stream_piece(A + 16u * lane, sbeg, send);
+  ring4[32 + lane] = load_stream_piece(A + 512u + 16u * lane, sbeg, send);
+  uint4 pre = load_stream_piece(A + 1024u + 16u * lane, sbeg, send);
+  __syncwarp();
+  auto ensure = [&](uint32_t pos) {
+    const uint32_t c = pos >> 9;
+    if (c == cur) return;
+    __syncwarp();
+    if (c == cur + 1) {
+      ring4[((cur + 2) & 1) * 32 + lane] = pre;
+      cur = c;
+    } else {  // jumped over a long literal run: re-prime
+      cur = c;
+      ring4[(c & 1) * 32 + lane] = load_stream_piece(A + 512ull * c + 16u * lane, sbeg, send);
+      ring4[((c + 1) & 1) * 32 + lane] = load_stream_piece(A + 512ull * (c + 1) + 16u * lane, sbeg, send);
+    }
+    pre = load_stream_piece(A + 512ull * (cur + 2) + 16u * lane, sbeg, send);
+    __syncwarp();
+  };
+#define SQYB_RB(pos) ((uint32_t)ring8[(pos) & (kRing - 1)])
+  uint32_t ip = shift, op = 0;
+  const uint32_t end = shift + csize;
+  uint32_t token = SQYB_RB(ip);
+  while (ip < end) {
+    ensure(ip);
+    ip++;
+    uint32_t lit = token >> 4;
+    if (lit == 15) {
+      uint32_t b;
+      do {
+        if (ip >= end) { err = kErrBadBlock; return op; }
+        b = SQYB_RB(ip);
+        ip++;
+        lit += b;
+      } while (b == 255);
+    }
+    if (lit) {
+      if (ip + lit > end || op + lit > dcap) { err = kErrBadBlock; return op; }
+      if (lit <= 32) {
+        if ((uint32_t)lane < lit) out8[op + lane] = (uint8_t)SQYB_RB(ip + lane);
+      } else if (ip + lit <= (cur + 2) * 512u) {
+        for (uint32_t k = lane; k < lit; k += 32) out8[op + k] = (uint8_t)SQYB_RB(ip + k);
+      } else {
+        for (uint32_t k = lane; k < lit; k += 32) out8[op + k] = __ldg(A + ip + k);
+      }
+      ip += lit;
+      op += lit;
+    }
+    if (ip >= end) break;
+    ensure(ip);
+    if (ip + 2 > end) { err = kErrBadBlock; return op; }
+    const uint32_t offset = SQYB_RB(ip) | (SQYB_RB(ip + 1) << 8);
+    ip += 2;
+    uint32_t mlen = token & 15u;
+    if (mlen == 15) {
+      uint32_t b;
+      do {
+        if (ip >= end) { err = kErrBadBlock; return op; }
+        b = SQYB_RB(ip);
+        ip++;
+        mlen += b;
+      } while (b == 255);
+    }
+    mlen += 4;
+    if (offset == 0 || offset > op || op + mlen > dcap) { err = kErrBadBlock; return op; }
+    token = SQYB_RB(ip);  // next token: chunk cur+1 is always resident, so this read is safe before ensure()
+    __syncwarp();
+    uint8_t* o = out8 + op;
+    if (mlen <= 32 && offset >= mlen) {
+      if ((uint32_t)lane < mlen) o[lane] = o[(int)lane - (int)offset];
+    } else if (offset >= 32) {
+      const bool overlap = mlen > offset;
+      for (uint32_t kb = 0; kb < mlen; kb += 32) {
+        const uint32_t k = kb + lane;
+        if (k < mlen) o[k] = o[(int)k - (int)offset];
+        if (overlap) __syncwarp();
+      }
+    } else if (offset == 1 && mlen >= 64) {
+      // run fill: byte head to a 4-byte boundary, 32-bit body, byte tail
+      const uint32_t v = o[-1];
+      const uint32_t head = (4u - ((uint32_t)(uintptr_t)o & 3u)) & 3u;
+      if ((uint32_t)lane < head) o[lane] = (uint8_t)v;
+      const uint32_t body = (mlen - head) >> 2;
+      uint32_t* o4 = reinterpret_cast<uint32_t*>(o + head);
+      const uint32_t v4 = v * 0x01010101u;
+      for (uint32_t k = lane; k < body; k += 32) o4[k] = v4;
+      const uint32_t done = head + (body << 2);
+      if ((uint32_t)lane < mlen - done) o[done + lane] = (uint8_t)v;
+    } else {
+      const uint8_t* base = o - offset;
+      for (uint32_t k = lane; k < mlen; k += 32) o[k] = base[k % offset];
+    }
+    __syncwarp();
+    op += mlen;
+  }
+#undef SQYB_RB
+  return op;
+}
+
+__global__ void __launch_bounds__(kSmallWarps * 32) lz4_decode_small_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
+                                                                           uint8_t* __restrict__ dst, DecCtl* ctl, DecTables T) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  if (ctl->error || ctl->n_small == 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* out8 = dsm + (size_t)warp * kSmallWarpSmem;
+  uint8_t* ring8 = out8 + kSmallBlock + 64;
+  const uint32_t nblocks = ctl->nblocks;
+  while (true) {
+    uint32_t b = 0;
+    if (lane == 0) b = atomicAdd(&ctl->ticket_small, 1u);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= nblocks) return;
+    const uint32_t word = T.word[b];
+    const uint32_t csize = word & 0x7FFFFFFFu;
+    const uint32_t dsize = T.dsize[b];
+    if (!small_block_eligible(word, dsize, T.link[b])) continue;
+    const uint8_t* s = src + T.src_off[b];
+    uint8_t* d = dst + T.dst_off[b];
+    uint32_t err = 0;
+    if (word & kLz4StoredFlag) {
+      if (csize != dsize) err = kErrSizeMismatch;
+      else warp_copy_from_stream(d, s, csize, lane);
+    } else {
+      const uint32_t got = decode_block_smem(s, csize, out8, dsize, ring8, src, src + src_bytes, err, lane);
+      if (!err && got != dsize) err = kErrSizeMismatch;
+      __syncwarp();
+      if (!err) {
+        if ((((uintptr_t)d) & 15) == 0) {
+          const uint4* o4 = reinterpret_cast<const uint4*>(out8);
+          const uint32_t nv = dsize >> 4;
+          for (uint32_t v = lane; v < nv; v += 32) st_stream(reinterpret_cast<uint4*>(d) + v, o4[v]);
+          for (uint32_t k = (nv << 4) + lane; k < dsize; k += 32) d[k] = out8[k];
+        } else {
+          for (uint32_t k = lane; k < dsize; k += 32) d[k] = out8[k];
+        }
+      }
+      __syncwarp();
+    }
+    if (err && lane == 0) atomicMax(&ctl->error, err);
+  }
+}
+
 // measures the decoded size of the blocks the directory could not infer
 __global__ void __launch_bounds__(kDecThreads) lz4_sizes_kernel(const uint8_t* __restrict__ src, DecCtl* ctl, DecTables T) {
   if (ctl->error || ctl->need_sizes == 0) return;
@@ -367,6 +542,7 @@ __global__ void __launch_bounds__(kDirThreads) lz4_offsets_kernel(DecCtl* ctl, D
   const uint32_t nblk = ctl->nblocks;
   const int tid = threadIdx.x;
   unsigned long long running = 0;
+  uint32_t n_small = 0, n_generic = 0;
   for (uint32_t base = 0; base < nblk; base += kDirThreads * kPerThread) {
     uint32_t d[kPerThread];
     unsigned long long local = 0;
@@ -382,11 +558,19 @@ __global__ void __launch_bounds__(kDirThreads) lz4_offsets_kernel(DecCtl* ctl, D
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k) {
       const uint32_t i = base + tid * kPerThread + k;
-      if (i < nblk) { T.dst_off[i] = off; T.done[i] = 0; off += d[k]; }
+      if (i < nblk) {
+        T.dst_off[i] = off;
+        T.done[i] = 0;
+        off += d[k];
+        if (small_block_eligible(T.word[i], d[k], T.link[i])) n_small++;
+        else n_generic++;
+      }
     }
     running += total;
     __syncthreads();
   }
+  atomicAdd(&ctl->n_small, n_small);
+  atomicAdd(&ctl->n_generic, n_generic);
   if (tid == 0) {
     ctl->total_decoded = running;
     // the reference accepts 0 < decoded <= expected (encoders/lz4.hpp:334-338); we refuse overruns
@@ -396,7 +580,7 @@ __global__ void __launch_bounds__(kDirThreads) lz4_offsets_kernel(DecCtl* ctl, D
 
 __global__ void __launch_bounds__(kDecThreads) lz4_decode_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                                  DecCtl* ctl, DecTables T) {
-  if (ctl->error) return;
+  if (ctl->error || ctl->n_generic == 0) return;
   const int lane = threadIdx.x & 31;
   const uint32_t nblocks = ctl->nblocks;
   while (true) {
@@ -409,6 +593,7 @@ __global__ void __launch_bounds__(kDecThreads) lz4_decode_kernel(const uint8_t* 
     const uint32_t dsize = T.dsize[b];
     const unsigned long long doff = T.dst_off[b];
     const uint32_t link = T.link[b];
+    if (small_block_eligible(word, dsize, link)) continue;  // taken by lz4_decode_small_kernel
     const uint8_t* s = src + T.src_off[b];
     uint8_t* d = dst + doff;
     bool waited = false;
@@ -462,8 +647,11 @@ int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t 
   lz4_directory_kernel<<<1, kDirThreads, 0, st>>>(src, src_bytes, ctl, T, (uint32_t)cap, measure_all);
   lz4_sizes_kernel<<<kNumSMs * 4, kDecThreads, 0, st>>>(src, ctl, T);
   lz4_offsets_kernel<<<1, kDirThreads, 0, st>>>(ctl, T, dst_bytes);
+  const size_t small_smem = kSmallWarps * kSmallWarpSmem;
+  SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_decode_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+  lz4_decode_small_kernel<<<kNumSMs * 3, kSmallWarps * 32, small_smem, st>>>(src, src_bytes, dst, ctl, T);
   lz4_decode_kernel<<<kNumSMs * 16, kDecThreads, 0, st>>>(src, dst, ctl, T);
-  SQYB_COUNT_LAUNCH(4);
+  SQYB_COUNT_LAUNCH(5);
   return (int)cudaGetLastError();
 }
 

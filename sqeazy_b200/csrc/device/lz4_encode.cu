@@ -54,7 +54,11 @@ struct __align__(16) EncSmem {
   unsigned long long goff;
 };
 
-__device__ __forceinline__ int ext_bytes(int v) { return v < 15 ? 0 : 1 + (v - 15) / 255; }
+__device__ __forceinline__ int ext_bytes(int v) {
+  if (v < 15) return 0;          // by far the common case: keep the division off the hot path
+  if (v < 270) return 1;
+  return 1 + (v - 15) / 255;
+}
 
 __device__ __forceinline__ uint32_t load4(const uint32_t* words, int byte_off) {
   const uint32_t w0 = words[byte_off >> 2], w1 = words[(byte_off >> 2) + 1];
@@ -203,12 +207,17 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
       const uint32_t h = (v * 2654435761u) >> (32 - kHashLog);
       uint32_t found = kNone;
       if (i + kLz4MFLimit <= n) {
-        const uint32_t c = S.htab[h];
-        if (c != kNone && load4(S.data, (int)c) == v) found = c;
-        else if (i >= 1 && v == ((lo >> 24) | (v << 8))) found = i - 1;
+        // short offsets first: in bit-plane data runs and 2/4-byte periods give the long matches, while a
+        // table hit from an earlier round is often a stale 4-byte coincidence (tools/lz4_model.c: +20 % ratio
+        // on background-removed stacks)
+        if (i >= 1 && v == ((lo >> 24) | (v << 8))) found = i - 1;
         else if (i >= 2 && v == ((lo >> 16) | (v << 16))) found = i - 2;
         else if (i >= 4 && v == lo) found = i - 4;
         else if (i >= 3 && v == ((lo >> 8) | (v << 24))) found = i - 3;
+        else {
+          const uint32_t c = S.htab[h];
+          if (c != kNone && load4(S.data, (int)c) == v) found = c;
+        }
       }
       S.cand[i] = (uint16_t)found;
       nfound += found != kNone;
@@ -394,7 +403,7 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
         unsigned long long st = kFlagPre;  // virtual predecessor of block 0: prefix 0
         if (idx >= 0) {
           st = ld_acquire_u64(status + idx);
-          while ((st >> 62) == 0) { __nanosleep(40); st = ld_acquire_u64(status + idx); }
+          while ((st >> 62) == 0) { __nanosleep(256); st = ld_acquire_u64(status + idx); }
         }
         const uint32_t pm = __ballot_sync(0xffffffffu, (st >> 62) == 2);
         const int first = pm ? __ffs(pm) - 1 : 32;

@@ -1,0 +1,111 @@
+/* CPU model of the GPU LZ4 encoder's match finding + greedy parse, for tuning the compression ratio
+ * without a GPU (development tool, not shipped, not an oracle). Computes encoded sizes only.
+ * build: gcc -O2 -o /tmp/lz4_model tools/lz4_model.c
+ * usage: lz4_model file block_bytes round cut hashlog mode
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static int ext_bytes(int v) { return v < 15 ? 0 : 1 + (v - 15) / 255; }
+static uint32_t ld4(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+/* candidates: cand[i] = position or -1. round-based table (positions of earlier rounds) + short offsets */
+static void find_candidates(const uint8_t* d, int n, int round, int hashlog, int mode, int* cand) {
+  int tsize = 1 << hashlog;
+  int* tab = malloc(sizeof(int) * tsize);
+  for (int i = 0; i < tsize; ++i) tab[i] = -1;
+  for (int r0 = 0; r0 < n; r0 += round) {
+    int r1 = r0 + round < n ? r0 + round : n;
+    for (int i = r0; i < r1; ++i) {
+      cand[i] = -1;
+      if (i + 12 > n) continue;
+      uint32_t v = ld4(d + i);
+      uint32_t h = (v * 2654435761u) >> (32 - hashlog);
+      int c = tab[h];
+      int found = -1;
+      if (mode & 1) { /* prefer short offsets first */
+        if (i >= 1 && ld4(d + i - 1) == v) found = i - 1;
+        else if (i >= 2 && ld4(d + i - 2) == v) found = i - 2;
+        else if (i >= 4 && ld4(d + i - 4) == v) found = i - 4;
+        else if (i >= 3 && ld4(d + i - 3) == v) found = i - 3;
+        else if (c >= 0 && ld4(d + c) == v) found = c;
+      } else {
+        if (c >= 0 && ld4(d + c) == v) found = c;
+        else if (i >= 1 && ld4(d + i - 1) == v) found = i - 1;
+        else if (i >= 2 && ld4(d + i - 2) == v) found = i - 2;
+        else if (i >= 4 && ld4(d + i - 4) == v) found = i - 4;
+        else if (i >= 3 && ld4(d + i - 3) == v) found = i - 3;
+      }
+      if ((mode & 2) && found >= 0 && c >= 0 && c != found && ld4(d + c) == v) {
+        /* both available: keep the one with the longer 8-byte agreement */
+        int a = 4, b = 4;
+        while (a < 12 && i + a < n - 5 && d[i + a] == d[found + a]) a++;
+        while (b < 12 && i + b < n - 5 && d[i + b] == d[c + b]) b++;
+        if (b > a) found = c;
+      }
+      cand[i] = found;
+    }
+    for (int i = r0; i < r1; ++i) {
+      if (i + 4 > n) continue;
+      uint32_t v = ld4(d + i);
+      uint32_t h = (v * 2654435761u) >> (32 - hashlog);
+      tab[h] = i; /* last writer of the round wins (GPU: racy, any) */
+    }
+  }
+  free(tab);
+}
+
+static long encode_block_size(const uint8_t* d, int n, int round, int cut, int hashlog, int mode, long* nseq_out) {
+  int* cand = malloc(sizeof(int) * (n + 16));
+  find_candidates(d, n, round, hashlog, mode, cand);
+  long out = 0;
+  int anchor = 0, pos = 0;
+  long nseq = 0;
+  while (pos < n) {
+    int c = cand[pos];
+    if (c < 0) { pos++; continue; }
+    int limit = n - 5;
+    int cut_hi = ((pos / cut) + 1) * cut;
+    if (cut_hi < limit) limit = cut_hi;
+    int maxlen = limit - pos;
+    if (maxlen < 4) { pos++; continue; }
+    int len = 4;
+    while (len < maxlen && d[pos + len] == d[c + len]) len++;
+    if ((mode & 4) && len < 5 && pos > anchor) { pos++; continue; } /* skip len-4 matches that need a new token */
+    int lit = pos - anchor;
+    out += 1 + ext_bytes(lit) + lit + 2 + ext_bytes(len - 4);
+    nseq++;
+    pos += len;
+    anchor = pos;
+  }
+  int lit = n - anchor;
+  out += 1 + ext_bytes(lit) + lit;
+  free(cand);
+  if (nseq_out) *nseq_out += nseq;
+  return out >= n ? n : out;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 7) return 1;
+  FILE* f = fopen(argv[1], "rb");
+  fseek(f, 0, SEEK_END);
+  long total = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  uint8_t* buf = malloc(total + 64);
+  if (fread(buf, 1, total, f) != (size_t)total) return 2;
+  memset(buf + total, 0, 64);
+  int block = atoi(argv[2]), round = atoi(argv[3]), cut = atoi(argv[4]), hashlog = atoi(argv[5]), mode = atoi(argv[6]);
+  long out = 0, nseq = 0;
+  for (long o = 0; o < total; o += block) {
+    int n = o + block <= total ? block : (int)(total - o);
+    int same = 1;
+    for (int i = 1; i < n; ++i) if (buf[o + i] != buf[o]) { same = 0; break; }
+    if (same && n >= 16) { out += 4 + 4 + ext_bytes(n - 10) + 6; continue; }
+    out += 4 + encode_block_size(buf + o, n, round, cut, hashlog, mode, &nseq);
+  }
+  printf("block=%d round=%d cut=%d hashlog=%d mode=%d: %ld -> %ld ratio %.3f seqs %ld (%.1f B/seq)\n", block, round, cut, hashlog, mode,
+         total, out, (double)total / out, nseq, nseq ? (double)total / nseq : 0.0);
+  return 0;
+}
