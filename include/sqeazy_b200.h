@@ -48,6 +48,13 @@ int sqyx_remove_background_UI16(const void* d_src, void* d_dst, long n, int thre
 int sqyx_estimate_background_UI16(const void* d_src, const long* shape3, long l2_bytes, float* supports4, int* threshold,
                                   void* stream);
 
+/* host-side pieces of the threshold estimate, for callers that histogram the sampled faces/rows themselves (z-slabs
+ * spread over several GPUs: partial histograms are summed with an all-reduce, then every rank evaluates the support):
+ * calc_support(threshold) of a 65536-bin histogram (hist_impl.hpp:63-84,359-381) and the number of leading frame
+ * elements the reference samples (background_scheme_utils.hpp:44-45; l2_bytes < 0 = this host's L2). */
+float sqyx_histogram_support(const unsigned* hist, float threshold);
+long sqyx_rmest_frame_portion(long frame_elems, long l2_bytes);
+
 /* 65536-bin uint32 histogram, ACCUMULATED into d_hist (zero it first). Does not synchronise.
  * reference: encoders/histogram_utils.hpp:41-55,98-154 */
 int sqyx_histogram_UI16(const void* d_src, long n, void* d_hist, void* stream);

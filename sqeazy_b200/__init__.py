@@ -33,7 +33,8 @@ SQYX_SYMBOLS = [
     "sqyx_bitswap_decode_UI16", "sqyx_remove_background_UI16", "sqyx_estimate_background_UI16", "sqyx_histogram_UI16",
     "sqyx_quantiser_luts", "sqyx_lut_apply_UI16", "sqyx_lut_decode_UI16", "sqyx_lz4_bound", "sqyx_lz4_encode",
     "sqyx_lz4_decode", "sqyx_device_count", "sqyx_kernel_launches", "sqyx_last_lz4_stats", "sqyx_host_l2_bytes",
-    "sqyx_release_scratch", "sqyx_set_device", "sqyx_enable_stage_timing", "sqyx_stage_ms",
+    "sqyx_release_scratch", "sqyx_set_device", "sqyx_enable_stage_timing", "sqyx_stage_ms", "sqyx_histogram_support",
+    "sqyx_rmest_frame_portion",
 ]
 
 _lib = None
@@ -50,8 +51,10 @@ def lib() -> ctypes.CDLL:
         L.SQY_Pipeline_Possible_UI16.restype = c_bool
         L.SQY_Pipeline_Possible_UI8.restype = c_bool
         L.SQY_Pipeline_Possible.restype = c_bool
-        for name in ("sqyx_lz4_bound", "sqyx_kernel_launches", "sqyx_host_l2_bytes"):
+        for name in ("sqyx_lz4_bound", "sqyx_kernel_launches", "sqyx_host_l2_bytes", "sqyx_rmest_frame_portion"):
             getattr(L, name).restype = c_long
+        L.sqyx_histogram_support.restype = c_float
+        L.sqyx_histogram_support.argtypes = [c_void_p, c_float]
         _lib = L
     return _lib
 
@@ -245,6 +248,15 @@ def quantiser_luts(hist: np.ndarray):
     if lib().sqyx_quantiser_luts(_vp(hist), _vp(enc), _vp(dec)) != 0:
         raise SqeazyError("sqyx_quantiser_luts failed")
     return enc, dec
+
+
+def histogram_support(hist: np.ndarray, threshold: float = 0.99) -> float:
+    hist = np.ascontiguousarray(hist, dtype=np.uint32)
+    return float(lib().sqyx_histogram_support(_vp(hist), c_float(threshold)))
+
+
+def rmest_frame_portion(frame_elems: int, l2_bytes: int = -1) -> int:
+    return int(lib().sqyx_rmest_frame_portion(c_long(frame_elems), c_long(l2_bytes)))
 
 
 def lut_apply_device(src, codes, enc: np.ndarray, stream=None):

@@ -601,6 +601,13 @@ int sqyx_histogram_UI16(const void* d_src, long n, void* d_hist, void* stream) {
                          static_cast<cudaStream_t>(stream)) ? 1 : 0;
 }
 
+float sqyx_histogram_support(const unsigned* hist, float threshold) { return hist ? histogram_support(hist, threshold) : 0.f; }
+
+long sqyx_rmest_frame_portion(long frame_elems, long l2_bytes) {
+  const size_t l2 = l2_bytes >= 0 ? (size_t)l2_bytes : host_l2_cache_bytes();
+  return (long)rmest_frame_portion((uint64_t)frame_elems, l2);
+}
+
 int sqyx_quantiser_luts(const unsigned* hist, unsigned char* enc, unsigned short* dec) {
   if (!hist || !enc || !dec) return 1;
   quantiser_luts_from_histogram(hist, enc, dec);
