@@ -8,13 +8,17 @@
 //
 // Per block (16 KiB of input staged in shared memory by 512 threads):
 //   load    : 128-bit coalesced loads -> smem; all-equal blocks take a closed-form path
-//   phase A : every position finds a match candidate in parallel: 32 rounds of 512 positions against a
-//             4096-entry shared-memory hash table (positions of earlier rounds) plus register-only
-//             checks of offsets 1..4 for runs inside the current round
-//   phase B : 16 warps, one 1 KiB sub-block each, walk their candidates greedily with ballots, extend
-//             the selected matches 128 bytes per step, and record (offset,length) in place
-//   combine : one thread chains the 16 sub-block summaries (literal carry, output offsets)
-//   phase C : warps emit tokens/literals/offsets into a shared-memory output buffer at scanned offsets
+//   phase A : every position finds a match candidate in parallel: offsets 1..4 from registers first, then a
+//             4096-entry shared-memory hash table holding positions of earlier 512-byte rounds; the first 3
+//             bytes after the 4-byte match give a 2-bit length code; a warp's 32 positions are one segment,
+//             so three ballots leave candidate mask + code planes per 32-byte segment
+//   phase B : every THREAD parses its own 32-byte segment greedily with bit operations only (no shuffles,
+//             no shared memory for matches shorter than 7); a match may overshoot into later segments of the
+//             warp's 1 KiB sub-block, whose entry points move until the warp's parse is stable
+//   phase C : warp scans chain literal carries and encoded sizes (segments without a match hand their
+//             literals to the next sequence)
+//   phase D : every thread emits its own sequences; trailing literals are copied by the thread that owns
+//             the bytes into the sequence that owns them
 //   store   : single-pass decoupled look-back over block sizes gives the final byte offset; the CTA
 //             writes its block header + bytes once, coalesced, straight into the frame (no
 //             remove_blanks pass, no strided scratch)
@@ -28,28 +32,26 @@ namespace {
 constexpr int kB = kLz4BlockBytes;
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kSub = kB / kWarps;        // 1024 positions per warp
-constexpr int kWinPerSub = kSub / 32;    // 32 ballot windows per sub-block
+constexpr int kSub = kB / kWarps;        // 1 KiB sub-block per warp: matches never cross it
+constexpr int kSegs = kB / 32;           // 32-byte segments, one per thread
 constexpr int kPad = 256;
 constexpr uint32_t kNone = 0xFFFFu;
 constexpr int kHashLog = 12;
+constexpr int kInf = 0x7FFFFFFF;
 
-static_assert(kWinPerSub == 32, "one selection mask per lane");
+static_assert(kSegs == kThreads, "one segment per thread");
 
 struct __align__(16) EncSmem {
   uint32_t data[(kB + kPad) / 4];
-  uint32_t out[(kB + 64) / 4];
-  uint16_t cand[kB];
+  union {
+    uint16_t cand[kB];                   // phase A/B: candidate position per input position
+    uint32_t out[(kB + 64) / 4];         // phase D: encoded bytes (every cand read happens before the first out write)
+  };
   uint16_t htab[1 << kHashLog];
-  int sb_nseq[kWarps];
-  int sb_first_lit[kWarps];
-  int sb_rest[kWarps];
-  int sb_tail[kWarps];
-  int sb_carry[kWarps];
-  int sb_out_off[kWarps];
-  int final_off;
-  int final_lit;
-  int total;
+  uint32_t segM[kSegs], segC0[kSegs], segC1[kSegs];   // per segment: candidate mask and 2-bit length code planes
+  int seg_litbase[kSegs];                // dest(p) = seg_litbase + p for the literal run that ends at the segment's first match
+  int w_T[kWarps], w_has[kWarps], w_carry_in[kWarps], w_size[kWarps], w_off[kWarps], w_first[kWarps], w_next[kWarps];
+  int final_off, final_lit, total;
   uint32_t ticket;
   unsigned long long goff;
 };
@@ -110,6 +112,17 @@ __device__ __forceinline__ void store_bytes(uint8_t* __restrict__ g, const uint3
   if (tid < nbytes - done) g[done + tid] = sb[done + tid];
 }
 
+// serial extension of a match already known to agree on 7 bytes
+__device__ __forceinline__ int extend_match(const uint32_t* data, int i, int c, int maxlen) {
+  int len = 7;
+  while (len < maxlen) {
+    const uint32_t x = load4(data, i + len) ^ load4(data, c + len);
+    if (x) { len += (__ffs(x) - 1) >> 3; break; }
+    len += 4;
+  }
+  return len < maxlen ? len : maxlen;
+}
+
 __global__ void __launch_bounds__(kThreads, 3)
 lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* __restrict__ dst, uint32_t nblocks,
                   unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket_counter,
@@ -142,16 +155,15 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
         x = ld_stream(s4 + v);
         same = same && (x.x == pat) && (x.y == pat) && (x.z == pat) && (x.w == pat);
       } else if (v * 16 < n) {
-        uint8_t tmp[16];
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
         for (int q = 0; q < 16; ++q) {
           const bool in = v * 16 + q < n;
-          tmp[q] = in ? bsrc[v * 16 + q] : 0;
-          same = same && (!in || tmp[q] == (uint8_t)pat);
+          const uint32_t byte = in ? bsrc[v * 16 + q] : 0;
+          same = same && (!in || byte == (pat & 0xffu));
+          w[q >> 2] |= byte << (8 * (q & 3));
         }
-        x.x = tmp[0] | (tmp[1] << 8) | (tmp[2] << 16) | ((uint32_t)tmp[3] << 24);
-        x.y = tmp[4] | (tmp[5] << 8) | (tmp[6] << 16) | ((uint32_t)tmp[7] << 24);
-        x.z = tmp[8] | (tmp[9] << 8) | (tmp[10] << 16) | ((uint32_t)tmp[11] << 24);
-        x.w = tmp[12] | (tmp[13] << 8) | (tmp[14] << 16) | ((uint32_t)tmp[15] << 24);
+        x = make_uint4(w[0], w[1], w[2], w[3]);
       }
       d4[v] = x;
     }
@@ -195,32 +207,47 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
     __syncthreads();
     csize = S.total;
   } else {
-    // ---------------- phase A: candidates ----------------
+    // ---------------- phase A: a candidate (and a 2-bit length code) for every position ----------------
     int nfound = 0;
     for (int r = 0; r < kB / kThreads; ++r) {
-      const int i = r * kThreads + tid;
+      const int i = r * kThreads + tid;   // this warp covers exactly segment r*16 + warp
       const int wi = i >> 2, sh = (i & 3) * 8;
-      const uint32_t w0 = S.data[wi], w1 = S.data[wi + 1];
+      const uint32_t w0 = S.data[wi], w1 = S.data[wi + 1], w2 = S.data[wi + 2];
       const uint32_t wp = wi > 0 ? S.data[wi - 1] : 0u;
-      const uint32_t v = __funnelshift_r(w0, w1, sh);    // bytes i .. i+3
+      const uint32_t v = __funnelshift_r(w0, w1, sh);    // bytes i   .. i+3
+      const uint32_t v2 = __funnelshift_r(w1, w2, sh);   // bytes i+4 .. i+7
       const uint32_t lo = __funnelshift_r(wp, w0, sh);   // bytes i-4 .. i-1
       const uint32_t h = (v * 2654435761u) >> (32 - kHashLog);
-      uint32_t found = kNone;
-      if (i + kLz4MFLimit <= n) {
-        // short offsets first: in bit-plane data runs and 2/4-byte periods give the long matches, while a
-        // table hit from an earlier round is often a stale 4-byte coincidence (tools/lz4_model.c: +20 % ratio
-        // on background-removed stacks)
-        if (i >= 1 && v == ((lo >> 24) | (v << 8))) found = i - 1;
-        else if (i >= 2 && v == ((lo >> 16) | (v << 16))) found = i - 2;
-        else if (i >= 4 && v == lo) found = i - 4;
-        else if (i >= 3 && v == ((lo >> 8) | (v << 24))) found = i - 3;
+      const int sub_hi = (i & ~(kSub - 1)) + kSub;
+      const int maxlen = min(sub_hi, n - kLz4LastLiterals) - i;
+      uint32_t found = kNone, x = 0;
+      if (maxlen >= kLz4MinMatch && i + kLz4MFLimit <= n) {
+        // offsets 1..4 first (register-only): runs and short periods carry the long matches of bit-plane data,
+        // a table hit from an earlier round is often a stale 4-byte coincidence (tools/lz4_model.c)
+        if (i >= 1 && v == ((lo >> 24) | (v << 8))) { found = i - 1; x = v2 ^ ((v >> 24) | (v2 << 8)); }
+        else if (i >= 2 && v == ((lo >> 16) | (v << 16))) { found = i - 2; x = v2 ^ ((v >> 16) | (v2 << 16)); }
+        else if (i >= 4 && v == lo) { found = i - 4; x = v2 ^ v; }
+        else if (i >= 3 && v == ((lo >> 8) | (v << 24))) { found = i - 3; x = v2 ^ ((v >> 8) | (v2 << 24)); }
         else {
           const uint32_t c = S.htab[h];
-          if (c != kNone && load4(S.data, (int)c) == v) found = c;
+          if (c != kNone && load4(S.data, (int)c) == v) { found = c; x = v2 ^ load4(S.data, (int)c + 4); }
         }
       }
+      const bool has = found != kNone;
+      int len = 4 + (x ? ((__ffs(x) - 1) >> 3) : 4);
+      if (len > maxlen) len = maxlen;
+      const int code = len - 4 < 3 ? len - 4 : 3;   // 0,1,2: exact length 4,5,6; 3: at least 7, extended in phase B
       S.cand[i] = (uint16_t)found;
-      nfound += found != kNone;
+      const uint32_t M = __ballot_sync(0xffffffffu, has);
+      const uint32_t C0 = __ballot_sync(0xffffffffu, has && (code & 1));
+      const uint32_t C1 = __ballot_sync(0xffffffffu, has && (code & 2));
+      if (lane == 0) {
+        const int seg = r * kWarps + warp;
+        S.segM[seg] = M;
+        S.segC0[seg] = C0;
+        S.segC1[seg] = C1;
+      }
+      nfound |= has;
       __syncthreads();
       if (i + 4 <= n) S.htab[h] = (uint16_t)i;
       __syncthreads();
@@ -230,158 +257,237 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
     if (!any_found) {
       stored = true;
     } else {
-      // ---------------- phase B: greedy selection per 1 KiB sub-block ----------------
-      const int sub_lo = warp * kSub;
-      const int sub_hi = min(sub_lo + kSub, n);
-      uint32_t selmask = 0;  // lane w holds the selection mask of window w
-      int nseq = 0, first_lit = 0, rest = 0, anchor = sub_lo;
-      if (sub_lo < n) {
-        const int match_end_limit = min(sub_hi, n - kLz4LastLiterals);
-        int pos = sub_lo;
-        for (int win = 0; win < kWinPerSub; ++win) {
-          const int base = sub_lo + win * 32;
-          if (base >= sub_hi) break;
-          const uint32_t c = (base + lane < sub_hi) ? (uint32_t)S.cand[base + lane] : kNone;
-          const uint32_t m = __ballot_sync(0xffffffffu, c != kNone);
-          while (true) {
-            const int rel = pos - base;
-            if (rel >= 32) break;
-            const uint32_t mm = rel > 0 ? (m & (0xffffffffu << rel)) : m;
-            if (!mm) break;
-            const int j = __ffs(mm) - 1;
-            const int mpos = base + j;
-            const int mc = (int)__shfl_sync(0xffffffffu, c, j);
-            // cooperative extension, 128 bytes per step
-            const int maxlen = match_end_limit - mpos;   // >= 4 is not guaranteed near the sub-block end
-            int len = maxlen;
-            if (maxlen >= kLz4MinMatch) {
-              int done = 4;
-              while (done < maxlen) {
-                const int k = done + lane * 4;
-                const uint32_t x = load4(S.data, mpos + k), y = load4(S.data, mc + k);
-                const uint32_t diff = x ^ y;
-                const uint32_t bm = __ballot_sync(0xffffffffu, diff != 0);
-                if (bm) {
-                  const int f = __ffs(bm) - 1;
-                  const uint32_t d = __shfl_sync(0xffffffffu, diff, f);
-                  len = done + f * 4 + ((__ffs(d) - 1) >> 3);
-                  break;
+      // ---------------- phase B: every thread parses its own 32-byte segment greedily ----------------
+      // A match may overshoot into the following segments of the same warp; their entry point moves and
+      // they re-parse until the warp's parse is stable (lane k is final after at most k+1 rounds).
+      const int seg_lo = tid * 32;
+      const int limit = min((warp + 1) * kSub, n - kLz4LastLiterals);
+      const uint32_t M = S.segM[tid], C0 = S.segC0[tid], C1 = S.segC1[tid];
+      uint32_t Sel = 0;
+      unsigned long long lens = 0;       // lengths of the long matches of this segment, 11 bits each, in order
+      int entry = 0, exit_abs = seg_lo + 32;
+      bool need = true;
+      while (true) {                     // cascade rounds
+        int pos = entry, nlong = 0, pj = 0, plen = 0;
+        const bool parsing = need;       // lanes whose entry did not move keep the parse of an earlier round
+        bool done = !need, pend = false;
+        if (need) { Sel = 0; lens = 0; }
+        int myend = 0;                   // end of the furthest match of this lane that the warp extended this round
+        while (true) {
+          if (!done && !pend) {
+            // thread-serial parse: bit operations only; a long match gets at most 16 more bytes here
+            while (true) {
+              if (pos >= 32) { done = true; break; }
+              const uint32_t mm = M & (0xffffffffu << pos);
+              if (!mm) { done = true; break; }
+              const int j = __ffs(mm) - 1;
+              const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
+              int len = 4 + code;
+              if (code == 3) {
+                const int i = seg_lo + j, c = (int)S.cand[i], maxlen = limit - i;
+                len = 7;
+                bool open = true;
+#pragma unroll 1
+                for (int it = 0; it < 4; ++it) {
+                  if (len >= maxlen) { open = false; break; }
+                  const uint32_t x = load4(S.data, i + len) ^ load4(S.data, c + len);
+                  if (x) { len += (__ffs(x) - 1) >> 3; open = false; break; }
+                  len += 4;
                 }
-                done += 128;
+                if (len >= maxlen) { len = maxlen; open = false; }
+                if (open) { pend = true; pj = j; plen = len; break; }   // still matching: the warp finishes it
+                lens |= (unsigned long long)len << (11 * nlong);
+                nlong++;
               }
-              if (len > maxlen) len = maxlen;
-              const int lit = mpos - anchor;
-              if (nseq == 0) {
-                first_lit = lit;
-                rest += 1 + 2 + ext_bytes(len - 4);
-              } else {
-                rest += 1 + ext_bytes(lit) + lit + 2 + ext_bytes(len - 4);
+              Sel |= 1u << j;
+              pos = j + len;
+            }
+          }
+          uint32_t pm = __ballot_sync(0xffffffffu, pend);
+          if (!pm) break;                // no lane is waiting => every lane is done
+          while (pm) {
+            const int l = __ffs(pm) - 1;
+            pm &= pm - 1;
+            const int i = __shfl_sync(0xffffffffu, seg_lo + pj, l);
+            const int cover = __reduce_max_sync(0xffffffffu, lane < l ? myend : 0);
+            if (i < cover) {
+              // an earlier lane's match already swallowed this position: this lane's speculative parse is stale and
+              // will be redone after the cascade step (its entry point moves)
+              if (lane == l) { pend = false; done = true; pos = 0; Sel = 0; lens = 0; }
+              continue;
+            }
+            const int c = (int)S.cand[i], maxlen = limit - i;
+            int len = __shfl_sync(0xffffffffu, plen, l);
+            while (len < maxlen) {       // 128 bytes per step
+              const int k = len + lane * 4;
+              const uint32_t x = load4(S.data, i + k) ^ load4(S.data, c + k);
+              const uint32_t bm = __ballot_sync(0xffffffffu, x != 0);
+              if (bm) {
+                const int f = __ffs(bm) - 1;
+                const uint32_t d = __shfl_sync(0xffffffffu, x, f);
+                len += f * 4 + ((__ffs(d) - 1) >> 3);
+                break;
               }
-              if (lane == 0) {
-                S.cand[mpos] = (uint16_t)(mpos - mc);
-                S.cand[mpos + 1] = (uint16_t)len;
-              }
-              if (lane == win) selmask |= 1u << j;
-              nseq++;
-              anchor = pos = mpos + len;
-            } else {
-              pos = mpos + 1;  // too close to the sub-block end: leave as literal
+              len += 128;
+            }
+            if (len > maxlen) len = maxlen;
+            if (lane == l) {
+              lens |= (unsigned long long)len << (11 * nlong);
+              nlong++;
+              Sel |= 1u << pj;
+              pos = pj + len;
+              pend = false;
+              myend = i + len;
             }
           }
         }
+        if (parsing) exit_abs = seg_lo + (pos > 32 ? pos : 32);
+        int incl = exit_abs;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl = max(incl, t);
+        }
+        int prev = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) prev = seg_lo;
+        const int ne = min(max(prev - seg_lo, 0), 32);
+        need = ne != entry;
+        entry = ne;
+        if (!__any_sync(0xffffffffu, need)) break;
       }
-      if (lane == 0) {
-        S.sb_nseq[warp] = nseq;
-        S.sb_first_lit[warp] = first_lit;
-        S.sb_rest[warp] = rest;
-        S.sb_tail[warp] = (sub_lo < n) ? sub_hi - anchor : 0;
+
+      // ---------------- phase C: sizes, literal carries, output offsets ----------------
+      const int seg_end = max(0, min(32, n - seg_lo));   // valid positions of this segment
+      if (entry > seg_end) entry = seg_end;
+      int nm = 0, rest = 0, F = 0, p = entry;
+      {
+        uint32_t m = Sel;
+        unsigned long long q = lens;
+        while (m) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
+          int len = 4 + code;
+          if (code == 3) { len = (int)(q & 0x7FF); q >>= 11; }
+          const int lit = j - p;
+          if (nm == 0) { F = lit; rest += 3 + ext_bytes(len - 4); }
+          else rest += 3 + ext_bytes(lit) + lit + ext_bytes(len - 4);
+          nm++;
+          p = j + len;
+        }
+      }
+      const int T = p < seg_end ? seg_end - p : 0;   // trailing literals, owned by a later sequence
+      const int has = nm > 0;
+      // carry scan: f_l(x) = has ? T : x + T ; combine(a,b) = (b.has ? b.T : a.T + b.T, a.has | b.has)
+      int sT = T, sH = has;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int tT = __shfl_up_sync(0xffffffffu, sT, d), tH = __shfl_up_sync(0xffffffffu, sH, d);
+        if (lane >= d) { sT = sH ? sT : tT + sT; sH |= tH; }
+      }
+      int eT = __shfl_up_sync(0xffffffffu, sT, 1), eH = __shfl_up_sync(0xffffffffu, sH, 1);   // exclusive
+      if (lane == 0) { eT = 0; eH = 0; }
+      // next segment (after this one) that owns a match
+      int nx = has ? tid : kInf;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_down_sync(0xffffffffu, nx, d);
+        if (lane + d < 32) nx = min(nx, t);
+      }
+      int nxt = __shfl_down_sync(0xffffffffu, nx, 1);
+      if (lane == 31) nxt = kInf;
+      if (lane == 31) { S.w_T[warp] = sT; S.w_has[warp] = sH; }
+      if (lane == 0) S.w_first[warp] = nx;
+      __syncthreads();
+      if (tid == 0) {
+        int x = 0;
+        for (int w = 0; w < kWarps; ++w) { S.w_carry_in[w] = x; x = S.w_has[w] ? S.w_T[w] : x + S.w_T[w]; }
+        S.final_lit = x;
+        int nn = kInf;
+        for (int w = kWarps - 1; w >= 0; --w) { S.w_next[w] = nn; nn = min(nn, S.w_first[w]); }
       }
       __syncthreads();
-      // ---------------- combine ----------------
-      if (tid == 0) {
-        int carry = 0, off = 0;
-        for (int k = 0; k < kWarps; ++k) {
-          S.sb_carry[k] = carry;
-          S.sb_out_off[k] = off;
-          if (S.sb_nseq[k] == 0) {
-            carry += S.sb_tail[k];
-          } else {
-            const int L = carry + S.sb_first_lit[k];
-            off += ext_bytes(L) + L + S.sb_rest[k];
-            carry = S.sb_tail[k];
+      const int C = eH ? eT : S.w_carry_in[warp] + eT;   // literals carried into this segment's first sequence
+      if (nxt == kInf) nxt = S.w_next[warp];
+      const int size = has ? ext_bytes(C + F) + C + F + rest : 0;
+      int incl = size;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (lane == 31) S.w_size[warp] = incl;
+      // offsets of the selected matches, fetched before `out` starts to overwrite `cand`
+      uint32_t offs[4] = {0, 0, 0, 0};
+      {
+        uint32_t m = Sel;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const int i = seg_lo + j;
+            offs[k >> 1] |= (uint32_t)(i - (int)S.cand[i]) << (16 * (k & 1));
           }
         }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int off = 0;
+        for (int w = 0; w < kWarps; ++w) { S.w_off[w] = off; off += S.w_size[w]; }
         S.final_off = off;
-        S.final_lit = carry;
-        S.total = off + 1 + ext_bytes(carry) + carry;
+        S.total = off + 1 + ext_bytes(S.final_lit) + S.final_lit;
       }
       __syncthreads();
       csize = S.total;
       if (csize >= n) {
         stored = true;
       } else {
-        // ---------------- phase C: emission ----------------
-        if (nseq > 0) {
-          int a_run = sub_lo - S.sb_carry[warp];
-          int ooff = S.sb_out_off[warp];
-          for (int win = 0; win < kWinPerSub; ++win) {
-            const uint32_t mask = __shfl_sync(0xffffffffu, selmask, win);
-            if (!mask) continue;
-            const int base = sub_lo + win * 32;
-            const bool sel = (mask >> lane) & 1u;
-            const int mpos = base + lane;
-            const int off = sel ? (int)S.cand[mpos] : 0;
-            const int len = sel ? (int)S.cand[mpos + 1] : 0;
-            const int end = mpos + len;
-            const uint32_t prevmask = mask & ((1u << lane) - 1u);
-            const int prevlane = prevmask ? 31 - __clz(prevmask) : 0;
-            const int prev_end = __shfl_sync(0xffffffffu, end, prevlane);
-            const int a = prevmask ? prev_end : a_run;
-            const int lit = sel ? mpos - a : 0;
-            const int elit = ext_bytes(lit), elen = ext_bytes(len - 4);
-            const int size = sel ? 1 + elit + lit + 2 + elen : 0;
-            int incl = size;
+        // ---------------- phase D: emission ----------------
+        const int final_litbase = S.final_off + 1 + ext_bytes(S.final_lit) - (n - S.final_lit);
+        if (has) {
+          int o = S.w_off[warp] + incl - size;
+          uint32_t m = Sel;
+          unsigned long long q = lens;
+          int pp = entry;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-              const int t = __shfl_up_sync(0xffffffffu, incl, d);
-              if (lane >= d) incl += t;
-            }
-            const int my_out = ooff + incl - size;
-            if (sel) {
-              uint8_t* p = out8 + my_out;
+          for (int k = 0; k < 8; ++k) {
+            if (m) {
+              const int j = __ffs(m) - 1;
+              m &= m - 1;
+              const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
+              int len = 4 + code;
+              if (code == 3) { len = (int)(q & 0x7FF); q >>= 11; }
+              const int own = j - pp;                    // literals of this sequence inside this segment
+              const int lit = k == 0 ? C + own : own;
+              const int el = ext_bytes(lit);
               const int ml = len - 4;
-              p[0] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (ml < 15 ? ml : 15));
-              if (lit >= 15) put_ext(p + 1, lit);
-              uint8_t* q = p + 1 + elit + lit;
-              q[0] = (uint8_t)(off & 0xff);
-              q[1] = (uint8_t)(off >> 8);
-              if (ml >= 15) put_ext(q + 2, ml);
+              out8[o] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (ml < 15 ? ml : 15));
+              if (lit >= 15) put_ext(out8 + o + 1, lit);
+              int d = o + 1 + el + (lit - own);          // where this segment's own literals go
+              if (k == 0) S.seg_litbase[tid] = o + 1 + el - (seg_lo + entry - C);
+              for (int t = 0; t < own; ++t) out8[d + t] = data8[seg_lo + pp + t];
+              d += own;
+              const uint32_t off = (offs[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+              out8[d] = (uint8_t)(off & 0xff);
+              out8[d + 1] = (uint8_t)(off >> 8);
+              if (ml >= 15) put_ext(out8 + d + 2, ml);
+              o = d + 2 + ext_bytes(ml);
+              pp = j + len;
             }
-            // literals: the whole warp copies each selected sequence's run
-            uint32_t rem = mask;
-            while (rem) {
-              const int j = __ffs(rem) - 1;
-              rem &= rem - 1;
-              const int la = __shfl_sync(0xffffffffu, a, j);
-              const int ll = __shfl_sync(0xffffffffu, lit, j);
-              const int lo = __shfl_sync(0xffffffffu, my_out, j) + 1 + ext_bytes(ll);
-              for (int k = lane; k < ll; k += 32) out8[lo + k] = data8[la + k];
-            }
-            const int last = 31 - __clz(mask);
-            a_run = __shfl_sync(0xffffffffu, end, last);
-            ooff += __shfl_sync(0xffffffffu, incl, 31);
           }
         }
-        // final literal-only sequence
-        {
+        __syncthreads();
+        // trailing literals belong to the next sequence (or to the block's final literal run)
+        if (T > 0) {
+          const int lb = nxt == kInf ? final_litbase : S.seg_litbase[nxt];
+          for (int t = 0; t < T; ++t) out8[lb + seg_lo + p + t] = data8[seg_lo + p + t];
+        }
+        if (tid == 0) {
           const int L = S.final_lit;
-          uint8_t* p = out8 + S.final_off;
-          const int e = ext_bytes(L);
-          if (tid == 0) {
-            p[0] = (uint8_t)((L < 15 ? L : 15) << 4);
-            if (L >= 15) put_ext(p + 1, L);
-          }
-          for (int k = tid; k < L; k += kThreads) p[1 + e + k] = data8[n - L + k];
+          uint8_t* fp = out8 + S.final_off;
+          fp[0] = (uint8_t)((L < 15 ? L : 15) << 4);
+          if (L >= 15) put_ext(fp + 1, L);
         }
       }
     }
