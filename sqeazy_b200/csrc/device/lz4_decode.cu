@@ -342,16 +342,18 @@ __device__ __forceinline__ uint32_t decode_block_warp(const uint8_t* __restrict_
 constexpr int kDecThreads = 128;
 
 // ------------------------------------------------------------------------------------------------
-// shared-memory path: independent blocks of at most 16 KiB (everything this library writes)
+// windowed block decoder: a warp per block of ANY size, independent or linked.
+// The last kWin output bytes live in a shared-memory ring (match sources with offset <= kWin-64 — the
+// overwhelming majority — never leave the SM); the ring is flushed to global memory in 512-byte chunks of
+// 16-byte stores as soon as a chunk is complete. Matches that reach further back (or, in a linked frame, in
+// front of the block) read the already flushed bytes with L1-bypassing loads. 3 KiB of shared memory per warp
+// keeps 48 blocks in flight per SM instead of the 13 a whole 16 KiB block per warp would allow.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kSmallBlock = kLz4BlockBytes;
-constexpr uint32_t kRing = 1024;  // two 512-byte chunks of the compressed stream per warp
-constexpr int kSmallWarps = 4;
-constexpr size_t kSmallWarpSmem = kSmallBlock + 64 + kRing;
-
-__device__ __forceinline__ bool small_block_eligible(uint32_t word, uint32_t dsize, uint32_t link) {
-  return link == kNoLink && dsize <= kSmallBlock && dsize > 0 && (word & 0x7FFFFFFFu) <= kSmallBlock + 64;
-}
+constexpr uint32_t kWin = 2048;   // output ring bytes per warp
+constexpr uint32_t kRing = 1024;  // compressed-stream ring per warp (two 512-byte chunks)
+constexpr int kWinWarps = 8;
+constexpr size_t kWinWarpSmem = kWin + kRing;
+constexpr uint32_t kNear = kWin - 64;
 
 __device__ __forceinline__ uint4 load_stream_piece(const uint8_t* addr, const uint8_t* sbeg, const uint8_t* send) {
   if (addr >= sbeg && addr + 16 <= send) return __ldg(reinterpret_cast<const uint4*>(addr));
@@ -363,11 +365,37 @@ __device__ __forceinline__ uint4 load_stream_piece(const uint8_t* addr, const ui
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Decodes one block into out8 (shared memory). The compressed stream is windowed through a 1 KiB ring
-// (chunk c of the 16-byte aligned stream lives in ring half c & 1; chunk cur+2 waits in registers).
-__device__ __forceinline__ uint32_t decode_block_smem(const uint8_t* __restrict__ s, uint32_t csize, uint8_t* out8, uint32_t dcap,
-                                                      uint8_t* ring8, const uint8_t* sbeg, const uint8_t* send, uint32_t& err,
-                                                      int lane) {
+struct WinOut {
+  uint8_t* win;        // shared ring
+  uint8_t* d;          // block's output in global memory
+  uint32_t flushed;    // bytes of this block already written to global (multiple of 512 until the end)
+  bool aligned;        // d is 16-byte aligned
+  int lane;
+  // writes every complete 512-byte chunk below `op` to global memory
+  __device__ __forceinline__ void flush_to(uint32_t op) {
+    while (op - flushed >= 512u) {
+      __syncwarp();
+      if (aligned) {
+        const uint4 v = *reinterpret_cast<const uint4*>(win + ((flushed + 16u * lane) & (kWin - 1)));
+        st_stream(reinterpret_cast<uint4*>(d + flushed) + lane, v);
+      } else {
+        for (uint32_t k = lane; k < 512u; k += 32) d[flushed + k] = win[(flushed + k) & (kWin - 1)];
+      }
+      flushed += 512u;
+    }
+  }
+  __device__ __forceinline__ void finish(uint32_t op) {
+    __syncwarp();
+    for (uint32_t k = flushed + lane; k < op; k += 32) d[k] = win[k & (kWin - 1)];
+    flushed = op;
+  }
+};
+
+// returns decoded size; err set on malformed input
+__device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restrict__ s, uint32_t csize, WinOut& O, uint32_t dcap,
+                                                        uint8_t* ring8, const uint8_t* sbeg, const uint8_t* send,
+                                                        unsigned long long before, uint32_t link, const uint32_t* done,
+                                                        bool& waited, uint32_t& err, int lane) {
   const uint8_t* A = reinterpret_cast<const uint8_t*>((uintptr_t)s & ~(uintptr_t)15);
   const uint32_t shift = (uint32_t)(s - A);
   uint4* ring4 = reinterpret_cast<uint4*>(ring8);
@@ -392,6 +420,7 @@ __device__ __forceinline__ uint32_t decode_block_smem(const uint8_t* __restrict_
     __syncwarp();
   };
 #define SQYB_RB(pos) ((uint32_t)ring8[(pos) & (kRing - 1)])
+#define SQYB_W(pos) O.win[(pos) & (kWin - 1)]
   uint32_t ip = shift, op = 0;
   const uint32_t end = shift + csize;
   uint32_t token = SQYB_RB(ip);
@@ -403,6 +432,7 @@ __device__ __forceinline__ uint32_t decode_block_smem(const uint8_t* __restrict_
       uint32_t b;
       do {
         if (ip >= end) { err = kErrBadBlock; return op; }
+        ensure(ip);   // 256 KiB blocks can carry > 1000 length bytes
         b = SQYB_RB(ip);
         ip++;
         lit += b;
@@ -411,14 +441,19 @@ __device__ __forceinline__ uint32_t decode_block_smem(const uint8_t* __restrict_
     if (lit) {
       if (ip + lit > end || op + lit > dcap) { err = kErrBadBlock; return op; }
       if (lit <= 32) {
-        if ((uint32_t)lane < lit) out8[op + lane] = (uint8_t)SQYB_RB(ip + lane);
-      } else if (ip + lit <= (cur + 2) * 512u) {
-        for (uint32_t k = lane; k < lit; k += 32) out8[op + k] = (uint8_t)SQYB_RB(ip + k);
+        if ((uint32_t)lane < lit) SQYB_W(op + lane) = (uint8_t)SQYB_RB(ip + lane);
+        op += lit;
       } else {
-        for (uint32_t k = lane; k < lit; k += 32) out8[op + k] = __ldg(A + ip + k);
+        const bool in_ring = ip + lit <= (cur + 2) * 512u;
+        for (uint32_t kb = 0; kb < lit; kb += 32) {
+          const uint32_t k = kb + lane;
+          if (k < lit) SQYB_W(op + k) = in_ring ? (uint8_t)SQYB_RB(ip + k) : __ldg(A + ip + k);
+          const uint32_t step = lit - kb < 32u ? lit - kb : 32u;
+          O.flush_to(op + kb + step);
+        }
+        op += lit;
       }
       ip += lit;
-      op += lit;
     }
     if (ip >= end) break;
     ensure(ip);
@@ -430,88 +465,78 @@ __device__ __forceinline__ uint32_t decode_block_smem(const uint8_t* __restrict_
       uint32_t b;
       do {
         if (ip >= end) { err = kErrBadBlock; return op; }
+        ensure(ip);
         b = SQYB_RB(ip);
         ip++;
         mlen += b;
       } while (b == 255);
     }
     mlen += 4;
-    if (offset == 0 || offset > op || op + mlen > dcap) { err = kErrBadBlock; return op; }
+    if (offset == 0 || op + mlen > dcap) { err = kErrBadBlock; return op; }
     token = SQYB_RB(ip);  // next token: chunk cur+1 is always resident, so this read is safe before ensure()
+    if (offset > op) {
+      // reaches in front of this block: only legal inside a linked frame, after the predecessor is complete
+      if (link == kNoLink || (unsigned long long)(offset - op) > before) { err = kErrBadBlock; return op; }
+      if (!waited) {
+        if (lane == 0) {
+          while (atomicAdd(const_cast<uint32_t*>(done) + link, 0u) == 0u) __nanosleep(100);
+          __threadfence();
+        }
+        waited = true;
+      }
+    }
     __syncwarp();
-    uint8_t* o = out8 + op;
-    if (mlen <= 32 && offset >= mlen) {
-      if ((uint32_t)lane < mlen) o[lane] = o[(int)lane - (int)offset];
-    } else if (offset >= 32) {
-      const bool overlap = mlen > offset;
+    if (offset <= kNear && offset <= op) {
+      // ---- source inside the ring ----
+      if (mlen <= 32 && offset >= mlen) {
+        if ((uint32_t)lane < mlen) SQYB_W(op + lane) = SQYB_W(op + lane - offset);
+        op += mlen;
+      } else if (offset >= 32) {
+        for (uint32_t kb = 0; kb < mlen; kb += 32) {
+          const uint32_t k = kb + lane;
+          if (k < mlen) SQYB_W(op + k) = SQYB_W(op + k - offset);
+          const uint32_t step = mlen - kb < 32u ? mlen - kb : 32u;
+          O.flush_to(op + kb + step);   // contains the __syncwarp that orders overlapping steps
+          __syncwarp();
+        }
+        op += mlen;
+      } else {
+        // short period: the pattern [op-offset, op) repeats; every byte's source lies in front of the match
+        const uint32_t base = op - offset;
+        for (uint32_t kb = 0; kb < mlen; kb += 32) {
+          const uint32_t k = kb + lane;
+          if (k < mlen) SQYB_W(op + k) = SQYB_W(base + (offset == 1 ? 0u : k % offset));
+          const uint32_t step = mlen - kb < 32u ? mlen - kb : 32u;
+          O.flush_to(op + kb + step);
+        }
+        op += mlen;
+      }
+    } else {
+      // ---- far source (already flushed) or bytes in front of a linked block: L1-bypassing global loads ----
+      O.flush_to(op);   // make sure everything up to the last complete chunk is in global memory
       for (uint32_t kb = 0; kb < mlen; kb += 32) {
         const uint32_t k = kb + lane;
-        if (k < mlen) o[k] = o[(int)k - (int)offset];
-        if (overlap) __syncwarp();
+        if (k < mlen) {
+          // may be negative in a linked frame; a short period (only possible when the match starts in front of
+          // the block) repeats the pattern [op-offset, op) so that no lane reads a byte written in this step
+          const long long sp = (long long)op - offset + (offset < 32u ? k % offset : k);
+          uint8_t v;
+          if (sp >= (long long)O.flushed) v = SQYB_W((uint32_t)sp);   // unflushed tail (overlapping far match)
+          else v = __ldcg(O.d + sp);
+          SQYB_W(op + k) = v;
+        }
+        const uint32_t step = mlen - kb < 32u ? mlen - kb : 32u;
+        O.flush_to(op + kb + step);
+        __syncwarp();
       }
-    } else if (offset == 1 && mlen >= 64) {
-      // run fill: byte head to a 4-byte boundary, 32-bit body, byte tail
-      const uint32_t v = o[-1];
-      const uint32_t head = (4u - ((uint32_t)(uintptr_t)o & 3u)) & 3u;
-      if ((uint32_t)lane < head) o[lane] = (uint8_t)v;
-      const uint32_t body = (mlen - head) >> 2;
-      uint32_t* o4 = reinterpret_cast<uint32_t*>(o + head);
-      const uint32_t v4 = v * 0x01010101u;
-      for (uint32_t k = lane; k < body; k += 32) o4[k] = v4;
-      const uint32_t done = head + (body << 2);
-      if ((uint32_t)lane < mlen - done) o[done + lane] = (uint8_t)v;
-    } else {
-      const uint8_t* base = o - offset;
-      for (uint32_t k = lane; k < mlen; k += 32) o[k] = base[k % offset];
+      op += mlen;
     }
     __syncwarp();
-    op += mlen;
+    O.flush_to(op);
   }
 #undef SQYB_RB
+#undef SQYB_W
   return op;
-}
-
-__global__ void __launch_bounds__(kSmallWarps * 32) lz4_decode_small_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
-                                                                           uint8_t* __restrict__ dst, DecCtl* ctl, DecTables T) {
-  extern __shared__ __align__(16) unsigned char dsm[];
-  if (ctl->error || ctl->n_small == 0) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t* out8 = dsm + (size_t)warp * kSmallWarpSmem;
-  uint8_t* ring8 = out8 + kSmallBlock + 64;
-  const uint32_t nblocks = ctl->nblocks;
-  while (true) {
-    uint32_t b = 0;
-    if (lane == 0) b = atomicAdd(&ctl->ticket_small, 1u);
-    b = __shfl_sync(0xffffffffu, b, 0);
-    if (b >= nblocks) return;
-    const uint32_t word = T.word[b];
-    const uint32_t csize = word & 0x7FFFFFFFu;
-    const uint32_t dsize = T.dsize[b];
-    if (!small_block_eligible(word, dsize, T.link[b])) continue;
-    const uint8_t* s = src + T.src_off[b];
-    uint8_t* d = dst + T.dst_off[b];
-    uint32_t err = 0;
-    if (word & kLz4StoredFlag) {
-      if (csize != dsize) err = kErrSizeMismatch;
-      else warp_copy_from_stream(d, s, csize, lane);
-    } else {
-      const uint32_t got = decode_block_smem(s, csize, out8, dsize, ring8, src, src + src_bytes, err, lane);
-      if (!err && got != dsize) err = kErrSizeMismatch;
-      __syncwarp();
-      if (!err) {
-        if ((((uintptr_t)d) & 15) == 0) {
-          const uint4* o4 = reinterpret_cast<const uint4*>(out8);
-          const uint32_t nv = dsize >> 4;
-          for (uint32_t v = lane; v < nv; v += 32) st_stream(reinterpret_cast<uint4*>(d) + v, o4[v]);
-          for (uint32_t k = (nv << 4) + lane; k < dsize; k += 32) d[k] = out8[k];
-        } else {
-          for (uint32_t k = lane; k < dsize; k += 32) d[k] = out8[k];
-        }
-      }
-      __syncwarp();
-    }
-    if (err && lane == 0) atomicMax(&ctl->error, err);
-  }
 }
 
 // measures the decoded size of the blocks the directory could not infer
@@ -562,8 +587,7 @@ __global__ void __launch_bounds__(kDirThreads) lz4_offsets_kernel(DecCtl* ctl, D
         T.dst_off[i] = off;
         T.done[i] = 0;
         off += d[k];
-        if (small_block_eligible(T.word[i], d[k], T.link[i])) n_small++;
-        else n_generic++;
+        n_generic++;
       }
     }
     running += total;
@@ -578,10 +602,13 @@ __global__ void __launch_bounds__(kDirThreads) lz4_offsets_kernel(DecCtl* ctl, D
   }
 }
 
-__global__ void __launch_bounds__(kDecThreads) lz4_decode_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                                 DecCtl* ctl, DecTables T) {
-  if (ctl->error || ctl->n_generic == 0) return;
-  const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(kWinWarps * 32, 6) lz4_decode_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
+                                                                        uint8_t* __restrict__ dst, DecCtl* ctl, DecTables T) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  if (ctl->error) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* win = dsm + (size_t)warp * kWinWarpSmem;
+  uint8_t* ring8 = win + kWin;
   const uint32_t nblocks = ctl->nblocks;
   while (true) {
     uint32_t b = 0;
@@ -593,7 +620,6 @@ __global__ void __launch_bounds__(kDecThreads) lz4_decode_kernel(const uint8_t* 
     const uint32_t dsize = T.dsize[b];
     const unsigned long long doff = T.dst_off[b];
     const uint32_t link = T.link[b];
-    if (small_block_eligible(word, dsize, link)) continue;  // taken by lz4_decode_small_kernel
     const uint8_t* s = src + T.src_off[b];
     uint8_t* d = dst + doff;
     bool waited = false;
@@ -602,9 +628,15 @@ __global__ void __launch_bounds__(kDecThreads) lz4_decode_kernel(const uint8_t* 
       if (csize != dsize) err = kErrSizeMismatch;
       else warp_copy_from_stream(d, s, csize, lane);
     } else {
-      // bytes of the same linked frame in front of this block (at most the 64 KiB window matters)
+      WinOut O;
+      O.win = win;
+      O.d = d;
+      O.flushed = 0;
+      O.aligned = (((uintptr_t)d) & 15) == 0;
+      O.lane = lane;
       const unsigned long long before = link != kNoLink ? doff : 0ull;
-      const uint32_t got = decode_block_warp<false>(s, csize, d, dsize, before, link, T.done, waited, err, lane);
+      const uint32_t got = decode_block_window(s, csize, O, dsize, ring8, src, src + src_bytes, before, link, T.done, waited, err, lane);
+      if (!err) O.finish(got);
       if (!err && got != dsize) err = kErrSizeMismatch;
     }
     if (err && lane == 0) atomicMax(&ctl->error, err);
@@ -617,6 +649,7 @@ __global__ void __launch_bounds__(kDecThreads) lz4_decode_kernel(const uint8_t* 
       __threadfence();
       atomicExch(T.done + b, 1u);
     }
+    __syncwarp();
   }
 }
 
@@ -647,11 +680,9 @@ int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t 
   lz4_directory_kernel<<<1, kDirThreads, 0, st>>>(src, src_bytes, ctl, T, (uint32_t)cap, measure_all);
   lz4_sizes_kernel<<<kNumSMs * 4, kDecThreads, 0, st>>>(src, ctl, T);
   lz4_offsets_kernel<<<1, kDirThreads, 0, st>>>(ctl, T, dst_bytes);
-  const size_t small_smem = kSmallWarps * kSmallWarpSmem;
-  SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_decode_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
-  lz4_decode_small_kernel<<<kNumSMs * 3, kSmallWarps * 32, small_smem, st>>>(src, src_bytes, dst, ctl, T);
-  lz4_decode_kernel<<<kNumSMs * 16, kDecThreads, 0, st>>>(src, dst, ctl, T);
-  SQYB_COUNT_LAUNCH(5);
+  const size_t win_smem = kWinWarps * kWinWarpSmem;
+  lz4_decode_kernel<<<kNumSMs * 6, kWinWarps * 32, win_smem, st>>>(src, src_bytes, dst, ctl, T);
+  SQYB_COUNT_LAUNCH(4);
   return (int)cudaGetLastError();
 }
 

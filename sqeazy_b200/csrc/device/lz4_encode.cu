@@ -229,8 +229,10 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
         else if (i >= 4 && v == lo) { found = i - 4; x = v2 ^ v; }
         else if (i >= 3 && v == ((lo >> 8) | (v << 24))) { found = i - 3; x = v2 ^ ((v >> 8) | (v2 << 24)); }
         else {
+          // the table is read and written without a barrier in between: an entry may already belong to this round
+          // (any earlier position with the same 4 bytes is a valid source; c < i and the compare make it safe)
           const uint32_t c = S.htab[h];
-          if (c != kNone && load4(S.data, (int)c) == v) { found = c; x = v2 ^ load4(S.data, (int)c + 4); }
+          if (c < (uint32_t)i && load4(S.data, (int)c) == v) { found = c; x = v2 ^ load4(S.data, (int)c + 4); }
         }
       }
       const bool has = found != kNone;
@@ -248,9 +250,8 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
         S.segC1[seg] = C1;
       }
       nfound |= has;
-      __syncthreads();
       if (i + 4 <= n) S.htab[h] = (uint16_t)i;
-      __syncthreads();
+      __syncthreads();   // one barrier per round keeps the warps within a round of each other
     }
     const int any_found = __syncthreads_or(nfound);
 
