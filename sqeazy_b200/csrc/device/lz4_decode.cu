@@ -369,11 +369,14 @@ struct WinOut {
   uint8_t* win;        // shared ring
   uint8_t* d;          // block's output in global memory
   uint32_t flushed;    // bytes of this block already written to global (multiple of 512 until the end)
+  uint32_t dcap;       // decoded size the block table promises: nothing is ever written to global beyond it
   bool aligned;        // d is 16-byte aligned
+  bool overflow;
   int lane;
   // writes every complete 512-byte chunk below `op` to global memory
   __device__ __forceinline__ void flush_to(uint32_t op) {
     while (op - flushed >= 512u) {
+      if (flushed + 512u > dcap) { overflow = true; return; }
       __syncwarp();
       if (aligned) {
         const uint4 v = *reinterpret_cast<const uint4*>(win + ((flushed + 16u * lane) & (kWin - 1)));
@@ -386,13 +389,16 @@ struct WinOut {
   }
   __device__ __forceinline__ void finish(uint32_t op) {
     __syncwarp();
+    if (op > dcap) { overflow = true; return; }
     for (uint32_t k = flushed + lane; k < op; k += 32) d[k] = win[k & (kWin - 1)];
     flushed = op;
   }
 };
 
-// returns decoded size; err set on malformed input
-__device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restrict__ s, uint32_t csize, WinOut& O, uint32_t dcap,
+// returns decoded size; err set on malformed input. Shared-memory accesses are masked into their rings and
+// global writes are fenced by WinOut::dcap, so a corrupt stream can produce garbage but never an out-of-bounds
+// access; the per-sequence work therefore carries no bounds branches, only a sticky `bad` flag.
+__device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restrict__ s, uint32_t csize, WinOut& O,
                                                         uint8_t* ring8, const uint8_t* sbeg, const uint8_t* send,
                                                         unsigned long long before, uint32_t link, const uint32_t* done,
                                                         bool& waited, uint32_t& err, int lane) {
@@ -424,6 +430,7 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
   uint32_t ip = shift, op = 0;
   const uint32_t end = shift + csize;
   uint32_t token = SQYB_RB(ip);
+  bool bad = false;
   while (ip < end) {
     ensure(ip);
     ip++;
@@ -439,11 +446,10 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
       } while (b == 255);
     }
     if (lit) {
-      if (ip + lit > end || op + lit > dcap) { err = kErrBadBlock; return op; }
       if (lit <= 32) {
         if ((uint32_t)lane < lit) SQYB_W(op + lane) = (uint8_t)SQYB_RB(ip + lane);
-        op += lit;
       } else {
+        if (ip + lit > end || op + lit > O.dcap) { err = kErrBadBlock; return op; }
         const bool in_ring = ip + lit <= (cur + 2) * 512u;
         for (uint32_t kb = 0; kb < lit; kb += 32) {
           const uint32_t k = kb + lane;
@@ -451,13 +457,12 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
           const uint32_t step = lit - kb < 32u ? lit - kb : 32u;
           O.flush_to(op + kb + step);
         }
-        op += lit;
       }
+      op += lit;
       ip += lit;
     }
     if (ip >= end) break;
     ensure(ip);
-    if (ip + 2 > end) { err = kErrBadBlock; return op; }
     const uint32_t offset = SQYB_RB(ip) | (SQYB_RB(ip + 1) << 8);
     ip += 2;
     uint32_t mlen = token & 15u;
@@ -472,7 +477,7 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
       } while (b == 255);
     }
     mlen += 4;
-    if (offset == 0 || op + mlen > dcap) { err = kErrBadBlock; return op; }
+    bad |= offset == 0;
     token = SQYB_RB(ip);  // next token: chunk cur+1 is always resident, so this read is safe before ensure()
     if (offset > op) {
       // reaches in front of this block: only legal inside a linked frame, after the predecessor is complete
@@ -490,26 +495,43 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
       // ---- source inside the ring ----
       if (mlen <= 32 && offset >= mlen) {
         if ((uint32_t)lane < mlen) SQYB_W(op + lane) = SQYB_W(op + lane - offset);
-        op += mlen;
       } else if (offset >= 32) {
         for (uint32_t kb = 0; kb < mlen; kb += 32) {
           const uint32_t k = kb + lane;
           if (k < mlen) SQYB_W(op + k) = SQYB_W(op + k - offset);
           const uint32_t step = mlen - kb < 32u ? mlen - kb : 32u;
-          O.flush_to(op + kb + step);   // contains the __syncwarp that orders overlapping steps
-          __syncwarp();
+          O.flush_to(op + kb + step);
+          __syncwarp();                 // orders overlapping steps
         }
-        op += mlen;
+      } else if (mlen >= 48 && (offset == 1 || offset == 2 || offset == 4)) {
+        // run fill: for a period dividing 4 every 4-byte aligned output word holds the same value
+        const uint32_t al = (op + 3u) & ~3u;          // first aligned output position
+        uint32_t word = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) word |= (uint32_t)SQYB_W(op - offset + ((al - op + j) % offset)) << (8 * j);
+        const uint32_t head = al - op;                // < 4 <= mlen
+        if ((uint32_t)lane < head) SQYB_W(op + lane) = SQYB_W(op - offset + lane % offset);
+        const uint32_t body = (mlen - head) >> 2;     // whole words
+        for (uint32_t wb = 0; wb < body; wb += 32) {
+          const uint32_t w = wb + lane;
+          if (w < body) *reinterpret_cast<uint32_t*>(O.win + ((al + 4u * w) & (kWin - 1))) = word;
+          const uint32_t stepw = body - wb < 32u ? body - wb : 32u;
+          O.flush_to(al + 4u * (wb + stepw));
+        }
+        const uint32_t donew = head + (body << 2);
+        if ((uint32_t)lane < mlen - donew) {
+          const uint32_t k = donew + lane;
+          SQYB_W(op + k) = (uint8_t)(word >> (8 * (k - head & 3u)));
+        }
       } else {
         // short period: the pattern [op-offset, op) repeats; every byte's source lies in front of the match
         const uint32_t base = op - offset;
         for (uint32_t kb = 0; kb < mlen; kb += 32) {
           const uint32_t k = kb + lane;
-          if (k < mlen) SQYB_W(op + k) = SQYB_W(base + (offset == 1 ? 0u : k % offset));
+          if (k < mlen) SQYB_W(op + k) = SQYB_W(base + k % offset);
           const uint32_t step = mlen - kb < 32u ? mlen - kb : 32u;
           O.flush_to(op + kb + step);
         }
-        op += mlen;
       }
     } else {
       // ---- far source (already flushed) or bytes in front of a linked block: L1-bypassing global loads ----
@@ -521,7 +543,7 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
           // the block) repeats the pattern [op-offset, op) so that no lane reads a byte written in this step
           const long long sp = (long long)op - offset + (offset < 32u ? k % offset : k);
           uint8_t v;
-          if (sp >= (long long)O.flushed) v = SQYB_W((uint32_t)sp);   // unflushed tail (overlapping far match)
+          if (sp >= (long long)O.flushed) v = SQYB_W((uint32_t)sp);   // unflushed tail
           else v = __ldcg(O.d + sp);
           SQYB_W(op + k) = v;
         }
@@ -529,13 +551,15 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
         O.flush_to(op + kb + step);
         __syncwarp();
       }
-      op += mlen;
     }
+    op += mlen;
     __syncwarp();
     O.flush_to(op);
+    if (O.overflow) { err = kErrBadBlock; return op; }
   }
 #undef SQYB_RB
 #undef SQYB_W
+  if (bad || ip != end) err = kErrBadBlock;
   return op;
 }
 
@@ -632,12 +656,14 @@ __global__ void __launch_bounds__(kWinWarps * 32, 6) lz4_decode_kernel(const uin
       O.win = win;
       O.d = d;
       O.flushed = 0;
+      O.dcap = dsize;
       O.aligned = (((uintptr_t)d) & 15) == 0;
+      O.overflow = false;
       O.lane = lane;
       const unsigned long long before = link != kNoLink ? doff : 0ull;
-      const uint32_t got = decode_block_window(s, csize, O, dsize, ring8, src, src + src_bytes, before, link, T.done, waited, err, lane);
+      const uint32_t got = decode_block_window(s, csize, O, ring8, src, src + src_bytes, before, link, T.done, waited, err, lane);
       if (!err) O.finish(got);
-      if (!err && got != dsize) err = kErrSizeMismatch;
+      if (!err && (O.overflow || got != dsize)) err = kErrSizeMismatch;
     }
     if (err && lane == 0) atomicMax(&ctl->error, err);
     // publish completion (linked frames): a block is done when it and its predecessor are done

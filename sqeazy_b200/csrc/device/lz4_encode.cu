@@ -52,8 +52,6 @@ struct __align__(16) EncSmem {
   int seg_litbase[kSegs];                // dest(p) = seg_litbase + p for the literal run that ends at the segment's first match
   int w_T[kWarps], w_has[kWarps], w_carry_in[kWarps], w_size[kWarps], w_off[kWarps], w_first[kWarps], w_next[kWarps];
   int final_off, final_lit, total;
-  uint32_t ticket;
-  unsigned long long goff;
 };
 
 __device__ __forceinline__ int ext_bytes(int v) {
@@ -125,15 +123,12 @@ __device__ __forceinline__ int extend_match(const uint32_t* data, int i, int c, 
 
 __global__ void __launch_bounds__(kThreads, 3)
 lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* __restrict__ dst, uint32_t nblocks,
-                  unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket_counter,
-                  unsigned long long* __restrict__ payload_bytes_out, uint32_t* __restrict__ stats) {
+                  uint8_t* __restrict__ staging, uint32_t* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EncSmem& S = *reinterpret_cast<EncSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  if (tid == 0) S.ticket = atomicAdd(ticket_counter, 1u);
-  __syncthreads();
-  const uint32_t b = S.ticket;
+  const uint32_t b = blockIdx.x;
   if (b >= nblocks) return;
   const uint64_t boff = (uint64_t)b * kB;
   const int n = (int)((raw_bytes - boff) < (uint64_t)kB ? (raw_bytes - boff) : (uint64_t)kB);
@@ -235,10 +230,13 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
           if (c < (uint32_t)i && load4(S.data, (int)c) == v) { found = c; x = v2 ^ load4(S.data, (int)c + 4); }
         }
       }
-      const bool has = found != kNone;
       int len = 4 + (x ? ((__ffs(x) - 1) >> 3) : 4);
       if (len > maxlen) len = maxlen;
-      const int code = len - 4 < 3 ? len - 4 : 3;   // 0,1,2: exact length 4,5,6; 3: at least 7, extended in phase B
+      // 4-byte matches save one byte and cost a sequence on both ends of the codec: dropping them keeps the ratio within
+      // ~1 % on bit planes, improves it on background-removed stacks and matches liblz4 on noisy 8-bit codes
+      // (tools/lz4_model.c), while halving the number of sequences
+      const bool has = found != kNone && len >= 5;
+      const int code = len - 5 < 3 ? len - 5 : 3;   // 0,1,2: exact length 5,6,7; 3: at least 8, extended in phase B
       S.cand[i] = (uint16_t)found;
       const uint32_t M = __ballot_sync(0xffffffffu, has);
       const uint32_t C0 = __ballot_sync(0xffffffffu, has && (code & 1));
@@ -283,10 +281,10 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
               if (!mm) { done = true; break; }
               const int j = __ffs(mm) - 1;
               const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
-              int len = 4 + code;
+              int len = 5 + code;
               if (code == 3) {
                 const int i = seg_lo + j, c = (int)S.cand[i], maxlen = limit - i;
-                len = 7;
+                len = 8;
                 bool open = true;
 #pragma unroll 1
                 for (int it = 0; it < 4; ++it) {
@@ -368,7 +366,7 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
           const int j = __ffs(m) - 1;
           m &= m - 1;
           const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
-          int len = 4 + code;
+          int len = 5 + code;
           if (code == 3) { len = (int)(q & 0x7FF); q >>= 11; }
           const int lit = j - p;
           if (nm == 0) { F = lit; rest += 3 + ext_bytes(len - 4); }
@@ -457,7 +455,7 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
               const int j = __ffs(m) - 1;
               m &= m - 1;
               const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
-              int len = 4 + code;
+              int len = 5 + code;
               if (code == 3) { len = (int)(q & 0x7FF); q >>= 11; }
               const int own = j - pp;                    // literals of this sequence inside this segment
               const int lit = k == 0 ? C + own : own;
@@ -496,57 +494,123 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
   }
   __syncthreads();
 
-  // ---------------- decoupled look-back over (4 + csize) ----------------
-  const unsigned long long mine = 4ull + (unsigned long long)csize;
-  if (warp == 0) {
-    unsigned long long excl = 0;
-    if (b == 0) {
-      if (lane == 0) st_release_u64(status + 0, kFlagPre | mine);
-    } else {
-      if (lane == 0) st_release_u64(status + b, kFlagAgg | mine);
-      long long look = (long long)b - 1;
-      while (true) {
-        const long long idx = look - lane;
-        unsigned long long st = kFlagPre;  // virtual predecessor of block 0: prefix 0
-        if (idx >= 0) {
-          st = ld_acquire_u64(status + idx);
-          while ((st >> 62) == 0) { __nanosleep(256); st = ld_acquire_u64(status + idx); }
-        }
-        const uint32_t pm = __ballot_sync(0xffffffffu, (st >> 62) == 2);
-        const int first = pm ? __ffs(pm) - 1 : 32;
-        unsigned long long contrib = lane <= first ? (st & kValMask) : 0ull;
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-        excl += contrib;
-        if (pm) break;
-        look -= 32;
-      }
-      if (lane == 0) st_release_u64(status + b, kFlagPre | (excl + mine));
-    }
-    if (lane == 0) S.goff = excl;
-  }
-  __syncthreads();
-
-  // ---------------- store ----------------
-  const unsigned long long goff = lz4_prefix_bytes(nblocks) + S.goff;
+  // ---------------- hand-off: size word + staged bytes; no CTA ever waits for another ----------------
+  // (a decoupled look-back here made fast CTAs — constant blocks — sit on their SM slot until slower predecessors had
+  //  published their sizes: 30-60 % of the kernel's stall samples, profiles/. Offsets are now a separate tiny scan and
+  //  the compressed blocks are moved once more by lz4_scatter_kernel; the extra traffic is 2x the compressed bytes.)
   const uint32_t word = stored ? ((uint32_t)n | kLz4StoredFlag) : (uint32_t)csize;
-  uint8_t* g = dst + goff;
-  if (tid < 4) g[tid] = (uint8_t)(word >> (8 * tid));
-  store_bytes(g + 4, stored ? S.data : S.out, csize, tid);
-  // index entry
+  if (!stored) {
+    uint4* st4 = reinterpret_cast<uint4*>(staging + (uint64_t)b * kB);
+    const uint4* o4 = reinterpret_cast<const uint4*>(S.out);
+    for (int v = tid; v < (csize + 15) / 16; v += kThreads) st4[v] = o4[v];
+  }
   if (tid == 0) {
-    uint8_t* ip = dst + kSkippableHeaderBytes + sizeof(SqybIndexHeader) + 4ull * b;
+    uint8_t* ip = dst + kSkippableHeaderBytes + sizeof(SqybIndexHeader) + 4ull * b;   // the block's entry in the index frame
     ip[0] = (uint8_t)word; ip[1] = (uint8_t)(word >> 8); ip[2] = (uint8_t)(word >> 16); ip[3] = (uint8_t)(word >> 24);
     if (stats) atomicAdd(stats + kind, 1u);
   }
-  if (b == nblocks - 1 && tid == 0) {
-    const unsigned long long end = goff + mine;
+}
+
+// exclusive prefix sum of (4 + block bytes) over the index words -> byte offset of every block header; one CTA
+constexpr int kScanThreads = 1024;
+constexpr int kScanPer = 8;
+__global__ void __launch_bounds__(kScanThreads) lz4_offsets_scan_kernel(uint8_t* __restrict__ dst, uint32_t nblocks,
+                                                                        unsigned long long* __restrict__ offsets,
+                                                                        unsigned long long* __restrict__ payload_bytes_out) {
+  __shared__ unsigned long long warp_sums[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint8_t* idx = dst + kSkippableHeaderBytes + sizeof(SqybIndexHeader);
+  unsigned long long running = 0;
+  for (uint32_t base = 0; base < nblocks; base += kScanThreads * kScanPer) {
+    unsigned long long sz[kScanPer], local = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) {
+      const uint32_t i = base + tid * kScanPer + k;
+      uint32_t w = 0;
+      if (i < nblocks) {
+        const uint8_t* p = idx + 4ull * i;
+        w = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+      }
+      sz[k] = i < nblocks ? 4ull + (w & 0x7FFFFFFFu) : 0ull;
+      local += sz[k];
+    }
+    unsigned long long v = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += t;
+    }
+    __syncthreads();
+    if (lane == 31) warp_sums[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = warp_sums[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += t;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    unsigned long long off = running + v - local + (warp > 0 ? warp_sums[warp - 1] : 0ull);
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) {
+      const uint32_t i = base + tid * kScanPer + k;
+      if (i < nblocks) offsets[i] = off;
+      off += sz[k];
+    }
+    running += warp_sums[31];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const unsigned long long end = lz4_prefix_bytes(nblocks) + running;
     for (int k = 0; k < 4; ++k) dst[end + k] = 0;  // EndMark
     *payload_bytes_out = end + 4;
-    // frame_bytes field of the index header
     const unsigned long long frame_bytes = end + 4 - (lz4_prefix_bytes(nblocks) - kLz4FrameHeaderBytes);
-    uint8_t* fp = dst + kSkippableHeaderBytes + 24;
+    uint8_t* fp = dst + kSkippableHeaderBytes + 24;   // SqybIndexHeader::frame_bytes
     for (int k = 0; k < 8; ++k) fp[k] = (uint8_t)(frame_bytes >> (8 * k));
+  }
+}
+
+// moves every block to its final place in the frame: header word + bytes (staged compressed bytes, or the raw input
+// for stored blocks). A warp per block; 16-byte stores, source words funnel-shifted to the destination's alignment.
+__global__ void __launch_bounds__(256) lz4_scatter_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes,
+                                                          const uint8_t* __restrict__ staging, uint8_t* __restrict__ dst,
+                                                          uint32_t nblocks, const unsigned long long* __restrict__ offsets) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t wpb = blockDim.x >> 5;
+  const uint8_t* idx = dst + kSkippableHeaderBytes + sizeof(SqybIndexHeader);
+  const unsigned long long first = lz4_prefix_bytes(nblocks);
+  for (uint32_t b = blockIdx.x * wpb + (threadIdx.x >> 5); b < nblocks; b += gridDim.x * wpb) {
+    const uint8_t* p = idx + 4ull * b;
+    const uint32_t word = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    const uint32_t nbytes = word & 0x7FFFFFFFu;
+    const uint8_t* from = (word & kLz4StoredFlag) ? src + (uint64_t)b * kB : staging + (uint64_t)b * kB;
+    uint8_t* g = dst + first + offsets[b];
+    if (lane < 4) g[lane] = (uint8_t)(word >> (8 * lane));
+    g += 4;
+    uint32_t head = (uint32_t)((16 - ((uintptr_t)g & 15)) & 15);
+    if (head > nbytes) head = nbytes;
+    if ((uint32_t)lane < head) g[lane] = __ldg(from + lane);
+    const uint8_t* f = from + head;
+    uint8_t* o = g + head;
+    const uint32_t rest = nbytes - head;
+    uint32_t nvec = rest >= 24 ? (rest - 8) >> 4 : 0;   // keeps the 5-word read inside the block's bytes
+    const uint32_t sh = ((uintptr_t)f & 3) * 8;
+    const uint32_t* fw = reinterpret_cast<const uint32_t*>((uintptr_t)f & ~(uintptr_t)3);
+    if (reinterpret_cast<const uint8_t*>(fw) < from) nvec = 0;   // never read in front of the block's first byte
+    for (uint32_t v = lane; v < nvec; v += 32) {
+      const uint32_t* q = fw + v * 4;
+      const uint32_t x0 = __ldg(q), x1 = __ldg(q + 1), x2 = __ldg(q + 2), x3 = __ldg(q + 3), x4 = __ldg(q + 4);
+      uint4 val;
+      val.x = __funnelshift_r(x0, x1, sh);
+      val.y = __funnelshift_r(x1, x2, sh);
+      val.z = __funnelshift_r(x2, x3, sh);
+      val.w = __funnelshift_r(x3, x4, sh);
+      reinterpret_cast<uint4*>(o)[v] = val;
+    }
+    for (uint32_t k = (nvec << 4) + lane; k < rest; k += 32) o[k] = __ldg(f + k);
   }
 }
 
@@ -578,24 +642,30 @@ __global__ void lz4_write_prefix_kernel(uint8_t* dst, uint64_t raw_bytes, uint32
 }  // namespace
 
 size_t k_lz4_encode_workspace_bytes(uint64_t raw_bytes) {
-  return 64 + 8 * lz4_nblocks(raw_bytes) + 64;
+  const uint64_t nb = lz4_nblocks(raw_bytes);
+  return 256 + 8 * nb + 256 + nb * (uint64_t)kB + 256;   // control | block offsets | staging (one slot per block)
 }
 
-// workspace layout: [0,8) payload bytes (u64) | [8,12) ticket | [16,32) stats | [64, ...) status[nblocks]
+// workspace layout: [0,8) payload bytes (u64) | [16,28) block-kind counters | [256, 256+8*nblocks) offsets | staging
 int k_lz4_encode(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, cudaStream_t st) {
   const uint64_t nb64 = lz4_nblocks(raw_bytes);
   if (nb64 > 0xFFFFFFF0ull) return -2;
   const uint32_t nblocks = (uint32_t)nb64;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  SQYB_CUDA_OK(cudaMemsetAsync(ws, 0, 64 + 8ull * nblocks, st));
+  SQYB_CUDA_OK(cudaMemsetAsync(ws, 0, 64, st));
   unsigned long long* payload = reinterpret_cast<unsigned long long*>(ws);
+  unsigned long long* offsets = reinterpret_cast<unsigned long long*>(ws + 256);
+  uint8_t* staging = ws + ((256 + 8ull * nblocks + 255) & ~255ull);
   lz4_write_prefix_kernel<<<1, 32, 0, st>>>(dst, raw_bytes, nblocks, payload);
-  SQYB_COUNT_LAUNCH(nblocks ? 2 : 1);
+  SQYB_COUNT_LAUNCH(1);
   if (nblocks) {
     SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
-    lz4_encode_kernel<<<nblocks, kThreads, sizeof(EncSmem), st>>>(
-        src, raw_bytes, dst, nblocks, reinterpret_cast<unsigned long long*>(ws + 64), reinterpret_cast<uint32_t*>(ws + 8),
-        payload, reinterpret_cast<uint32_t*>(ws + 16));
+    lz4_encode_kernel<<<nblocks, kThreads, sizeof(EncSmem), st>>>(src, raw_bytes, dst, nblocks, staging,
+                                                                    reinterpret_cast<uint32_t*>(ws + 16));
+    lz4_offsets_scan_kernel<<<1, kScanThreads, 0, st>>>(dst, nblocks, offsets, payload);
+    const uint32_t scatter_blocks = (nblocks + 7) / 8 < (uint32_t)kNumSMs * 8 ? (nblocks + 7) / 8 : (uint32_t)kNumSMs * 8;
+    lz4_scatter_kernel<<<scatter_blocks, 256, 0, st>>>(src, raw_bytes, staging, dst, nblocks, offsets);
+    SQYB_COUNT_LAUNCH(3);
   }
   return (int)cudaGetLastError();
 }

@@ -74,6 +74,8 @@ static long encode_block_size(const uint8_t* d, int n, int round, int cut, int h
     int len = 4;
     while (len < maxlen && d[pos + len] == d[c + len]) len++;
     if ((mode & 4) && len < 5 && pos > anchor) { pos++; continue; } /* skip len-4 matches that need a new token */
+    if ((mode & 8) && len < 5) { pos++; continue; }                 /* minimum match length 5 */
+    if ((mode & 16) && len < 6) { pos++; continue; }                /* minimum match length 6 */
     int lit = pos - anchor;
     out += 1 + ext_bytes(lit) + lit + 2 + ext_bytes(len - 4);
     nseq++;

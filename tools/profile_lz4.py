@@ -11,7 +11,20 @@ torch.cuda.set_device(0)
 sq.set_device(0)
 vol = torch_volume(shape, "scmos")
 planes = torch.empty_like(vol)
-sq.bitswap_encode_device(1, vol.view(-1), planes.view(-1))
+thr = 0
+if len(sys.argv) > 3 and sys.argv[3] == "rmest":
+    _, thr = sq.estimate_background_device(vol)
+if len(sys.argv) > 3 and sys.argv[3] == "quant":
+    import numpy as np
+    hist = torch.zeros(65536, dtype=torch.int32, device="cuda")
+    sq.histogram_device(vol, hist)
+    torch.cuda.synchronize()
+    enc, dec = sq.quantiser_luts(hist.cpu().numpy().view(np.uint32))
+    planes = torch.empty(vol.numel(), dtype=torch.uint8, device="cuda")
+    sq.lut_apply_device(vol, planes, enc)
+    vol = planes
+else:
+    sq.bitswap_encode_device(1, vol.view(-1), planes.view(-1), threshold=thr)
 out = torch.empty_like(vol)
 payload = None
 for _ in range(reps):
