@@ -648,7 +648,29 @@ __global__ void __launch_bounds__(kWinWarps * 32, 6) lz4_decode_kernel(const uin
     uint8_t* d = dst + doff;
     bool waited = false;
     uint32_t err = 0;
-    if (word & kLz4StoredFlag) {
+    // closed-form run block (what the encoder emits for an all-equal block): token 0x1F, byte, offset 1, length
+    // bytes, token 0x50, five bytes -> a 16-byte-store fill, no ring traffic
+    bool filled = false;
+    if (!(word & kLz4StoredFlag) && csize >= 12 && csize <= 96 && dsize >= 64 && link == kNoLink && (((uintptr_t)d) & 15) == 0) {
+      const uint32_t t0 = __ldg(s), v = __ldg(s + 1), o0 = __ldg(s + 2), o1 = __ldg(s + 3);
+      if (t0 == 0x1Fu && o0 == 1u && o1 == 0u) {
+        uint32_t ip = 4, mlen = 15 + 4, b;
+        do { b = ip < csize ? __ldg(s + ip) : 0u; ip++; mlen += b; } while (b == 255u && ip < csize);
+        bool ok = ip + 6 == csize && 1u + mlen + 5u == dsize && __ldg(s + ip) == 0x50u;
+        for (uint32_t k = 0; ok && k < 5; ++k) ok = __ldg(s + ip + 1 + k) == v;
+        if (ok) {
+          const uint32_t v4 = v * 0x01010101u;
+          const uint4 fill = make_uint4(v4, v4, v4, v4);
+          const uint32_t nv = dsize >> 4;
+          for (uint32_t q = lane; q < nv; q += 32) st_stream(reinterpret_cast<uint4*>(d) + q, fill);
+          for (uint32_t k = (nv << 4) + lane; k < dsize; k += 32) d[k] = (uint8_t)v;
+          filled = true;
+        }
+      }
+    }
+    if (filled) {
+      // nothing else to do
+    } else if (word & kLz4StoredFlag) {
       if (csize != dsize) err = kErrSizeMismatch;
       else warp_copy_from_stream(d, s, csize, lane);
     } else {

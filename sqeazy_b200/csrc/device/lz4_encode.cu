@@ -271,7 +271,6 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
         const bool parsing = need;       // lanes whose entry did not move keep the parse of an earlier round
         bool done = !need, pend = false;
         if (need) { Sel = 0; lens = 0; }
-        int myend = 0;                   // end of the furthest match of this lane that the warp extended this round
         while (true) {
           if (!done && !pend) {
             // thread-serial parse: bit operations only; a long match gets at most 16 more bytes here
@@ -308,13 +307,6 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
             const int l = __ffs(pm) - 1;
             pm &= pm - 1;
             const int i = __shfl_sync(0xffffffffu, seg_lo + pj, l);
-            const int cover = __reduce_max_sync(0xffffffffu, lane < l ? myend : 0);
-            if (i < cover) {
-              // an earlier lane's match already swallowed this position: this lane's speculative parse is stale and
-              // will be redone after the cascade step (its entry point moves)
-              if (lane == l) { pend = false; done = true; pos = 0; Sel = 0; lens = 0; }
-              continue;
-            }
             const int c = (int)S.cand[i], maxlen = limit - i;
             int len = __shfl_sync(0xffffffffu, plen, l);
             while (len < maxlen) {       // 128 bytes per step
@@ -336,8 +328,12 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
               Sel |= 1u << pj;
               pos = pj + len;
               pend = false;
-              myend = i + len;
             }
+            // later lanes whose pending match starts inside [i, i+len) parsed a stale speculation: drop them all at
+            // once (their entry point moves in the cascade step, so they are parsed again)
+            const bool stale = pend && lane > l && seg_lo + pj < i + len;
+            if (stale) { pend = false; done = true; pos = 0; Sel = 0; lens = 0; }
+            pm &= ~__ballot_sync(0xffffffffu, stale);
           }
         }
         if (parsing) exit_abs = seg_lo + (pos > 32 ? pos : 32);

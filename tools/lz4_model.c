@@ -30,7 +30,7 @@ static void find_candidates(const uint8_t* d, int n, int round, int hashlog, int
         else if (i >= 2 && ld4(d + i - 2) == v) found = i - 2;
         else if (i >= 4 && ld4(d + i - 4) == v) found = i - 4;
         else if (i >= 3 && ld4(d + i - 3) == v) found = i - 3;
-        else if (c >= 0 && ld4(d + c) == v) found = c;
+        else if (c >= 0 && ld4(d + c) == v && !((mode & 32) && (i & 1))) found = c;
       } else {
         if (c >= 0 && ld4(d + c) == v) found = c;
         else if (i >= 1 && ld4(d + i - 1) == v) found = i - 1;
@@ -51,7 +51,7 @@ static void find_candidates(const uint8_t* d, int n, int round, int hashlog, int
       if (i + 4 > n) continue;
       uint32_t v = ld4(d + i);
       uint32_t h = (v * 2654435761u) >> (32 - hashlog);
-      tab[h] = i; /* last writer of the round wins (GPU: racy, any) */
+      if (!((mode & 32) && (i & 1))) tab[h] = i; /* last writer of the round wins (GPU: racy, any) */
     }
   }
   free(tab);
