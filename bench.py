@@ -56,7 +56,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -87,6 +87,20 @@ class ClockSampler:
             os.remove(self.path)
         except Exception:
             pass
+        if not sm:
+            # timed region shorter than one sampling period: one immediate reading (GPU still warm), flagged as such
+            try:
+                line = subprocess.check_output(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}",
+                                                "--format=csv,noheader,nounits"], timeout=10).decode().strip()
+                p = [x.strip() for x in line.split(",")]
+                sm.append(float(p[1]))
+                mx = float(p[2])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+                out["note"] = "timed region < sampling period: sampled right after it"
+            except Exception:
+                pass
         if sm:
             sm.sort()
             # median of the upper half = clocks under load (idle samples between steps drag a plain median down)
@@ -301,8 +315,14 @@ def main():
     payload_bytes = stats["payload_bytes"]
     peak, peak_kind = measured_peak_hbm()
     achieved = (lz4_in_bytes + payload_bytes) / (stage["lz4_encode"] / 1e3) / 1e9 if stage["lz4_encode"] > 0 else 0.0
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of lz4_encode_kernel from the committed `ncu --set full` capture
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get("lz4_encode_kernel_dram_bytes_per_launch")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "lz4_encode_kernel", "achieved": achieved, "peak": peak, "peak_source": peak_kind + " copy bandwidth",
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": lz4_in_bytes + payload_bytes, "kernel_ms": stage["lz4_encode"],
                 "stage_ms": stage,
                 "stage_gbs": {"filter_bitswap_encode(4B/voxel)": (2 * raw_bytes / (stage["filter_bitswap_encode"] / 1e3) / 1e9) if stage["filter_bitswap_encode"] else None,

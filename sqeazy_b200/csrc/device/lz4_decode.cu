@@ -8,11 +8,13 @@
 //   directory : one CTA parses the stream. Our index frame -> block table by a parallel prefix sum;
 //               foreign frames -> thread 0 walks the 4-byte block headers.
 //   sizes     : only for foreign blocks whose decoded size is not implied (last block of a frame):
-//               a warp per block parses tokens without copying.
+//               a warp per block walks the tokens without copying.
 //   offsets   : one CTA prefix-sums decoded sizes into output offsets and validates the total.
-//   decode    : persistent grid, a warp per block; tokens/lengths parsed warp-uniformly, literals and
-//               matches copied 32 lanes wide; linked blocks wait on their predecessor's flag only when
-//               a match reaches in front of the block.
+//   decode    : persistent grid, a warp per block of any size. The last 2 KiB of output live in a
+//               shared-memory ring (match sources), the compressed stream in a 1 KiB ring; complete
+//               512-byte chunks are flushed with 16-byte stores. Far matches and bytes in front of a
+//               linked block are read back from global memory; linked blocks wait on their
+//               predecessor's flag only when a match reaches in front of the block.
 #include "common.cuh"
 #include "kernels.h"
 #include "lz4_format.h"
@@ -38,9 +40,7 @@ struct DecCtl {          // lives at the start of the workspace
   uint32_t ticket_size;
   uint32_t ticket_decode;
   uint32_t need_sizes;   // number of blocks whose decoded size must be measured
-  uint32_t ticket_small;
-  uint32_t n_small;      // blocks that take the shared-memory path
-  uint32_t n_generic;    // blocks that take the global-memory path
+  uint32_t pad[3];
   unsigned long long total_decoded;
 };
 
@@ -276,65 +276,23 @@ __device__ __forceinline__ void warp_copy_from_stream(uint8_t* __restrict__ dst,
   }
 }
 
-template <bool kSizeOnly>
-__device__ __forceinline__ uint32_t decode_block_warp(const uint8_t* __restrict__ src, uint32_t csize, uint8_t* dst,
-                                                      uint32_t dcap, unsigned long long before, uint32_t link,
-                                                      const uint32_t* done, bool& waited, uint32_t& err, int lane) {
+// token walk without copying: decoded size of one block (for foreign blocks whose size is not implied)
+__device__ __forceinline__ uint32_t measure_block_warp(const uint8_t* __restrict__ src, uint32_t csize, uint32_t& err, int lane) {
   uint32_t ip = 0, op = 0;
   while (ip < csize) {
     const uint32_t token = __ldg(src + ip);
     ip++;
     uint32_t lit = token >> 4;
     if (lit == 15) lit += read_ext(src, ip, csize, lane);
-    if (lit) {
-      if (ip + lit > csize || op + lit > dcap) { err = kErrBadBlock; return op; }
-      if (!kSizeOnly) {
-        if (lit <= 32) { if ((uint32_t)lane < lit) dst[op + lane] = __ldg(src + ip + lane); }
-        else warp_copy_from_stream(dst + op, src + ip, lit, lane);
-      }
-      ip += lit;
-      op += lit;
-    }
+    if (ip + lit > csize) { err = kErrBadBlock; return op; }
+    ip += lit;
+    op += lit;
     if (ip >= csize) break;
     if (ip + 2 > csize) { err = kErrBadBlock; return op; }
-    const uint32_t offset = (uint32_t)__ldg(src + ip) | ((uint32_t)__ldg(src + ip + 1) << 8);
     ip += 2;
     uint32_t mlen = token & 15u;
     if (mlen == 15) mlen += read_ext(src, ip, csize, lane);
-    mlen += 4;
-    if (offset == 0 || op + mlen > dcap) { err = kErrBadBlock; return op; }
-    if (!kSizeOnly) {
-      if (offset > op) {
-        // reaches in front of this block: only legal inside a linked frame
-        if (link == kNoLink || (unsigned long long)(offset - op) > before) { err = kErrBadBlock; return op; }
-        if (!waited) {
-          if (lane == 0) {
-            while (atomicAdd(const_cast<uint32_t*>(done) + link, 0u) == 0u) __nanosleep(100);
-            __threadfence();
-          }
-          waited = true;
-        }
-      }
-      __syncwarp();
-      uint8_t* o = dst + op;
-      if (offset >= 32) {
-        // 32 bytes per step never overlap their own source; later steps may read earlier ones
-        const bool overlap = mlen > offset;
-        for (uint32_t kb = 0; kb < mlen; kb += 32) {
-          const uint32_t k = kb + lane;
-          if (k < mlen) o[k] = o[(long long)k - offset];
-          if (overlap) __syncwarp();
-        }
-      } else if (offset == 1) {
-        const uint8_t v = *(o - 1);
-        for (uint32_t k = lane; k < mlen; k += 32) o[k] = v;
-      } else {
-        const uint8_t* base = o - offset;
-        for (uint32_t k = lane; k < mlen; k += 32) o[k] = base[k % offset];
-      }
-      __syncwarp();
-    }
-    op += mlen;
+    op += mlen + 4;
   }
   return op;
 }
@@ -574,10 +532,8 @@ __global__ void __launch_bounds__(kDecThreads) lz4_sizes_kernel(const uint8_t* _
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= nblocks) return;
     if (T.dsize[b] != 0 || (T.word[b] & kLz4StoredFlag)) continue;
-    bool waited = false;
     uint32_t err = 0;
-    const uint32_t sz = decode_block_warp<true>(src + T.src_off[b], T.word[b] & 0x7FFFFFFFu, nullptr, 0xFFFFFFFFu, 0, kNoLink,
-                                               nullptr, waited, err, lane);
+    const uint32_t sz = measure_block_warp(src + T.src_off[b], T.word[b] & 0x7FFFFFFFu, err, lane);
     if (lane == 0) {
       T.dsize[b] = sz;
       if (err) atomicMax(&ctl->error, err);
@@ -591,7 +547,6 @@ __global__ void __launch_bounds__(kDirThreads) lz4_offsets_kernel(DecCtl* ctl, D
   const uint32_t nblk = ctl->nblocks;
   const int tid = threadIdx.x;
   unsigned long long running = 0;
-  uint32_t n_small = 0, n_generic = 0;
   for (uint32_t base = 0; base < nblk; base += kDirThreads * kPerThread) {
     uint32_t d[kPerThread];
     unsigned long long local = 0;
@@ -611,14 +566,11 @@ __global__ void __launch_bounds__(kDirThreads) lz4_offsets_kernel(DecCtl* ctl, D
         T.dst_off[i] = off;
         T.done[i] = 0;
         off += d[k];
-        n_generic++;
       }
     }
     running += total;
     __syncthreads();
   }
-  atomicAdd(&ctl->n_small, n_small);
-  atomicAdd(&ctl->n_generic, n_generic);
   if (tid == 0) {
     ctl->total_decoded = running;
     // the reference accepts 0 < decoded <= expected (encoders/lz4.hpp:334-338); we refuse overruns

@@ -47,9 +47,12 @@ struct __align__(16) EncSmem {
     uint16_t cand[kB];                   // phase A/B: candidate position per input position
     uint32_t out[(kB + 64) / 4];         // phase D: encoded bytes (every cand read happens before the first out write)
   };
-  uint16_t htab[1 << kHashLog];
-  uint32_t segM[kSegs], segC0[kSegs], segC1[kSegs];   // per segment: candidate mask and 2-bit length code planes
-  int seg_litbase[kSegs];                // dest(p) = seg_litbase + p for the literal run that ends at the segment's first match
+  union {
+    uint16_t htab[1 << kHashLog];        // phase A2 only
+    int seg_litbase[kSegs];              // phase D: dest(p) = seg_litbase + p for the literal run ending at the segment's first match
+  };
+  uint32_t E[4][kSegs + 4];              // E[d-1][t] bit j: data[32t+j] == data[32t+j-d]   (d = 1..4, the short offsets)
+  uint32_t segHM[kSegs], segHC0[kSegs], segHC1[kSegs];   // per segment: hash-candidate mask and 2-bit length code planes
   int w_T[kWarps], w_has[kWarps], w_carry_in[kWarps], w_size[kWarps], w_off[kWarps], w_first[kWarps], w_next[kWarps];
   int final_off, final_lit, total;
 };
@@ -108,17 +111,6 @@ __device__ __forceinline__ void store_bytes(uint8_t* __restrict__ g, const uint3
   }
   const int done = head + (body << 4);
   if (tid < nbytes - done) g[done + tid] = sb[done + tid];
-}
-
-// serial extension of a match already known to agree on 7 bytes
-__device__ __forceinline__ int extend_match(const uint32_t* data, int i, int c, int maxlen) {
-  int len = 7;
-  while (len < maxlen) {
-    const uint32_t x = load4(data, i + len) ^ load4(data, c + len);
-    if (x) { len += (__ffs(x) - 1) >> 3; break; }
-    len += 4;
-  }
-  return len < maxlen ? len : maxlen;
 }
 
 __global__ void __launch_bounds__(kThreads, 3)
@@ -202,53 +194,108 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
     __syncthreads();
     csize = S.total;
   } else {
-    // ---------------- phase A: a candidate (and a 2-bit length code) for every position ----------------
-    int nfound = 0;
+    // ---------------- phase A0: byte-equality bit masks for the offsets 1..4 ----------------
+    // In bit-plane data runs and 2/4-byte periods carry the long matches. A thread compares its 32-byte segment with
+    // itself shifted by d bytes (__vcmpeq4 on 8 words) and keeps one bit per position; a match of length L at i with
+    // offset d is then simply L consecutive ones in E_d starting at bit i — found, measured and extended with shifts,
+    // ANDs and ffs on registers, never touching the bytes again.
+    const int seg_lo = tid * 32;
+    {
+      uint32_t W[9];
+      W[0] = tid > 0 ? S.data[8 * tid - 1] : 0u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) W[k + 1] = S.data[8 * tid + k];
+      const int lim = n - kLz4LastLiterals - seg_lo;     // match bytes never touch the last 5 bytes of the block
+      const uint32_t tailmask = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : (1u << lim) - 1u);
+#pragma unroll
+      for (int d = 1; d <= 4; ++d) {
+        uint32_t e = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t prev = d == 4 ? W[k] : __funnelshift_r(W[k], W[k + 1], 32 - 8 * d);   // bytes 4k-d .. 4k-d+3
+          const uint32_t eq = __vcmpeq4(W[k + 1], prev);
+          e |= (((eq & 0x08040201u) * 0x01010101u) >> 24) << (4 * k);
+        }
+        if (tid == 0) e &= ~((1u << d) - 1u);            // no source in front of the block
+        S.E[d - 1][tid] = e & tailmask;
+      }
+      if (tid < 4) S.E[tid][kSegs] = 0;
+    }
+    __syncthreads();
+
+    // ---------------- phase A1: short-offset candidates of this thread's segment (registers only) ----------------
+    uint32_t Ms = 0, D0 = 0, D1 = 0, C0 = 0, C1 = 0;     // candidate mask, offset-1 planes, length code planes
+    {
+      uint32_t L6 = 0, L7 = 0, L8 = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int d = q == 0 ? 1 : (q == 1 ? 2 : (q == 2 ? 4 : 3));   // priority order
+        // matches never cross the warp's 1 KiB sub-block: the last segment sees no successor
+        const unsigned long long e =
+            (unsigned long long)S.E[d - 1][tid] | ((unsigned long long)(lane == 31 ? 0u : S.E[d - 1][tid + 1]) << 32);
+        const unsigned long long r5 = e & (e >> 1) & (e >> 2) & (e >> 3) & (e >> 4);
+        const unsigned long long r6 = r5 & (e >> 5), r7 = r6 & (e >> 6), r8 = r7 & (e >> 7);
+        const uint32_t sel = (uint32_t)r5 & ~Ms;         // at least 5 bytes and no better-ranked offset yet
+        Ms |= sel;
+        L6 |= sel & (uint32_t)r6;
+        L7 |= sel & (uint32_t)r7;
+        L8 |= sel & (uint32_t)r8;
+        if ((d - 1) & 1) D0 |= sel;
+        if ((d - 1) & 2) D1 |= sel;
+      }
+      const int lim = n - kLz4MFLimit + 1 - seg_lo;      // a match starts at most 12 bytes before the block end
+      const uint32_t valid = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : (1u << lim) - 1u);
+      Ms &= valid;
+      C0 = (L6 ^ L7 ^ L8) & Ms;                          // code = number of the planes L6,L7,L8 that are set: 5,6,7,>=8 bytes
+      C1 = L7 & Ms;
+      S.segHM[tid] = ~Ms & valid;                        // positions that still want a hash candidate
+    }
+    __syncthreads();
+
+    // ---------------- phase A2: hash candidates for the positions without a short-offset match ----------------
+    // 32 rounds of 512 positions against a 4096-entry table of earlier positions; a warp whose segment is fully covered
+    // by short-offset matches skips the round. Only the positions that look up are inserted.
+    int nfound = Ms != 0;
     for (int r = 0; r < kB / kThreads; ++r) {
-      const int i = r * kThreads + tid;   // this warp covers exactly segment r*16 + warp
-      const int wi = i >> 2, sh = (i & 3) * 8;
-      const uint32_t w0 = S.data[wi], w1 = S.data[wi + 1], w2 = S.data[wi + 2];
-      const uint32_t wp = wi > 0 ? S.data[wi - 1] : 0u;
-      const uint32_t v = __funnelshift_r(w0, w1, sh);    // bytes i   .. i+3
-      const uint32_t v2 = __funnelshift_r(w1, w2, sh);   // bytes i+4 .. i+7
-      const uint32_t lo = __funnelshift_r(wp, w0, sh);   // bytes i-4 .. i-1
-      const uint32_t h = (v * 2654435761u) >> (32 - kHashLog);
-      const int sub_hi = (i & ~(kSub - 1)) + kSub;
-      const int maxlen = min(sub_hi, n - kLz4LastLiterals) - i;
-      uint32_t found = kNone, x = 0;
-      if (maxlen >= kLz4MinMatch && i + kLz4MFLimit <= n) {
-        // offsets 1..4 first (register-only): runs and short periods carry the long matches of bit-plane data,
-        // a table hit from an earlier round is often a stale 4-byte coincidence (tools/lz4_model.c)
-        if (i >= 1 && v == ((lo >> 24) | (v << 8))) { found = i - 1; x = v2 ^ ((v >> 24) | (v2 << 8)); }
-        else if (i >= 2 && v == ((lo >> 16) | (v << 16))) { found = i - 2; x = v2 ^ ((v >> 16) | (v2 << 16)); }
-        else if (i >= 4 && v == lo) { found = i - 4; x = v2 ^ v; }
-        else if (i >= 3 && v == ((lo >> 8) | (v << 24))) { found = i - 3; x = v2 ^ ((v >> 8) | (v2 << 24)); }
-        else {
+      const int seg = r * kWarps + warp;   // this warp covers exactly one segment per round
+      const uint32_t ns = S.segHM[seg];
+      uint32_t HM = 0, HC0 = 0, HC1 = 0;
+      if (ns) {
+        const int i = r * kThreads + tid;
+        bool found = false;
+        int code = 0;
+        if ((ns >> lane) & 1u) {
+          const uint32_t v = load4(S.data, i);
+          const uint32_t h = (v * 2654435761u) >> (32 - kHashLog);
           // the table is read and written without a barrier in between: an entry may already belong to this round
           // (any earlier position with the same 4 bytes is a valid source; c < i and the compare make it safe)
           const uint32_t c = S.htab[h];
-          if (c < (uint32_t)i && load4(S.data, (int)c) == v) { found = c; x = v2 ^ load4(S.data, (int)c + 4); }
+          if (c < (uint32_t)i && load4(S.data, (int)c) == v) {
+            const int maxlen = min((i & ~(kSub - 1)) + kSub, n - kLz4LastLiterals) - i;
+            const uint32_t x = load4(S.data, i + 4) ^ load4(S.data, (int)c + 4);
+            int len = 4 + (x ? ((__ffs(x) - 1) >> 3) : 4);
+            if (len > maxlen) len = maxlen;
+            // 4-byte matches save one byte and cost a sequence on both ends of the codec: dropping them keeps the ratio
+            // within ~1 % on bit planes, improves it on background-removed stacks and matches liblz4 on noisy 8-bit
+            // codes (tools/lz4_model.c), while halving the number of sequences
+            if (len >= 5) {
+              found = true;
+              code = len - 5 < 3 ? len - 5 : 3;   // 0,1,2: exact length 5,6,7; 3: at least 8, extended in phase B
+              S.cand[i] = (uint16_t)c;
+            }
+          }
+          S.htab[h] = (uint16_t)i;
         }
+        HM = __ballot_sync(0xffffffffu, found);
+        HC0 = __ballot_sync(0xffffffffu, found && (code & 1));
+        HC1 = __ballot_sync(0xffffffffu, found && (code & 2));
       }
-      int len = 4 + (x ? ((__ffs(x) - 1) >> 3) : 4);
-      if (len > maxlen) len = maxlen;
-      // 4-byte matches save one byte and cost a sequence on both ends of the codec: dropping them keeps the ratio within
-      // ~1 % on bit planes, improves it on background-removed stacks and matches liblz4 on noisy 8-bit codes
-      // (tools/lz4_model.c), while halving the number of sequences
-      const bool has = found != kNone && len >= 5;
-      const int code = len - 5 < 3 ? len - 5 : 3;   // 0,1,2: exact length 5,6,7; 3: at least 8, extended in phase B
-      S.cand[i] = (uint16_t)found;
-      const uint32_t M = __ballot_sync(0xffffffffu, has);
-      const uint32_t C0 = __ballot_sync(0xffffffffu, has && (code & 1));
-      const uint32_t C1 = __ballot_sync(0xffffffffu, has && (code & 2));
       if (lane == 0) {
-        const int seg = r * kWarps + warp;
-        S.segM[seg] = M;
-        S.segC0[seg] = C0;
-        S.segC1[seg] = C1;
+        S.segHM[seg] = HM;
+        S.segHC0[seg] = HC0;
+        S.segHC1[seg] = HC1;
       }
-      nfound |= has;
-      if (i + 4 <= n) S.htab[h] = (uint16_t)i;
+      nfound |= HM != 0;
       __syncthreads();   // one barrier per round keeps the warps within a round of each other
     }
     const int any_found = __syncthreads_or(nfound);
@@ -259,9 +306,10 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
       // ---------------- phase B: every thread parses its own 32-byte segment greedily ----------------
       // A match may overshoot into the following segments of the same warp; their entry point moves and
       // they re-parse until the warp's parse is stable (lane k is final after at most k+1 rounds).
-      const int seg_lo = tid * 32;
       const int limit = min((warp + 1) * kSub, n - kLz4LastLiterals);
-      const uint32_t M = S.segM[tid], C0 = S.segC0[tid], C1 = S.segC1[tid];
+      const uint32_t M = Ms | S.segHM[tid];              // hash candidates exist only where no short-offset one does
+      C0 |= S.segHC0[tid];
+      C1 |= S.segHC1[tid];
       uint32_t Sel = 0;
       unsigned long long lens = 0;       // lengths of the long matches of this segment, 11 bits each, in order
       int entry = 0, exit_abs = seg_lo + 32;
@@ -281,7 +329,22 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
               const int j = __ffs(mm) - 1;
               const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
               int len = 5 + code;
-              if (code == 3) {
+              if (code == 3 && ((Ms >> j) & 1u)) {
+                // short-offset match: count the ones that follow in E_d, 32 positions per step
+                const int i = seg_lo + j, maxlen = limit - i;
+                const uint32_t* Ed = S.E[((D0 >> j) & 1u) | (((D1 >> j) & 1u) << 1)];
+                len = 8;
+                while (len < maxlen) {
+                  const int p = i + len, avail = 32 - (p & 31);
+                  const uint32_t z = ~(Ed[p >> 5] >> (p & 31));     // zeros where the match goes on
+                  const int ones = z ? __ffs(z) - 1 : 32;
+                  if (ones < avail) { len += ones; break; }
+                  len += avail;
+                }
+                if (len > maxlen) len = maxlen;
+                lens |= (unsigned long long)len << (11 * nlong);
+                nlong++;
+              } else if (code == 3) {
                 const int i = seg_lo + j, c = (int)S.cand[i], maxlen = limit - i;
                 len = 8;
                 bool open = true;
@@ -422,7 +485,8 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
             const int j = __ffs(m) - 1;
             m &= m - 1;
             const int i = seg_lo + j;
-            offs[k >> 1] |= (uint32_t)(i - (int)S.cand[i]) << (16 * (k & 1));
+            const uint32_t off = ((Ms >> j) & 1u) ? 1u + ((D0 >> j) & 1u) + 2u * ((D1 >> j) & 1u) : (uint32_t)(i - (int)S.cand[i]);
+            offs[k >> 1] |= off << (16 * (k & 1));
           }
         }
       }

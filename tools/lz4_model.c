@@ -15,6 +15,7 @@ static uint32_t ld4(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; 
 static void find_candidates(const uint8_t* d, int n, int round, int hashlog, int mode, int* cand) {
   int tsize = 1 << hashlog;
   int* tab = malloc(sizeof(int) * tsize);
+  static int noshort[1 << 20];
   for (int i = 0; i < tsize; ++i) tab[i] = -1;
   for (int r0 = 0; r0 < n; r0 += round) {
     int r1 = r0 + round < n ? r0 + round : n;
@@ -45,10 +46,24 @@ static void find_candidates(const uint8_t* d, int n, int round, int hashlog, int
         while (b < 12 && i + b < n - 5 && d[i + b] == d[c + b]) b++;
         if (b > a) found = c;
       }
+      if (mode & 64) {
+        static const int ds[4] = {1, 2, 4, 3};
+        found = -1;
+        for (int q = 0; q < 4 && found < 0; ++q) {
+          int dd = ds[q];
+          if (i < dd) continue;
+          int l = 0;
+          while (l < 5 && i + l < n - 5 && d[i + l] == d[i + l - dd]) l++;
+          if (l >= 5) found = i - dd;
+        }
+        noshort[i] = found < 0;
+        if (found < 0 && c >= 0 && ld4(d + c) == v) found = c;
+      }
       cand[i] = found;
     }
     for (int i = r0; i < r1; ++i) {
       if (i + 4 > n) continue;
+      if ((mode & 64) && !noshort[i]) continue;
       uint32_t v = ld4(d + i);
       uint32_t h = (v * 2654435761u) >> (32 - hashlog);
       if (!((mode & 32) && (i & 1))) tab[h] = i; /* last writer of the round wins (GPU: racy, any) */
