@@ -87,7 +87,7 @@ __device__ __forceinline__ unsigned long long block_scan_incl(unsigned long long
 }
 
 constexpr int kDirThreads = 1024;
-constexpr int kPerThread = 8;
+constexpr int kPerThread = 16;
 
 __global__ void __launch_bounds__(kDirThreads) lz4_directory_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
                                                                     DecCtl* ctl, DecTables T, uint32_t capacity,
@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(kDirThreads) lz4_directory_kernel(const uint8_
     if (mode == 1) {
       // ---- our frame: block table by parallel prefix sum over the index words ----
       const uint8_t* idx = src + sh_args[0];
+      const bool idx_aligned = (((uintptr_t)idx) & 3) == 0;
       const unsigned long long first_hdr = sh_args[1];
       const uint32_t nblk = (uint32_t)(sh_args[2] & 0xFFFFFFFFu), bb = (uint32_t)(sh_args[2] >> 32);
       const unsigned long long raw = sh_args[3];
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(kDirThreads) lz4_directory_kernel(const uint8_
 #pragma unroll
         for (int k = 0; k < kPerThread; ++k) {
           const uint32_t i = base + tid * kPerThread + k;
-          w[k] = i < nblk ? rd32(idx + 4ull * i) : 0u;
+          w[k] = i < nblk ? (idx_aligned ? __ldg(reinterpret_cast<const uint32_t*>(idx) + i) : rd32(idx + 4ull * i)) : 0u;
           local += i < nblk ? 4ull + (w[k] & 0x7FFFFFFFu) : 0ull;
         }
         unsigned long long total;
@@ -464,11 +465,12 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
       } else if (mlen >= 48 && (offset == 1 || offset == 2 || offset == 4)) {
         // run fill: for a period dividing 4 every 4-byte aligned output word holds the same value
         const uint32_t al = (op + 3u) & ~3u;          // first aligned output position
+        const uint32_t om = offset - 1u;              // period is a power of two: modulo = mask
         uint32_t word = 0;
 #pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) word |= (uint32_t)SQYB_W(op - offset + ((al - op + j) % offset)) << (8 * j);
+        for (uint32_t j = 0; j < 4; ++j) word |= (uint32_t)SQYB_W(op - offset + ((al - op + j) & om)) << (8 * j);
         const uint32_t head = al - op;                // < 4 <= mlen
-        if ((uint32_t)lane < head) SQYB_W(op + lane) = SQYB_W(op - offset + lane % offset);
+        if ((uint32_t)lane < head) SQYB_W(op + lane) = SQYB_W(op - offset + (lane & om));
         const uint32_t body = (mlen - head) >> 2;     // whole words
         for (uint32_t wb = 0; wb < body; wb += 32) {
           const uint32_t w = wb + lane;
@@ -479,14 +481,27 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
         const uint32_t donew = head + (body << 2);
         if ((uint32_t)lane < mlen - donew) {
           const uint32_t k = donew + lane;
-          SQYB_W(op + k) = (uint8_t)(word >> (8 * (k - head & 3u)));
+          SQYB_W(op + k) = (uint8_t)(word >> (8 * ((k - head) & 3u)));
+        }
+      } else if (offset == 1) {
+        // short byte run
+        const uint8_t v = SQYB_W(op - 1u);
+        for (uint32_t kb = 0; kb < mlen; kb += 32) {
+          if (kb + lane < mlen) SQYB_W(op + kb + lane) = v;
         }
       } else {
-        // short period: the pattern [op-offset, op) repeats; every byte's source lies in front of the match
+        // short period: the pattern [op-offset, op) repeats; every byte's source lies in front of the match.
+        // k mod offset without an integer division: k < 64 per step, exact through a float reciprocal.
         const uint32_t base = op - offset;
+        const float inv = __frcp_rn((float)offset);
+        uint32_t kbm = 0;                             // kb mod offset
         for (uint32_t kb = 0; kb < mlen; kb += 32) {
           const uint32_t k = kb + lane;
-          if (k < mlen) SQYB_W(op + k) = SQYB_W(base + k % offset);
+          const uint32_t x = kbm + lane;              // < 63
+          const uint32_t r = x - offset * (uint32_t)__float2int_rz(((float)x + 0.5f) * inv);
+          if (k < mlen) SQYB_W(op + k) = SQYB_W(base + r);
+          const uint32_t y = kbm + 32u;               // < 63
+          kbm = y - offset * (uint32_t)__float2int_rz(((float)y + 0.5f) * inv);
           const uint32_t step = mlen - kb < 32u ? mlen - kb : 32u;
           O.flush_to(op + kb + step);
         }

@@ -566,20 +566,22 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
   }
   if (tid == 0) {
     uint8_t* ip = dst + kSkippableHeaderBytes + sizeof(SqybIndexHeader) + 4ull * b;   // the block's entry in the index frame
-    ip[0] = (uint8_t)word; ip[1] = (uint8_t)(word >> 8); ip[2] = (uint8_t)(word >> 16); ip[3] = (uint8_t)(word >> 24);
+    if ((((uintptr_t)ip) & 3) == 0) *reinterpret_cast<uint32_t*>(ip) = word;
+    else { ip[0] = (uint8_t)word; ip[1] = (uint8_t)(word >> 8); ip[2] = (uint8_t)(word >> 16); ip[3] = (uint8_t)(word >> 24); }
     if (stats) atomicAdd(stats + kind, 1u);
   }
 }
 
 // exclusive prefix sum of (4 + block bytes) over the index words -> byte offset of every block header; one CTA
 constexpr int kScanThreads = 1024;
-constexpr int kScanPer = 8;
+constexpr int kScanPer = 16;
 __global__ void __launch_bounds__(kScanThreads) lz4_offsets_scan_kernel(uint8_t* __restrict__ dst, uint32_t nblocks,
                                                                         unsigned long long* __restrict__ offsets,
                                                                         unsigned long long* __restrict__ payload_bytes_out) {
   __shared__ unsigned long long warp_sums[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint8_t* idx = dst + kSkippableHeaderBytes + sizeof(SqybIndexHeader);
+  const bool idx_aligned = (((uintptr_t)idx) & 3) == 0;
   unsigned long long running = 0;
   for (uint32_t base = 0; base < nblocks; base += kScanThreads * kScanPer) {
     unsigned long long sz[kScanPer], local = 0;
@@ -589,7 +591,8 @@ __global__ void __launch_bounds__(kScanThreads) lz4_offsets_scan_kernel(uint8_t*
       uint32_t w = 0;
       if (i < nblocks) {
         const uint8_t* p = idx + 4ull * i;
-        w = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+        w = idx_aligned ? reinterpret_cast<const uint32_t*>(idx)[i]
+                        : (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
       }
       sz[k] = i < nblocks ? 4ull + (w & 0x7FFFFFFFu) : 0ull;
       local += sz[k];
