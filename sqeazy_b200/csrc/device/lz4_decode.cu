@@ -462,7 +462,7 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
           O.flush_to(op + kb + step);
           __syncwarp();                 // orders overlapping steps
         }
-      } else if (mlen >= 48 && (offset == 1 || offset == 2 || offset == 4)) {
+      } else if (mlen >= 256 && (offset == 1 || offset == 2 || offset == 4)) {
         // run fill: for a period dividing 4 every 4-byte aligned output word holds the same value
         const uint32_t al = (op + 3u) & ~3u;          // first aligned output position
         const uint32_t om = offset - 1u;              // period is a power of two: modulo = mask
@@ -483,11 +483,13 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
           const uint32_t k = donew + lane;
           SQYB_W(op + k) = (uint8_t)(word >> (8 * ((k - head) & 3u)));
         }
-      } else if (offset == 1) {
-        // short byte run
-        const uint8_t v = SQYB_W(op - 1u);
+      } else if ((offset & (offset - 1u)) == 0u) {
+        // period 1, 2, 4, 8 or 16: k mod offset is a mask (the common case: byte runs and 16/32-bit periodic data)
+        const uint32_t base = op - offset, om = offset - 1u;
         for (uint32_t kb = 0; kb < mlen; kb += 32) {
-          if (kb + lane < mlen) SQYB_W(op + kb + lane) = v;
+          const uint32_t k = kb + lane;
+          if (k < mlen) SQYB_W(op + k) = SQYB_W(base + (k & om));
+          if (kb + 32u < mlen) O.flush_to(op + kb + 32u);
         }
       } else {
         // short period: the pattern [op-offset, op) repeats; every byte's source lies in front of the match.
