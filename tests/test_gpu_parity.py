@@ -182,6 +182,11 @@ def lz4_inputs():
         "period64": np.tile(rng.integers(0, 256, size=64, dtype=np.uint8), 2000),
         "sparse_bits": (rng.random(200000) < 0.05).astype(np.uint8) * rng.integers(1, 256, size=200000, dtype=np.uint8),
         "ramp16": (np.arange(1 << 18) % 32768).astype(np.uint16).view(np.uint8),
+        # long periods: match sources lie outside the decoder's 2 KiB shared-memory window (far path), overlapping copies
+        "period3000": np.tile(rng.integers(0, 256, size=3000, dtype=np.uint8), 40),
+        "period5000_ragged": np.tile(rng.integers(0, 256, size=5000, dtype=np.uint8), 13)[:-77],
+        "far_and_near": np.concatenate([np.tile(rng.integers(0, 256, size=2500, dtype=np.uint8), 3), np.zeros(700, np.uint8),
+                                        np.tile(np.array([5, 6], np.uint8), 900), np.tile(rng.integers(0, 256, size=2500, dtype=np.uint8), 4)]),
         "planes_scmos": None,
     }
     return cases
@@ -256,6 +261,27 @@ def test_lz4_decodes_port_frames(sq, cuda, port):
     out = cuda.zeros(a.size, dtype=cuda.int16, device="cuda")
     assert sq.lz4_decode_device(dev(cuda, payload), out) == a.nbytes
     assert np.array_equal(host16(out), a)
+
+
+@pytest.mark.parametrize("period", [1, 3, 7, 40, 1985, 3000, 40000, 70000])
+def test_lz4_decodes_foreign_frames_with_any_offset(sq, cuda, port, period):
+    """256 KiB blocks from the oracle's encoder: offsets from 1 to 64 KiB, near / far / overlapping copies"""
+    rng = np.random.default_rng(period)
+    a = np.tile(rng.integers(0, 256, size=period, dtype=np.uint8), (700000 // period) + 2)[:700001]
+    payload = port.lz4_frames_encode(a, chunk=1 << 19)
+    out = cuda.zeros(a.size, dtype=cuda.uint8, device="cuda")
+    assert sq.lz4_decode_device(dev(cuda, payload), out) == a.size
+    assert np.array_equal(out.cpu().numpy(), a)
+
+
+def test_lz4_decodes_long_literal_runs_in_big_blocks(sq, cuda, ref):
+    """a 256 KiB liblz4 block with ~200 KB of literals carries ~800 length bytes: the stream window must follow them"""
+    rng = np.random.default_rng(8)
+    a = np.concatenate([np.zeros(30000, np.uint8), rng.integers(0, 256, size=200000, dtype=np.uint8), np.zeros(32144, np.uint8)])
+    payload = ref.lz4_encode(a, nthreads=1)
+    out = cuda.zeros(a.size, dtype=cuda.uint8, device="cuda")
+    assert sq.lz4_decode_device(dev(cuda, payload), out) == a.size
+    assert np.array_equal(out.cpu().numpy(), a)
 
 
 def test_lz4_rejects_garbage(sq, cuda):
@@ -383,6 +409,19 @@ def test_quantiser_with_global_histogram(sq, cuda, port):
     for sl in (slice(0, 8), slice(8, 16)):
         blob = sq.encode_device("quantiser->lz4", d[sl].contiguous(), global_hist=hist)
         assert np.array_equal(sq.decode(blob.cpu().numpy()), whole[sl])
+
+
+def test_distributed_threshold_matches_single_gpu(sq, cuda, port):
+    """sqeazy_b200.dist.global_background_threshold (the multi-GPU path, here with one rank) == sqyx_estimate_background"""
+    from sqeazy_b200 import dist as sqdist
+
+    vol = numpy_volume((9, 64, 96), "ref", index=14)
+    d = dev(cuda, vol)
+    sup, thr = sq.estimate_background_device(d, l2_bytes=1 << 12)
+    thr2, sup2 = sqdist.global_background_threshold(d, 0, vol.shape, l2_bytes=1 << 12, histogram_fn=lambda sub, row: sq.histogram_device(sub, row),
+                                                   support_fn=lambda h: sq.histogram_support(h, 0.99))
+    assert thr2 == thr and np.array_equal(sup2.view(np.uint32), sup.view(np.uint32))
+    assert np.array_equal(sup.view(np.uint32), port.darkest_face_supports(vol, 1 << 12).view(np.uint32))
 
 
 def test_large_volume_roundtrip_properties(sq, cuda):
