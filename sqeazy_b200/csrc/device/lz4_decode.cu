@@ -483,7 +483,7 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
           const uint32_t k = donew + lane;
           SQYB_W(op + k) = (uint8_t)(word >> (8 * ((k - head) & 3u)));
         }
-      } else if ((offset & (offset - 1u)) == 0u) {
+      } else if ((offset & (offset - 1u)) == 0u && mlen < 1024u) {
         // period 1, 2, 4, 8 or 16: k mod offset is a mask (the common case: byte runs and 16/32-bit periodic data)
         const uint32_t base = op - offset, om = offset - 1u;
         for (uint32_t kb = 0; kb < mlen; kb += 32) {
@@ -492,20 +492,22 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
           if (kb + 32u < mlen) O.flush_to(op + kb + 32u);
         }
       } else {
-        // short period: the pattern [op-offset, op) repeats; every byte's source lies in front of the match.
-        // k mod offset without an integer division: k < 64 per step, exact through a float reciprocal.
+        // any other short period (or a long match with period 8/16). The pattern [op-offset, op) repeats; the first D bytes
+        // (D = smallest multiple of the period >= 32) are taken from it, everything after that is a copy from D bytes
+        // back, i.e. from an earlier 32-byte step — the ring may wrap over the original pattern on long matches.
         const uint32_t base = op - offset;
+        const uint32_t D = offset * ((31u + offset) / offset);
         const float inv = __frcp_rn((float)offset);
-        uint32_t kbm = 0;                             // kb mod offset
         for (uint32_t kb = 0; kb < mlen; kb += 32) {
           const uint32_t k = kb + lane;
-          const uint32_t x = kbm + lane;              // < 63
-          const uint32_t r = x - offset * (uint32_t)__float2int_rz(((float)x + 0.5f) * inv);
-          if (k < mlen) SQYB_W(op + k) = SQYB_W(base + r);
-          const uint32_t y = kbm + 32u;               // < 63
-          kbm = y - offset * (uint32_t)__float2int_rz(((float)y + 0.5f) * inv);
+          if (k < mlen) {
+            uint32_t src = op + k - D;
+            if (k < D) src = base + (k - offset * (uint32_t)__float2int_rz(((float)k + 0.5f) * inv));   // k < 62: exact
+            SQYB_W(op + k) = SQYB_W(src);
+          }
           const uint32_t step = mlen - kb < 32u ? mlen - kb : 32u;
           O.flush_to(op + kb + step);
+          __syncwarp();
         }
       }
     } else {

@@ -263,7 +263,7 @@ def test_lz4_decodes_port_frames(sq, cuda, port):
     assert np.array_equal(host16(out), a)
 
 
-@pytest.mark.parametrize("period", [1, 3, 7, 40, 1985, 3000, 40000, 70000])
+@pytest.mark.parametrize("period", [1, 2, 3, 4, 5, 7, 8, 16, 31, 32, 33, 40, 1984, 1985, 2048, 3000, 40000, 70000])
 def test_lz4_decodes_foreign_frames_with_any_offset(sq, cuda, port, period):
     """256 KiB blocks from the oracle's encoder: offsets from 1 to 64 KiB, near / far / overlapping copies"""
     rng = np.random.default_rng(period)
