@@ -33,7 +33,7 @@ SQYX_SYMBOLS = [
     "sqyx_bitswap_decode_UI16", "sqyx_remove_background_UI16", "sqyx_estimate_background_UI16", "sqyx_histogram_UI16",
     "sqyx_quantiser_luts", "sqyx_lut_apply_UI16", "sqyx_lut_decode_UI16", "sqyx_lz4_bound", "sqyx_lz4_encode",
     "sqyx_lz4_decode", "sqyx_device_count", "sqyx_kernel_launches", "sqyx_last_lz4_stats", "sqyx_host_l2_bytes",
-    "sqyx_release_scratch", "sqyx_set_device", "sqyx_enable_stage_timing", "sqyx_stage_ms", "sqyx_histogram_support",
+    "sqyx_release_scratch", "sqyx_set_lz4_lane_max", "sqyx_set_device", "sqyx_enable_stage_timing", "sqyx_stage_ms", "sqyx_histogram_support",
     "sqyx_rmest_frame_portion",
 ]
 
@@ -311,6 +311,13 @@ def last_lz4_stats():
     o = (c_long * 4)()
     lib().sqyx_last_lz4_stats(o)
     return {"general_blocks": o[0], "constant_blocks": o[1], "stored_blocks": o[2], "payload_bytes": o[3]}
+
+
+def set_lz4_lane_max(nbytes: int) -> int:
+    """decoded-size limit of the lane-serial LZ4 block decoder (0 = warp-per-block only); returns the previous value"""
+    f = lib().sqyx_set_lz4_lane_max
+    f.restype = c_long
+    return int(f(c_long(int(nbytes))))
 
 
 def host_l2_bytes() -> int:

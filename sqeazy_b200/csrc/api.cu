@@ -508,6 +508,8 @@ int sqyx_last_lz4_stats(long* out4) {
   return 0;
 }
 
+long sqyx_set_lz4_lane_max(long bytes) { return k_lz4_set_lane_max(bytes); }
+
 int sqyx_release_scratch(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   Arena* A = nullptr;

@@ -32,6 +32,8 @@ int k_lz4_encode(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* wor
 size_t k_lz4_decode_workspace_bytes(uint64_t dst_bytes);
 int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, int measure_all,
                  cudaStream_t st);
+// decoded-size limit of the lane-serial block decoder (0 = warp-per-block decoder only); returns the previous value
+long k_lz4_set_lane_max(long bytes);
 int k_lz4_decode_status(void* workspace, uint32_t* error, uint64_t* total_decoded, cudaStream_t st);
 
 }  // namespace sqyb

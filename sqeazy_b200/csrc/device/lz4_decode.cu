@@ -19,6 +19,8 @@
 #include "kernels.h"
 #include "lz4_format.h"
 
+#include <cstdlib>
+
 namespace sqyb {
 namespace {
 
@@ -40,7 +42,9 @@ struct DecCtl {          // lives at the start of the workspace
   uint32_t ticket_size;
   uint32_t ticket_decode;
   uint32_t need_sizes;   // number of blocks whose decoded size must be measured
-  uint32_t pad[3];
+  uint32_t nwork;        // blocks queued for the lane-serial decoder
+  uint32_t ticket_lane;
+  uint32_t nwarp;        // blocks left to the warp-per-block decoder
   unsigned long long total_decoded;
 };
 
@@ -51,7 +55,11 @@ struct DecTables {
   uint32_t* dsize;               // decoded size (0 = unknown until the size pass)
   uint32_t* link;                // previous block of the same linked frame or kNoLink
   uint32_t* done;                // completion flags for linked frames
+  uint32_t* kind;                // who decodes the block (BlockKind), written by lz4_classify_kernel
+  uint32_t* work;                // queue of the lane-serial decoder
 };
+
+enum BlockKind : uint32_t { kKindWarp = 0, kKindDone = 1, kKindLane = 2 };
 
 __device__ __forceinline__ uint32_t rd32(const uint8_t* p) {
   return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
@@ -597,6 +605,119 @@ __global__ void __launch_bounds__(kDirThreads) lz4_offsets_kernel(DecCtl* ctl, D
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// classification: a warp per block. Stored blocks are copied and closed-form run blocks (what the encoder emits for
+// an all-equal block: token 0x1F, byte, offset 1, length bytes, token 0x50, five bytes) are filled here with
+// coalesced 16-byte stores; other independent blocks are queued for the lane-serial decoder; linked blocks and
+// blocks above `lane_max` decoded bytes stay with the warp-per-block decoder.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lz4_classify_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, DecCtl* ctl,
+                                                           DecTables T, uint32_t lane_max) {
+  if (ctl->error) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t nblocks = ctl->nblocks;
+  const uint32_t wpb = blockDim.x >> 5;
+  for (uint32_t b = blockIdx.x * wpb + (threadIdx.x >> 5); b < nblocks; b += gridDim.x * wpb) {
+    const uint32_t word = T.word[b];
+    const uint32_t csize = word & 0x7FFFFFFFu;
+    const uint32_t dsize = T.dsize[b];
+    const uint32_t link = T.link[b];
+    const uint8_t* s = src + T.src_off[b];
+    uint8_t* d = dst + T.dst_off[b];
+    uint32_t kind = kKindWarp, err = 0;
+    if (link == kNoLink) {
+      if (word & kLz4StoredFlag) {
+        if (csize != dsize) err = kErrSizeMismatch;
+        else warp_copy_from_stream(d, s, csize, lane);
+        kind = kKindDone;
+      } else if (csize >= 12 && csize <= 96 && dsize >= 64 && (((uintptr_t)d) & 15) == 0 && __ldg(s) == 0x1Fu &&
+                 __ldg(s + 2) == 1u && __ldg(s + 3) == 0u) {
+        const uint32_t v = __ldg(s + 1);
+        uint32_t ip = 4, mlen = 15 + 4, x;
+        do { x = ip < csize ? __ldg(s + ip) : 0u; ip++; mlen += x; } while (x == 255u && ip < csize);
+        bool ok = ip + 6 == csize && 1u + mlen + 5u == dsize && __ldg(s + ip) == 0x50u;
+        for (uint32_t k = 0; ok && k < 5; ++k) ok = __ldg(s + ip + 1 + k) == v;
+        if (ok) {
+          const uint32_t v4 = v * 0x01010101u;
+          const uint4 fill = make_uint4(v4, v4, v4, v4);
+          const uint32_t nv = dsize >> 4;
+          for (uint32_t q = lane; q < nv; q += 32) st_stream(reinterpret_cast<uint4*>(d) + q, fill);
+          for (uint32_t k = (nv << 4) + lane; k < dsize; k += 32) d[k] = (uint8_t)v;
+          kind = kKindDone;
+        }
+      }
+      if (kind == kKindWarp && dsize <= lane_max && csize > 0 && (((uintptr_t)d) & 15) == 0) kind = kKindLane;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      T.kind[b] = kind;
+      if (err) atomicMax(&ctl->error, err);
+      if (kind == kKindDone) { __threadfence(); atomicExch(T.done + b, 1u); }
+      else if (kind == kKindLane) T.work[atomicAdd(&ctl->nwork, 1u)] = b;
+      else atomicAdd(&ctl->nwarp, 1u);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// lane-serial decoder (lz4_lane.inl): every thread takes blocks from the queue until it is empty
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kLaneThreads = 128;
+constexpr uint32_t kLaneCtasPerSM = 12;
+constexpr uint32_t kLaneStride = kLaneThreads;
+#define SQYB_LANE_FN __device__ __forceinline__
+__device__ __forceinline__ uint32_t lane_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+__device__ __forceinline__ uint32_t lane_funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_l(lo, hi, sh); }
+__device__ __forceinline__ int lane_ffs(uint32_t x) { return __ffs((int)x); }
+// 16-byte aligned chunk of the compressed stream. A chunk that only partly overlaps [sbeg, send) is still loaded whole:
+// an aligned 16-byte access never crosses a page, so it cannot fault, and the bytes outside the stream are never
+// interpreted (every position is checked against the block's end). Chunks entirely outside read as zero.
+__device__ __forceinline__ uint4 lane_load_chunk(const uint8_t* a, const uint8_t* sbeg, const uint8_t* send) {
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (a + 16 > sbeg && a < send) v = __ldg(reinterpret_cast<const uint4*>(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lane_load_out32(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint32_t*>(p)); }
+__device__ __forceinline__ void lane_store_out16(uint8_t* p, const uint4& v) { st_stream(reinterpret_cast<uint4*>(p), v); }
+#include "lz4_lane.inl"
+
+__global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSM) lz4_decode_lanes_kernel(const uint8_t* __restrict__ src,
+                                                                                         uint64_t src_bytes,
+                                                                                         uint8_t* __restrict__ dst, DecCtl* ctl,
+                                                                                         DecTables T) {
+  extern __shared__ __align__(16) uint32_t lane_smem[];   // 32 words per thread, word j of thread t at [j * kLaneThreads + t]
+  if (ctl->error) return;
+  const uint32_t nwork = ctl->nwork;
+  uint32_t* base = lane_smem + threadIdx.x;
+  const uint8_t* send = src + src_bytes;
+  Lane L;
+  L.mode = kLaneIdle;
+  L.A = src; L.d = dst; L.ip = L.end = L.op = L.dcap = L.rem = L.off = L.cur = L.acc = 0; L.pre = make_uint4(0, 0, 0, 0);
+  uint32_t b = 0;
+  bool alive = true;
+  // every lane stays in the loop until the whole warp has run out of work: the vote at the top is the point where the
+  // lanes reconverge after the divergent steps of the previous iteration
+  while (true) {
+    if (alive && (L.mode & 15u) == kLaneIdle) {
+      const uint32_t idx = atomicAdd(&ctl->ticket_lane, 1u);
+      alive = idx < nwork;
+      if (alive) {
+        b = T.work[idx];
+        lane_begin(L, base, src + T.src_off[b], T.word[b] & 0x7FFFFFFFu, dst + T.dst_off[b], T.dsize[b], src, send);
+      }
+    }
+    if (!__any_sync(0xffffffffu, alive)) break;
+    if (alive) {
+      const uint32_t rc = lane_step(L, base, src, send);
+      if ((L.mode & 15u) == kLaneIdle) {
+        if (rc) atomicMax(&ctl->error, rc);
+        __threadfence();
+        atomicExch(T.done + b, 1u);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kWinWarps * 32, 6) lz4_decode_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
                                                                         uint8_t* __restrict__ dst, DecCtl* ctl, DecTables T) {
   extern __shared__ __align__(16) unsigned char dsm[];
@@ -605,11 +726,13 @@ __global__ void __launch_bounds__(kWinWarps * 32, 6) lz4_decode_kernel(const uin
   uint8_t* win = dsm + (size_t)warp * kWinWarpSmem;
   uint8_t* ring8 = win + kWin;
   const uint32_t nblocks = ctl->nblocks;
+  if (ctl->nwarp == 0) return;
   while (true) {
     uint32_t b = 0;
     if (lane == 0) b = atomicAdd(&ctl->ticket_decode, 1u);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= nblocks) return;
+    if (T.kind[b] != kKindWarp) continue;
     const uint32_t word = T.word[b];
     const uint32_t csize = word & 0x7FFFFFFFu;
     const uint32_t dsize = T.dsize[b];
@@ -674,11 +797,30 @@ __global__ void __launch_bounds__(kWinWarps * 32, 6) lz4_decode_kernel(const uin
 
 }  // namespace
 
+// Blocks that decode to at most this many bytes go to the lane-serial decoder (this library's 16 KiB blocks, liblz4's
+// 64 KiB blocks). SQYB_LZ4_LANE_MAX overrides it (0 = warp-per-block decoder only), for measurements.
+static std::atomic<long> g_lane_max{-1};
+static uint32_t lane_max_bytes() {
+  long v = g_lane_max.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = std::getenv("SQYB_LZ4_LANE_MAX");
+    v = e ? std::strtol(e, nullptr, 10) : 65536;
+    if (v < 0) v = 0;
+    g_lane_max.store(v, std::memory_order_relaxed);
+  }
+  return (uint32_t)(v > 0x7FFFFFFF ? 0x7FFFFFFF : v);
+}
+long k_lz4_set_lane_max(long bytes) {
+  const long prev = (long)lane_max_bytes();
+  if (bytes >= 0) g_lane_max.store(bytes, std::memory_order_relaxed);
+  return prev;
+}
+
 size_t k_lz4_decode_capacity(uint64_t dst_bytes) { return (size_t)(dst_bytes / kLz4BlockBytes + 1024); }
 
 size_t k_lz4_decode_workspace_bytes(uint64_t dst_bytes) {
   const size_t cap = k_lz4_decode_capacity(dst_bytes);
-  return 256 + cap * (8 + 8 + 4 + 4 + 4 + 4) + 256;
+  return 256 + cap * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4) + 256;
 }
 
 // Enqueues the whole decode; the status lands in workspace (see k_lz4_decode_status).
@@ -694,14 +836,20 @@ int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t 
   T.word = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
   T.dsize = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
   T.link = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
-  T.done = reinterpret_cast<uint32_t*>(p);
+  T.done = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
+  T.kind = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
+  T.work = reinterpret_cast<uint32_t*>(p);
   SQYB_CUDA_OK(cudaMemsetAsync(ctl, 0, sizeof(DecCtl), st));
   lz4_directory_kernel<<<1, kDirThreads, 0, st>>>(src, src_bytes, ctl, T, (uint32_t)cap, measure_all);
   lz4_sizes_kernel<<<kNumSMs * 4, kDecThreads, 0, st>>>(src, ctl, T);
   lz4_offsets_kernel<<<1, kDirThreads, 0, st>>>(ctl, T, dst_bytes);
+  lz4_classify_kernel<<<kNumSMs * 8, 256, 0, st>>>(src, dst, ctl, T, lane_max_bytes());
+  const size_t lane_smem = 32 * sizeof(uint32_t) * kLaneThreads;
+  SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_decode_lanes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  lz4_decode_lanes_kernel<<<kNumSMs * kLaneCtasPerSM, kLaneThreads, lane_smem, st>>>(src, src_bytes, dst, ctl, T);
   const size_t win_smem = kWinWarps * kWinWarpSmem;
   lz4_decode_kernel<<<kNumSMs * 6, kWinWarps * 32, win_smem, st>>>(src, src_bytes, dst, ctl, T);
-  SQYB_COUNT_LAUNCH(4);
+  SQYB_COUNT_LAUNCH(6);
   return (int)cudaGetLastError();
 }
 

@@ -1,0 +1,96 @@
+"""Both LZ4 block decoders of the library — one block per THREAD (lane-serial, lz4_lane.inl) and one block per warp
+(sliding window) — must produce identical bytes on this library's frames, on liblz4's frames (reference encoder,
+encoders/lz4_utils.hpp:99-274) and on the oracle's frames; corrupt streams must fail cleanly on both."""
+import numpy as np
+import pytest
+
+from sqeazy_b200.synth import numpy_volume
+from test_gpu_parity import dev, host16, lz4_inputs
+
+pytestmark = pytest.mark.gpu
+
+WARP_ONLY = 0
+LANES_FOR_ALL = 1 << 30
+
+
+@pytest.fixture(params=[WARP_ONLY, LANES_FOR_ALL], ids=["warp", "lanes"])
+def decoder(request, sq, cuda):
+    prev = sq.set_lz4_lane_max(request.param)
+    yield request.param
+    sq.set_lz4_lane_max(prev)
+
+
+@pytest.mark.parametrize("name", [k for k in lz4_inputs().keys() if k != "empty"])
+def test_own_frames(sq, cuda, port, decoder, name):
+    a = lz4_inputs()[name]
+    if a is None:
+        a = port.bitswap_encode(1, numpy_volume((8, 256, 256), "scmos", index=5)).view(np.uint8)
+    payload = sq.lz4_encode_device(dev(cuda, a))
+    out = cuda.full((a.size + 64,), 0x5A, dtype=cuda.uint8, device="cuda")
+    assert sq.lz4_decode_device(payload, out[: a.size]) == a.size
+    h = out.cpu().numpy()
+    assert np.array_equal(h[: a.size], a)
+    assert np.all(h[a.size:] == 0x5A), "decoder wrote past the end of the output"
+
+
+@pytest.mark.parametrize("period", [1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 31, 32, 33, 39, 40, 41, 48, 63, 64, 65, 1000, 70000])
+def test_foreign_frames_with_any_offset(sq, cuda, port, decoder, period):
+    """256 KiB blocks from the oracle's encoder: ring-served, doubling, fill and far copies of the lane decoder"""
+    rng = np.random.default_rng(period)
+    a = np.tile(rng.integers(0, 256, size=period, dtype=np.uint8), (300000 // period) + 2)[:300001]
+    a[100000:100040] = rng.integers(0, 256, size=40, dtype=np.uint8)   # break the period once
+    payload = port.lz4_frames_encode(a, chunk=1 << 18)
+    out = cuda.zeros(a.size, dtype=cuda.uint8, device="cuda")
+    assert sq.lz4_decode_device(dev(cuda, payload), out) == a.size
+    assert np.array_equal(out.cpu().numpy(), a)
+
+
+def test_reference_frames(sq, cuda, ref, decoder):
+    """liblz4 frames made by the reference's lz4_scheme: serial (linked: always the warp decoder), parallel, 64 KiB blocks"""
+    vol = numpy_volume((10, 256, 512), "ref", index=9)
+    planes = ref.bitswap_encode(1, vol)
+    for nthreads, config in ((1, b""), (8, b""), (3, b"n_chunks_of_input=7"), (4, b"blocksize_kb=64,framestep_kb=64")):
+        payload = ref.lz4_encode(planes, nthreads=nthreads, config=config)
+        out = cuda.zeros(planes.size, dtype=cuda.int16, device="cuda")
+        assert sq.lz4_decode_device(dev(cuda, payload), out) == planes.nbytes, (nthreads, config)
+        assert np.array_equal(host16(out), planes), (nthreads, config)
+
+
+def test_decoders_agree_on_bit_planes(sq, cuda, port):
+    planes = port.bitswap_encode(1, numpy_volume((16, 512, 512), "scmos", index=3)).view(np.uint8)
+    payload = sq.lz4_encode_device(dev(cuda, planes))
+    outs = []
+    for mode in (WARP_ONLY, LANES_FOR_ALL, 65536):
+        prev = sq.set_lz4_lane_max(mode)
+        try:
+            out = cuda.zeros(planes.size, dtype=cuda.uint8, device="cuda")
+            assert sq.lz4_decode_device(payload, out) == planes.size
+            outs.append(out.cpu().numpy())
+        finally:
+            sq.set_lz4_lane_max(prev)
+    assert np.array_equal(outs[0], planes) and np.array_equal(outs[1], planes) and np.array_equal(outs[2], planes)
+
+
+def test_corrupt_blocks_fail_cleanly(sq, cuda, port, decoder):
+    """bit flips inside the compressed blocks: the decode either fails or returns the promised size (LZ4 has no checksum
+    here), never crashes or writes out of bounds, and the library keeps working afterwards"""
+    rng = np.random.default_rng(99)
+    planes = port.bitswap_encode(1, numpy_volume((4, 256, 256), "ref", index=2)).view(np.uint8)
+    payload = sq.lz4_encode_device(dev(cuda, planes)).cpu().numpy()
+    nblocks = (planes.size + 16383) // 16384
+    first = 8 + 32 + 4 * nblocks + 7     # skippable header + index header + block words + frame header
+    failures = 0
+    for trial in range(24):
+        bad = payload.copy()
+        pos = rng.integers(first, bad.size - 4, size=1 + trial % 5)
+        bad[pos] ^= rng.integers(1, 256, size=pos.size, dtype=np.uint8)
+        out = cuda.full((planes.size + 4096,), 0x33, dtype=cuda.uint8, device="cuda")
+        try:
+            sq.lz4_decode_device(dev(cuda, bad), out[: planes.size])
+        except sq.SqeazyError:
+            failures += 1
+        assert np.all(out[planes.size:].cpu().numpy() == 0x33)
+    assert failures > 0
+    out = cuda.zeros(planes.size, dtype=cuda.uint8, device="cuda")
+    assert sq.lz4_decode_device(dev(cuda, payload), out) == planes.size
+    assert np.array_equal(out.cpu().numpy(), planes)

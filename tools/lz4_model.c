@@ -57,7 +57,7 @@ static void find_candidates(const uint8_t* d, int n, int round, int hashlog, int
           if (l >= 5) found = i - dd;
         }
         noshort[i] = found < 0;
-        if (found < 0 && c >= 0 && ld4(d + c) == v) found = c;
+        if (found < 0 && c >= 0 && ld4(d + c) == v && !(mode & 128)) found = c; /* 128: short offsets only */
       }
       cand[i] = found;
     }
