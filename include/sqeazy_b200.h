@@ -93,7 +93,7 @@ int sqyx_stage_ms(float* out7, int reset);
 long sqyx_host_l2_bytes(void);
 /* LZ4 decode policy: independent blocks that decode to at most `bytes` bytes are decoded one block per THREAD
  * (lane-serial decoder), larger and linked blocks one block per warp. 0 = warp decoder only, negative = query.
- * Default 65536 (or the environment variable SQYB_LZ4_LANE_MAX). Returns the previous value. */
+ * Default 0 (or the environment variable SQYB_LZ4_LANE_MAX). Returns the previous value. */
 long sqyx_set_lz4_lane_max(long bytes);
 /* releases the cached device scratch of the current device */
 int sqyx_release_scratch(void);

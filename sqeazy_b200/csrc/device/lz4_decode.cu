@@ -320,7 +320,8 @@ constexpr uint32_t kWin = 2048;   // output ring bytes per warp
 constexpr uint32_t kRing = 1024;  // compressed-stream ring per warp (two 512-byte chunks)
 constexpr int kWinWarps = 8;
 constexpr size_t kWinWarpSmem = kWin + kRing;
-constexpr uint32_t kNear = kWin - 64;
+constexpr uint32_t kBatchOut = 512;       // output bytes a batch of sequences may produce before the next flush
+constexpr uint32_t kNear = kWin - kBatchOut - 64;
 
 __device__ __forceinline__ uint4 load_stream_piece(const uint8_t* addr, const uint8_t* sbeg, const uint8_t* send) {
   if (addr >= sbeg && addr + 16 <= send) return __ldg(reinterpret_cast<const uint4*>(addr));
@@ -396,10 +397,191 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
 #define SQYB_W(pos) O.win[(pos) & (kWin - 1)]
   uint32_t ip = shift, op = 0;
   const uint32_t end = shift + csize;
-  uint32_t token = SQYB_RB(ip);
   bool bad = false;
+  // copies one match to output position op (warp-cooperative); false on a malformed stream
+  auto do_match = [&](uint32_t op, uint32_t offset, uint32_t mlen) -> bool {
+    if (offset > op) {
+        // reaches in front of this block: only legal inside a linked frame, after the predecessor is complete
+        if (link == kNoLink || (unsigned long long)(offset - op) > before) { err = kErrBadBlock; return false; }
+        if (!waited) {
+          if (lane == 0) {
+            while (atomicAdd(const_cast<uint32_t*>(done) + link, 0u) == 0u) __nanosleep(100);
+            __threadfence();
+          }
+          waited = true;
+        }
+      }
+      __syncwarp();
+      if (offset <= kNear && offset <= op) {
+        // ---- source inside the ring ----
+        if (mlen <= 32 && offset >= mlen) {
+          if ((uint32_t)lane < mlen) SQYB_W(op + lane) = SQYB_W(op + lane - offset);
+        } else if (offset >= 32) {
+          for (uint32_t kb = 0; kb < mlen; kb += 32) {
+            const uint32_t k = kb + lane;
+            if (k < mlen) SQYB_W(op + k) = SQYB_W(op + k - offset);
+            const uint32_t step = mlen - kb < 32u ? mlen - kb : 32u;
+            O.flush_to(op + kb + step);
+            __syncwarp();                 // orders overlapping steps
+          }
+        } else if (mlen >= 256 && (offset == 1 || offset == 2 || offset == 4)) {
+          // run fill: for a period dividing 4 every 4-byte aligned output word holds the same value
+          const uint32_t al = (op + 3u) & ~3u;          // first aligned output position
+          const uint32_t om = offset - 1u;              // period is a power of two: modulo = mask
+          uint32_t word = 0;
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) word |= (uint32_t)SQYB_W(op - offset + ((al - op + j) & om)) << (8 * j);
+          const uint32_t head = al - op;                // < 4 <= mlen
+          if ((uint32_t)lane < head) SQYB_W(op + lane) = SQYB_W(op - offset + (lane & om));
+          const uint32_t body = (mlen - head) >> 2;     // whole words
+          for (uint32_t wb = 0; wb < body; wb += 32) {
+            const uint32_t w = wb + lane;
+            if (w < body) *reinterpret_cast<uint32_t*>(O.win + ((al + 4u * w) & (kWin - 1))) = word;
+            const uint32_t stepw = body - wb < 32u ? body - wb : 32u;
+            O.flush_to(al + 4u * (wb + stepw));
+          }
+          const uint32_t donew = head + (body << 2);
+          if ((uint32_t)lane < mlen - donew) {
+            const uint32_t k = donew + lane;
+            SQYB_W(op + k) = (uint8_t)(word >> (8 * ((k - head) & 3u)));
+          }
+        } else if ((offset & (offset - 1u)) == 0u && mlen < 1024u) {
+          // period 1, 2, 4, 8 or 16: k mod offset is a mask (the common case: byte runs and 16/32-bit periodic data)
+          const uint32_t base = op - offset, om = offset - 1u;
+          for (uint32_t kb = 0; kb < mlen; kb += 32) {
+            const uint32_t k = kb + lane;
+            if (k < mlen) SQYB_W(op + k) = SQYB_W(base + (k & om));
+            if (kb + 32u < mlen) O.flush_to(op + kb + 32u);
+          }
+        } else {
+          // any other short period (or a long match with period 8/16). The pattern [op-offset, op) repeats; the first D bytes
+          // (D = smallest multiple of the period >= 32) are taken from it, everything after that is a copy from D bytes
+          // back, i.e. from an earlier 32-byte step — the ring may wrap over the original pattern on long matches.
+          const uint32_t base = op - offset;
+          const uint32_t D = offset * ((31u + offset) / offset);
+          const float inv = __frcp_rn((float)offset);
+          for (uint32_t kb = 0; kb < mlen; kb += 32) {
+            const uint32_t k = kb + lane;
+            if (k < mlen) {
+              uint32_t src = op + k - D;
+              if (k < D) src = base + (k - offset * (uint32_t)__float2int_rz(((float)k + 0.5f) * inv));   // k < 62: exact
+              SQYB_W(op + k) = SQYB_W(src);
+            }
+            const uint32_t step = mlen - kb < 32u ? mlen - kb : 32u;
+            O.flush_to(op + kb + step);
+            __syncwarp();
+          }
+        }
+      } else {
+        // ---- far source (already flushed) or bytes in front of a linked block: L1-bypassing global loads ----
+        O.flush_to(op);   // make sure everything up to the last complete chunk is in global memory
+        for (uint32_t kb = 0; kb < mlen; kb += 32) {
+          const uint32_t k = kb + lane;
+          if (k < mlen) {
+            // may be negative in a linked frame; a short period (only possible when the match starts in front of
+            // the block) repeats the pattern [op-offset, op) so that no lane reads a byte written in this step
+            const long long sp = (long long)op - offset + (offset < 32u ? k % offset : k);
+            uint8_t v;
+            if (sp >= (long long)O.flushed) v = SQYB_W((uint32_t)sp);   // unflushed tail
+            else v = __ldcg(O.d + sp);
+            SQYB_W(op + k) = v;
+          }
+          const uint32_t step = mlen - kb < 32u ? mlen - kb : 32u;
+          O.flush_to(op + kb + step);
+          __syncwarp();
+        }
+      }
+    return true;
+  };
   while (ip < end) {
     ensure(ip);
+    // ---- batch of sequences. The token chain is serial, but a sequence header is only a few bytes: lane j parses the
+    // bytes at ip+j AS IF a token started there (token, one optional length byte each, offset), all 32 candidates in
+    // parallel; the real chain is then followed from lane 0 with one shuffle per sequence (next token = candidate
+    // lane `qrel`), which also hands every sequence its output position. Then the owners copy their literals in
+    // parallel and the matches are replayed in order. A sequence is "simple" (batchable) when it has at most 32
+    // literals, length chains of at most one byte (lengths < 270) and lies inside the resident compressed window;
+    // everything else — and any batch that would write more than kBatchOut bytes, which keeps near sources inside the
+    // output ring without a flush — goes through the single-sequence path below.
+    const uint32_t ringend = (cur + 2u) * 512u;
+    uint32_t my_lits, my_lit, my_mlen, my_off, my_q, my_mo = 0;
+    bool my_simple = true, my_fin;
+    {
+      const uint32_t pos = ip + lane;
+      const uint32_t token = SQYB_RB(pos);
+      uint32_t q = pos + 1u;
+      my_lit = token >> 4;
+      uint32_t ml = token & 15u;
+      if (my_lit == 15u) { const uint32_t x = SQYB_RB(q); q++; my_lit += x; my_simple = x != 255u; }
+      my_lits = q;
+      q += my_lit;
+      my_fin = q == end;
+      my_off = SQYB_RB(q) | (SQYB_RB(q + 1u) << 8);
+      if (!my_fin) {
+        q += 2u;
+        if (ml == 15u) { const uint32_t x = SQYB_RB(q); q++; ml += x; my_simple = my_simple && x != 255u; }
+        ml += 4u;
+      } else {
+        ml = 0u;
+      }
+      my_mlen = ml;
+      my_q = q - ip;                                   // where the next token starts, relative to ip (< 32+1+1+32+2+1)
+      my_simple = my_simple && my_lit <= 32u && q <= ringend && (my_fin || q < end);
+    }
+    const uint32_t my_pack = my_q | ((my_lit + my_mlen) << 8) | (my_simple ? 1u << 20 : 0u) | (my_fin ? 1u << 21 : 0u);
+    uint32_t c = 0, o = op, n = 0, pnext = 0;
+    bool last = false;
+    uint32_t owners = 0;
+    while (c < 32u) {
+      const uint32_t pk = __shfl_sync(0xffffffffu, my_pack, c);
+      const uint32_t tot = (pk >> 8) & 0xfffu;
+      if (!(pk & (1u << 20)) || o - op + tot > kBatchOut) break;
+      if ((uint32_t)lane == c) my_mo = o + my_lit;
+      owners |= 1u << c;
+      o += tot;
+      n++;
+      pnext = pk & 0xffu;
+      if (pk & (1u << 21)) { last = true; break; }
+      c = pnext;
+    }
+    if (n > 0u) {
+      if (o > O.dcap) { err = kErrBadBlock; return op; }
+      // literals: the owner lane of every sequence copies its literals
+      if ((owners >> lane) & 1u) {
+        const uint32_t dst0 = my_mo - my_lit;
+        for (uint32_t k = 0; k < my_lit; ++k) SQYB_W(dst0 + k) = (uint8_t)SQYB_RB(my_lits + k);
+      }
+      __syncwarp();
+      // matches, in stream order (= lane order of the owners)
+      uint32_t todo = owners;
+      if (last) todo &= ~(0x80000000u >> __clz(owners));   // the final sequence has no match
+      while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const uint32_t mo = __shfl_sync(0xffffffffu, my_mo, i), offset = __shfl_sync(0xffffffffu, my_off, i),
+                       mlen = __shfl_sync(0xffffffffu, my_mlen, i);
+        bad |= offset == 0;
+        if (offset <= kNear && offset <= mo && mlen <= 32u) {
+          // the common case, in one step: k mod offset only matters when the match overlaps itself
+          uint32_t k = lane;
+          if (offset < mlen) {
+            if ((offset & (offset - 1u)) == 0u) k = lane & (offset - 1u);
+            else k = lane - offset * (uint32_t)__float2int_rz(((float)lane + 0.5f) * __frcp_rn((float)offset));
+          }
+          if ((uint32_t)lane < mlen) SQYB_W(mo + lane) = SQYB_W(mo - offset + k);
+        } else if (!do_match(mo, offset, mlen)) {
+          return op;
+        }
+        __syncwarp();
+      }
+      op = o;
+      ip += pnext;
+      O.flush_to(op);
+      if (O.overflow) { err = kErrBadBlock; return op; }
+      continue;
+    }
+    // ---- single sequence (long literal run, long match, or a sequence that crosses the resident window) ----
+    uint32_t token = SQYB_RB(ip);
     ip++;
     uint32_t lit = token >> 4;
     if (lit == 15) {
@@ -413,17 +595,13 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
       } while (b == 255);
     }
     if (lit) {
-      if (lit <= 32) {
-        if ((uint32_t)lane < lit) SQYB_W(op + lane) = (uint8_t)SQYB_RB(ip + lane);
-      } else {
-        if (ip + lit > end || op + lit > O.dcap) { err = kErrBadBlock; return op; }
-        const bool in_ring = ip + lit <= (cur + 2) * 512u;
-        for (uint32_t kb = 0; kb < lit; kb += 32) {
-          const uint32_t k = kb + lane;
-          if (k < lit) SQYB_W(op + k) = in_ring ? (uint8_t)SQYB_RB(ip + k) : __ldg(A + ip + k);
-          const uint32_t step = lit - kb < 32u ? lit - kb : 32u;
-          O.flush_to(op + kb + step);
-        }
+      if (ip + lit > end || op + lit > O.dcap) { err = kErrBadBlock; return op; }
+      const bool in_ring = ip + lit <= (cur + 2) * 512u;
+      for (uint32_t kb = 0; kb < lit; kb += 32) {
+        const uint32_t k = kb + lane;
+        if (k < lit) SQYB_W(op + k) = in_ring ? (uint8_t)SQYB_RB(ip + k) : __ldg(A + ip + k);
+        const uint32_t step = lit - kb < 32u ? lit - kb : 32u;
+        O.flush_to(op + kb + step);
       }
       op += lit;
       ip += lit;
@@ -445,98 +623,9 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
     }
     mlen += 4;
     bad |= offset == 0;
-    token = SQYB_RB(ip);  // next token: chunk cur+1 is always resident, so this read is safe before ensure()
-    if (offset > op) {
-      // reaches in front of this block: only legal inside a linked frame, after the predecessor is complete
-      if (link == kNoLink || (unsigned long long)(offset - op) > before) { err = kErrBadBlock; return op; }
-      if (!waited) {
-        if (lane == 0) {
-          while (atomicAdd(const_cast<uint32_t*>(done) + link, 0u) == 0u) __nanosleep(100);
-          __threadfence();
-        }
-        waited = true;
-      }
-    }
+    if (op + mlen > O.dcap) { err = kErrBadBlock; return op; }
     __syncwarp();
-    if (offset <= kNear && offset <= op) {
-      // ---- source inside the ring ----
-      if (mlen <= 32 && offset >= mlen) {
-        if ((uint32_t)lane < mlen) SQYB_W(op + lane) = SQYB_W(op + lane - offset);
-      } else if (offset >= 32) {
-        for (uint32_t kb = 0; kb < mlen; kb += 32) {
-          const uint32_t k = kb + lane;
-          if (k < mlen) SQYB_W(op + k) = SQYB_W(op + k - offset);
-          const uint32_t step = mlen - kb < 32u ? mlen - kb : 32u;
-          O.flush_to(op + kb + step);
-          __syncwarp();                 // orders overlapping steps
-        }
-      } else if (mlen >= 256 && (offset == 1 || offset == 2 || offset == 4)) {
-        // run fill: for a period dividing 4 every 4-byte aligned output word holds the same value
-        const uint32_t al = (op + 3u) & ~3u;          // first aligned output position
-        const uint32_t om = offset - 1u;              // period is a power of two: modulo = mask
-        uint32_t word = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) word |= (uint32_t)SQYB_W(op - offset + ((al - op + j) & om)) << (8 * j);
-        const uint32_t head = al - op;                // < 4 <= mlen
-        if ((uint32_t)lane < head) SQYB_W(op + lane) = SQYB_W(op - offset + (lane & om));
-        const uint32_t body = (mlen - head) >> 2;     // whole words
-        for (uint32_t wb = 0; wb < body; wb += 32) {
-          const uint32_t w = wb + lane;
-          if (w < body) *reinterpret_cast<uint32_t*>(O.win + ((al + 4u * w) & (kWin - 1))) = word;
-          const uint32_t stepw = body - wb < 32u ? body - wb : 32u;
-          O.flush_to(al + 4u * (wb + stepw));
-        }
-        const uint32_t donew = head + (body << 2);
-        if ((uint32_t)lane < mlen - donew) {
-          const uint32_t k = donew + lane;
-          SQYB_W(op + k) = (uint8_t)(word >> (8 * ((k - head) & 3u)));
-        }
-      } else if ((offset & (offset - 1u)) == 0u && mlen < 1024u) {
-        // period 1, 2, 4, 8 or 16: k mod offset is a mask (the common case: byte runs and 16/32-bit periodic data)
-        const uint32_t base = op - offset, om = offset - 1u;
-        for (uint32_t kb = 0; kb < mlen; kb += 32) {
-          const uint32_t k = kb + lane;
-          if (k < mlen) SQYB_W(op + k) = SQYB_W(base + (k & om));
-          if (kb + 32u < mlen) O.flush_to(op + kb + 32u);
-        }
-      } else {
-        // any other short period (or a long match with period 8/16). The pattern [op-offset, op) repeats; the first D bytes
-        // (D = smallest multiple of the period >= 32) are taken from it, everything after that is a copy from D bytes
-        // back, i.e. from an earlier 32-byte step — the ring may wrap over the original pattern on long matches.
-        const uint32_t base = op - offset;
-        const uint32_t D = offset * ((31u + offset) / offset);
-        const float inv = __frcp_rn((float)offset);
-        for (uint32_t kb = 0; kb < mlen; kb += 32) {
-          const uint32_t k = kb + lane;
-          if (k < mlen) {
-            uint32_t src = op + k - D;
-            if (k < D) src = base + (k - offset * (uint32_t)__float2int_rz(((float)k + 0.5f) * inv));   // k < 62: exact
-            SQYB_W(op + k) = SQYB_W(src);
-          }
-          const uint32_t step = mlen - kb < 32u ? mlen - kb : 32u;
-          O.flush_to(op + kb + step);
-          __syncwarp();
-        }
-      }
-    } else {
-      // ---- far source (already flushed) or bytes in front of a linked block: L1-bypassing global loads ----
-      O.flush_to(op);   // make sure everything up to the last complete chunk is in global memory
-      for (uint32_t kb = 0; kb < mlen; kb += 32) {
-        const uint32_t k = kb + lane;
-        if (k < mlen) {
-          // may be negative in a linked frame; a short period (only possible when the match starts in front of
-          // the block) repeats the pattern [op-offset, op) so that no lane reads a byte written in this step
-          const long long sp = (long long)op - offset + (offset < 32u ? k % offset : k);
-          uint8_t v;
-          if (sp >= (long long)O.flushed) v = SQYB_W((uint32_t)sp);   // unflushed tail
-          else v = __ldcg(O.d + sp);
-          SQYB_W(op + k) = v;
-        }
-        const uint32_t step = mlen - kb < 32u ? mlen - kb : 32u;
-        O.flush_to(op + kb + step);
-        __syncwarp();
-      }
-    }
+    if (!do_match(op, offset, mlen)) return op;
     op += mlen;
     __syncwarp();
     O.flush_to(op);
@@ -718,7 +807,7 @@ __global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSM) lz4_decode_lanes
   }
 }
 
-__global__ void __launch_bounds__(kWinWarps * 32, 6) lz4_decode_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
+__global__ void __launch_bounds__(kWinWarps * 32, 5) lz4_decode_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
                                                                         uint8_t* __restrict__ dst, DecCtl* ctl, DecTables T) {
   extern __shared__ __align__(16) unsigned char dsm[];
   if (ctl->error) return;
@@ -797,14 +886,16 @@ __global__ void __launch_bounds__(kWinWarps * 32, 6) lz4_decode_kernel(const uin
 
 }  // namespace
 
-// Blocks that decode to at most this many bytes go to the lane-serial decoder (this library's 16 KiB blocks, liblz4's
-// 64 KiB blocks). SQYB_LZ4_LANE_MAX overrides it (0 = warp-per-block decoder only), for measurements.
+// Independent blocks that decode to at most this many bytes go to the lane-serial decoder. Default 0 = off: measured on
+// B200 (profiles/README.md) it needs ~2.5x fewer instructions than the warp decoder but runs at 8-12 of 32 lanes and
+// has too few independent streams to hide its latencies (one lane per 16 KiB block), so it is slower at every size
+// tried. SQYB_LZ4_LANE_MAX / sqyx_set_lz4_lane_max() switch it on for measurements and tests.
 static std::atomic<long> g_lane_max{-1};
 static uint32_t lane_max_bytes() {
   long v = g_lane_max.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = std::getenv("SQYB_LZ4_LANE_MAX");
-    v = e ? std::strtol(e, nullptr, 10) : 65536;
+    v = e ? std::strtol(e, nullptr, 10) : 0;
     if (v < 0) v = 0;
     g_lane_max.store(v, std::memory_order_relaxed);
   }
@@ -846,10 +937,13 @@ int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t 
   lz4_classify_kernel<<<kNumSMs * 8, 256, 0, st>>>(src, dst, ctl, T, lane_max_bytes());
   const size_t lane_smem = 32 * sizeof(uint32_t) * kLaneThreads;
   SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_decode_lanes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  lz4_decode_lanes_kernel<<<kNumSMs * kLaneCtasPerSM, kLaneThreads, lane_smem, st>>>(src, src_bytes, dst, ctl, T);
+  if (lane_max_bytes() > 0) {
+    lz4_decode_lanes_kernel<<<kNumSMs * kLaneCtasPerSM, kLaneThreads, lane_smem, st>>>(src, src_bytes, dst, ctl, T);
+    SQYB_COUNT_LAUNCH(1);
+  }
   const size_t win_smem = kWinWarps * kWinWarpSmem;
-  lz4_decode_kernel<<<kNumSMs * 6, kWinWarps * 32, win_smem, st>>>(src, src_bytes, dst, ctl, T);
-  SQYB_COUNT_LAUNCH(6);
+  lz4_decode_kernel<<<kNumSMs * 5, kWinWarps * 32, win_smem, st>>>(src, src_bytes, dst, ctl, T);
+  SQYB_COUNT_LAUNCH(5);
   return (int)cudaGetLastError();
 }
 
