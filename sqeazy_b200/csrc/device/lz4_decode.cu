@@ -45,6 +45,9 @@ struct DecCtl {          // lives at the start of the workspace
   uint32_t nwork;        // blocks queued for the lane-serial decoder
   uint32_t ticket_lane;
   uint32_t nwarp;        // blocks left to the warp-per-block decoder
+  // fast path: the stream is exactly one frame of this library -> the block table is built by many CTAs
+  uint32_t fast, fast_nblk, fast_bb, fast_pad;
+  unsigned long long fast_idx, fast_first, fast_raw;
   unsigned long long total_decoded;
 };
 
@@ -96,6 +99,7 @@ __device__ __forceinline__ unsigned long long block_scan_incl(unsigned long long
 
 constexpr int kDirThreads = 1024;
 constexpr int kPerThread = 16;
+constexpr uint32_t kTile = 4096;        // blocks per CTA tile of the fast table build (256 threads x 16)
 
 __global__ void __launch_bounds__(kDirThreads) lz4_directory_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
                                                                     DecCtl* ctl, DecTables T, uint32_t capacity,
@@ -131,7 +135,18 @@ __global__ void __launch_bounds__(kDirThreads) lz4_directory_kernel(const uint8_
                   (unsigned long long)nblk * bb >= raw && (nblk == 0 || (unsigned long long)(nblk - 1) * bb < raw)) {
                 ours = true;
                 if ((unsigned long long)sh_nb + nblk > capacity) sh_err = kErrTooManyBlocks;
-                else {
+                else if (pos == 0 && sh_nb == 0 && fstart + fbytes == src_bytes && nblk >= 2u * kTile && bb <= 65536u) {
+                  // the whole stream is one frame of ours: lz4_tile_sums_kernel + lz4_expand_kernel build the table
+                  ctl->fast = 1u;
+                  ctl->fast_nblk = nblk;
+                  ctl->fast_bb = bb;
+                  ctl->fast_idx = body + sizeof(SqybIndexHeader);
+                  ctl->fast_first = fstart + kLz4FrameHeaderBytes;
+                  ctl->fast_raw = raw;
+                  sh_nb = nblk;
+                  sh_pos = src_bytes;
+                  sh_mode = 2;
+                } else {
                   sh_args[0] = body + sizeof(SqybIndexHeader);   // index words
                   sh_args[1] = fstart + kLz4FrameHeaderBytes;    // first block header
                   sh_args[2] = ((unsigned long long)bb << 32) | nblk;
@@ -657,9 +672,116 @@ __global__ void __launch_bounds__(kDecThreads) lz4_sizes_kernel(const uint8_t* _
   }
 }
 
+// ---- fast table build for a stream that is one frame of this library (everything the encoder writes) ----
+// A single CTA spends ~1 ms on the prefix sum + table stores of a 4 GiB frame (262144 blocks: one SM's store
+// bandwidth); two small multi-CTA kernels do it in a few microseconds: per-tile sums, then every tile adds the sums
+// in front of it, scans its 4096 block sizes in shared memory and writes its table rows with coalesced stores.
+__device__ __forceinline__ uint32_t index_word(const uint8_t* idx, bool aligned, uint32_t i) {
+  return aligned ? __ldg(reinterpret_cast<const uint32_t*>(idx) + i) : rd32(idx + 4ull * i);
+}
+
+__global__ void __launch_bounds__(256) lz4_tile_sums_kernel(const uint8_t* __restrict__ src, const DecCtl* ctl,
+                                                            unsigned long long* __restrict__ tile_sums) {
+  __shared__ uint32_t wsum[8];
+  if (ctl->error || !ctl->fast) return;
+  const uint32_t nblk = ctl->fast_nblk, ntiles = (nblk + kTile - 1) / kTile;
+  const uint8_t* idx = src + ctl->fast_idx;
+  const bool aligned = (((uintptr_t)idx) & 3) == 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t i = t * kTile + k * 256 + tid;
+      if (i < nblk) s += 4u + (index_word(idx, aligned, i) & 0x7FFFFFFFu);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+    __syncthreads();
+    if (lane == 0) wsum[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t x = 0;
+      for (int w = 0; w < 8; ++w) x += wsum[w];
+      tile_sums[t] = x;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) lz4_expand_kernel(const uint8_t* __restrict__ src, DecCtl* ctl, DecTables T,
+                                                         const unsigned long long* __restrict__ tile_sums, uint64_t dst_bytes) {
+  __shared__ uint32_t words[kTile];
+  __shared__ uint32_t pre[kTile];            // exclusive prefix of (4 + size) inside the tile
+  __shared__ unsigned long long red[8];
+  __shared__ uint32_t tsum[256];
+  if (ctl->error || !ctl->fast) return;
+  const uint32_t nblk = ctl->fast_nblk, bb = ctl->fast_bb, ntiles = (nblk + kTile - 1) / kTile;
+  const unsigned long long raw = ctl->fast_raw, first = ctl->fast_first;
+  const uint8_t* idx = src + ctl->fast_idx;
+  const bool aligned = (((uintptr_t)idx) & 3) == 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (blockIdx.x == 0 && tid == 0) {
+    ctl->total_decoded = raw;
+    if (raw > dst_bytes || (raw == 0 && dst_bytes != 0)) ctl->error = kErrSizeMismatch;
+  }
+  for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    // bytes in front of this tile
+    unsigned long long b = 0;
+    for (uint32_t u = tid; u < t; u += 256) b += tile_sums[u];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) b += __shfl_down_sync(0xffffffffu, b, d);
+    __syncthreads();
+    if (lane == 0) red[warp] = b;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t i = t * kTile + k * 256 + tid;
+      words[k * 256 + tid] = i < nblk ? index_word(idx, aligned, i) : 0u;
+    }
+    __syncthreads();
+    unsigned long long base = first;
+    for (int w = 0; w < 8; ++w) base += red[w];
+    // thread-local scan over 16 consecutive blocks, then a scan of the 256 thread totals
+    uint32_t loc[16], s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t i = t * kTile + tid * 16 + k;
+      loc[k] = s;
+      s += i < nblk ? 4u + (words[tid * 16 + k] & 0x7FFFFFFFu) : 0u;
+    }
+    uint32_t incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += x;
+    }
+    if (lane == 31) tsum[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += tsum[w];
+    const uint32_t tbase = wbase + incl - s;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) pre[tid * 16 + k] = tbase + loc[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t j = k * 256 + tid, i = t * kTile + j;
+      if (i < nblk) {
+        T.src_off[i] = base + pre[j] + 4u;
+        T.word[i] = words[j];
+        const unsigned long long rem = raw - (unsigned long long)i * bb;
+        T.dsize[i] = (uint32_t)(rem < bb ? rem : bb);
+        T.link[i] = kNoLink;
+        T.dst_off[i] = (unsigned long long)i * bb;
+        T.done[i] = 0u;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(kDirThreads) lz4_offsets_kernel(DecCtl* ctl, DecTables T, uint64_t dst_bytes) {
   __shared__ unsigned long long warp_sums[32];
-  if (ctl->error) return;
+  if (ctl->error || ctl->fast) return;
   const uint32_t nblk = ctl->nblocks;
   const int tid = threadIdx.x;
   unsigned long long running = 0;
@@ -911,7 +1033,7 @@ size_t k_lz4_decode_capacity(uint64_t dst_bytes) { return (size_t)(dst_bytes / k
 
 size_t k_lz4_decode_workspace_bytes(uint64_t dst_bytes) {
   const size_t cap = k_lz4_decode_capacity(dst_bytes);
-  return 256 + cap * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4) + 256;
+  return 256 + cap * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4) + 8 * (cap / kTile + 2) + 256;
 }
 
 // Enqueues the whole decode; the status lands in workspace (see k_lz4_decode_status).
@@ -929,9 +1051,13 @@ int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t 
   T.link = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
   T.done = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
   T.kind = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
-  T.work = reinterpret_cast<uint32_t*>(p);
+  T.work = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
+  unsigned long long* tile_sums = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(p) + 7) & ~(uintptr_t)7);
+  const uint32_t tiles = (uint32_t)(cap / kTile + 1), tile_grid = tiles < 1024u ? tiles : 1024u;
   SQYB_CUDA_OK(cudaMemsetAsync(ctl, 0, sizeof(DecCtl), st));
   lz4_directory_kernel<<<1, kDirThreads, 0, st>>>(src, src_bytes, ctl, T, (uint32_t)cap, measure_all);
+  lz4_tile_sums_kernel<<<tile_grid, 256, 0, st>>>(src, ctl, tile_sums);
+  lz4_expand_kernel<<<tile_grid, 256, 0, st>>>(src, ctl, T, tile_sums, dst_bytes);
   lz4_sizes_kernel<<<kNumSMs * 4, kDecThreads, 0, st>>>(src, ctl, T);
   lz4_offsets_kernel<<<1, kDirThreads, 0, st>>>(ctl, T, dst_bytes);
   lz4_classify_kernel<<<kNumSMs * 8, 256, 0, st>>>(src, dst, ctl, T, lane_max_bytes());
@@ -943,7 +1069,7 @@ int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t 
   }
   const size_t win_smem = kWinWarps * kWinWarpSmem;
   lz4_decode_kernel<<<kNumSMs * 5, kWinWarps * 32, win_smem, st>>>(src, src_bytes, dst, ctl, T);
-  SQYB_COUNT_LAUNCH(5);
+  SQYB_COUNT_LAUNCH(7);
   return (int)cudaGetLastError();
 }
 

@@ -75,15 +75,18 @@ def test_corrupt_blocks_fail_cleanly(sq, cuda, port, decoder):
     """bit flips inside the compressed blocks: the decode either fails or returns the promised size (LZ4 has no checksum
     here), never crashes or writes out of bounds, and the library keeps working afterwards"""
     rng = np.random.default_rng(99)
-    planes = port.bitswap_encode(1, numpy_volume((4, 256, 256), "ref", index=2)).view(np.uint8)
+    planes = port.bitswap_encode(1, numpy_volume((4, 256, 256), "scmos", index=2)).view(np.uint8)
     payload = sq.lz4_encode_device(dev(cuda, planes)).cpu().numpy()
     nblocks = (planes.size + 16383) // 16384
     first = 8 + 32 + 4 * nblocks + 7     # skippable header + index header + block words + frame header
     failures = 0
-    for trial in range(24):
+    for trial in range(25):
         bad = payload.copy()
-        pos = rng.integers(first, bad.size - 4, size=1 + trial % 5)
-        bad[pos] ^= rng.integers(1, 256, size=pos.size, dtype=np.uint8)
+        if trial < 24:
+            pos = rng.integers(first, bad.size - 4, size=1 + trial % 5)
+            bad[pos] ^= rng.integers(1, 256, size=pos.size, dtype=np.uint8)
+        else:
+            bad[first + 4: first + 4 + 4096] = 0xFF   # length chains that run past every bound: must be refused
         out = cuda.full((planes.size + 4096,), 0x33, dtype=cuda.uint8, device="cuda")
         try:
             sq.lz4_decode_device(dev(cuda, bad), out[: planes.size])
@@ -94,3 +97,24 @@ def test_corrupt_blocks_fail_cleanly(sq, cuda, port, decoder):
     out = cuda.zeros(planes.size, dtype=cuda.uint8, device="cuda")
     assert sq.lz4_decode_device(dev(cuda, payload), out) == planes.size
     assert np.array_equal(out.cpu().numpy(), planes)
+
+
+def test_large_ragged_frame_uses_the_tiled_table_build(sq, cuda):
+    """>= 8192 blocks: the block table comes from lz4_tile_sums_kernel + lz4_expand_kernel (many CTAs) instead of the
+    single-CTA directory scan; ragged block count, short last block, mixed constant / general / stored blocks"""
+    n = 16384 * 8192 + 16384 * 37 + 12345
+    g = cuda.Generator(device="cuda")
+    g.manual_seed(5)
+    a = cuda.zeros(n, dtype=cuda.uint8, device="cuda")
+    # sparse bytes over the first third, noise in the middle of the second third, zeros elsewhere
+    third = n // 3
+    sparse = cuda.rand(third, generator=g, device="cuda") < 0.03
+    a[:third] = sparse.to(cuda.uint8) * cuda.randint(1, 256, (third,), generator=g, device="cuda", dtype=cuda.uint8)
+    a[third + 1000: third + 1000 + (1 << 20)] = cuda.randint(0, 256, (1 << 20,), generator=g, device="cuda", dtype=cuda.uint8)
+    payload = sq.lz4_encode_device(a)
+    st = sq.last_lz4_stats()
+    assert st["general_blocks"] > 1000 and st["constant_blocks"] > 1000 and st["stored_blocks"] > 30
+    out = cuda.full((n + 64,), 0x77, dtype=cuda.uint8, device="cuda")
+    assert sq.lz4_decode_device(payload, out[:n]) == n
+    assert cuda.equal(out[:n], a)
+    assert bool((out[n:] == 0x77).all())
