@@ -514,8 +514,8 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
     // bytes at ip+j AS IF a token started there (token, one optional length byte each, offset), all 32 candidates in
     // parallel; the real chain is then followed from lane 0 with one shuffle per sequence (next token = candidate
     // lane `qrel`), which also hands every sequence its output position. Then the owners copy their literals in
-    // parallel and the matches are replayed in order. A sequence is "simple" (batchable) when it has at most 32
-    // literals, length chains of at most one byte (lengths < 270) and lies inside the resident compressed window;
+    // parallel and the matches are replayed in order. A sequence is "simple" (batchable) when its length chains have
+    // at most one byte (lengths < 270) and it lies inside the resident compressed window;
     // everything else — and any batch that would write more than kBatchOut bytes, which keeps near sources inside the
     // output ring without a flush — goes through the single-sequence path below.
     const uint32_t ringend = (cur + 2u) * 512u;
@@ -540,31 +540,41 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
         ml = 0u;
       }
       my_mlen = ml;
-      my_q = q - ip;                                   // where the next token starts, relative to ip (< 32+1+1+32+2+1)
-      my_simple = my_simple && my_lit <= 32u && q <= ringend && (my_fin || q < end);
+      my_q = q - ip;                                   // where the next token starts, relative to ip (simple: < 31+2+269+2+2)
+      my_simple = my_simple && q <= ringend && (my_fin || q < end);
     }
-    const uint32_t my_pack = my_q | ((my_lit + my_mlen) << 8) | (my_simple ? 1u << 20 : 0u) | (my_fin ? 1u << 21 : 0u);
+    const uint32_t my_pack = (my_q & 0x1ffu) | (((my_lit + my_mlen) & 0x7ffu) << 9) | (my_simple ? 1u << 20 : 0u) | (my_fin ? 1u << 21 : 0u);
     uint32_t c = 0, o = op, n = 0, pnext = 0;
     bool last = false;
     uint32_t owners = 0;
     while (c < 32u) {
       const uint32_t pk = __shfl_sync(0xffffffffu, my_pack, c);
-      const uint32_t tot = (pk >> 8) & 0xfffu;
+      const uint32_t tot = (pk >> 9) & 0x7ffu;
       if (!(pk & (1u << 20)) || o - op + tot > kBatchOut) break;
       if ((uint32_t)lane == c) my_mo = o + my_lit;
       owners |= 1u << c;
       o += tot;
       n++;
-      pnext = pk & 0xffu;
+      pnext = pk & 0x1ffu;
       if (pk & (1u << 21)) { last = true; break; }
       c = pnext;
     }
     if (n > 0u) {
       if (o > O.dcap) { err = kErrBadBlock; return op; }
-      // literals: the owner lane of every sequence copies its literals
-      if ((owners >> lane) & 1u) {
+      // literals: the owner lane of every sequence copies up to 16 of them itself; longer runs (noisy data) are copied
+      // by the whole warp, 32 bytes per step
+      const bool mine = (owners >> lane) & 1u;
+      if (mine && my_lit <= 16u) {
         const uint32_t dst0 = my_mo - my_lit;
         for (uint32_t k = 0; k < my_lit; ++k) SQYB_W(dst0 + k) = (uint8_t)SQYB_RB(my_lits + k);
+      }
+      uint32_t big = __ballot_sync(0xffffffffu, mine && my_lit > 16u);
+      while (big) {
+        const int i = __ffs(big) - 1;
+        big &= big - 1u;
+        const uint32_t lit = __shfl_sync(0xffffffffu, my_lit, i), from = __shfl_sync(0xffffffffu, my_lits, i),
+                       to = __shfl_sync(0xffffffffu, my_mo, i) - lit;
+        for (uint32_t k = lane; k < lit; k += 32u) SQYB_W(to + k) = (uint8_t)SQYB_RB(from + k);
       }
       __syncwarp();
       // matches, in stream order (= lane order of the owners)

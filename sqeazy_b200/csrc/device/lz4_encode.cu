@@ -574,8 +574,8 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
 
 // Compaction (replaces remove_blanks, lz4_utils.hpp:175-190): the byte offset of a block is the prefix sum of
 // (4 + block bytes) over the index words. A single-CTA scan of 262144 words costs 0.23 ms (one SM's latency), so the
-// sum is split: lz4_tile_sums_kernel adds up tiles of 1024 blocks, and every CTA of lz4_scatter_kernel adds the tile
-// sums in front of its tile, scans its own 1024 words in shared memory and then moves its blocks.
+// sum is split over many CTAs: lz4_tile_sums_kernel adds up tiles of 1024 blocks, lz4_block_offsets_kernel adds the
+// tile sums in front of its tile and scans its own 1024 words.
 constexpr int kEncTile = 1024;
 
 __device__ __forceinline__ uint32_t enc_index_word(const uint8_t* idx, bool aligned, uint32_t i) {
@@ -611,21 +611,17 @@ __global__ void __launch_bounds__(256) lz4_tile_sums_kernel(const uint8_t* __res
   }
 }
 
-// moves every block to its final place in the frame: header word + bytes (staged compressed bytes, or the raw input
-// for stored blocks). A CTA per tile of 1024 blocks, a warp per block; 16-byte stores, source words funnel-shifted to
-// the destination's alignment. The CTA of the last tile also writes the EndMark and the sizes.
-__global__ void __launch_bounds__(256) lz4_scatter_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes,
-                                                          const uint8_t* __restrict__ staging, uint8_t* __restrict__ dst,
-                                                          uint32_t nblocks, const unsigned long long* __restrict__ tile_sums,
-                                                          unsigned long long* __restrict__ payload_bytes_out) {
-  __shared__ uint32_t words[kEncTile];
-  __shared__ uint32_t pre[kEncTile];
+// byte offset of every block header (relative to the first one); the CTA of the last tile also writes the EndMark and
+// the sizes
+__global__ void __launch_bounds__(256) lz4_block_offsets_kernel(uint8_t* __restrict__ dst, uint32_t nblocks,
+                                                                const unsigned long long* __restrict__ tile_sums,
+                                                                unsigned long long* __restrict__ offsets,
+                                                                unsigned long long* __restrict__ payload_bytes_out) {
   __shared__ unsigned long long red[8];
   __shared__ uint32_t tsum[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint8_t* idx = dst + kSkippableHeaderBytes + sizeof(SqybIndexHeader);
   const bool aligned = (((uintptr_t)idx) & 3) == 0;
-  const unsigned long long first = lz4_prefix_bytes(nblocks);
   const uint32_t ntiles = (nblocks + kEncTile - 1) / kEncTile;
   for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     unsigned long long bsum = 0;
@@ -635,13 +631,12 @@ __global__ void __launch_bounds__(256) lz4_scatter_kernel(const uint8_t* __restr
     __syncthreads();
     if (lane == 0) red[warp] = bsum;
     // thread-local scan over 4 consecutive blocks + scan of the 256 thread totals
-    uint32_t w4[4], loc[4], s = 0;
+    uint32_t loc[4], s = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t i = t * kEncTile + tid * 4 + k;
-      w4[k] = i < nblocks ? enc_index_word(idx, aligned, i) : 0u;
       loc[k] = s;
-      s += i < nblocks ? 4u + (w4[k] & 0x7FFFFFFFu) : 0u;
+      s += i < nblocks ? 4u + (enc_index_word(idx, aligned, i) & 0x7FFFFFFFu) : 0u;
     }
     uint32_t incl = s;
 #pragma unroll
@@ -653,56 +648,65 @@ __global__ void __launch_bounds__(256) lz4_scatter_kernel(const uint8_t* __restr
     __syncthreads();
     uint32_t wbase = 0;
     for (int w = 0; w < warp; ++w) wbase += tsum[w];
+    unsigned long long base = 0;
+    for (int w = 0; w < 8; ++w) base += red[w];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      words[tid * 4 + k] = w4[k];
-      pre[tid * 4 + k] = wbase + incl - s + loc[k];
+      const uint32_t i = t * kEncTile + tid * 4 + k;
+      if (i < nblocks) offsets[i] = base + wbase + incl - s + loc[k];
     }
-    unsigned long long base = first;
-    for (int w = 0; w < 8; ++w) base += red[w];
-    __syncthreads();
     if (t == ntiles - 1 && tid == 0) {
       uint32_t tot = 0;
       for (int w = 0; w < 8; ++w) tot += tsum[w];
-      const unsigned long long end = base + tot;
+      const unsigned long long end = lz4_prefix_bytes(nblocks) + base + tot;
       for (int k = 0; k < 4; ++k) dst[end + k] = 0;  // EndMark
       *payload_bytes_out = end + 4;
-      const unsigned long long frame_bytes = end + 4 - (first - kLz4FrameHeaderBytes);
+      const unsigned long long frame_bytes = end + 4 - (lz4_prefix_bytes(nblocks) - kLz4FrameHeaderBytes);
       uint8_t* fp = dst + kSkippableHeaderBytes + 24;   // SqybIndexHeader::frame_bytes
       for (int k = 0; k < 8; ++k) fp[k] = (uint8_t)(frame_bytes >> (8 * k));
     }
-    const uint32_t tile_n = nblocks - t * kEncTile < (uint32_t)kEncTile ? nblocks - t * kEncTile : (uint32_t)kEncTile;
-    for (uint32_t j = warp; j < tile_n; j += 8) {
-      const uint32_t b = t * kEncTile + j;
-      const uint32_t word = words[j];
-      const uint32_t nbytes = word & 0x7FFFFFFFu;
-      const uint8_t* from = (word & kLz4StoredFlag) ? src + (uint64_t)b * kB : staging + (uint64_t)b * kB;
-      uint8_t* g = dst + base + pre[j];
-      if (lane < 4) g[lane] = (uint8_t)(word >> (8 * lane));
-      g += 4;
-      uint32_t head = (uint32_t)((16 - ((uintptr_t)g & 15)) & 15);
-      if (head > nbytes) head = nbytes;
-      if ((uint32_t)lane < head) g[lane] = __ldg(from + lane);
-      const uint8_t* f = from + head;
-      uint8_t* o = g + head;
-      const uint32_t rest = nbytes - head;
-      uint32_t nvec = rest >= 24 ? (rest - 8) >> 4 : 0;   // keeps the 5-word read inside the block's bytes
-      const uint32_t sh = ((uintptr_t)f & 3) * 8;
-      const uint32_t* fw = reinterpret_cast<const uint32_t*>((uintptr_t)f & ~(uintptr_t)3);
-      if (reinterpret_cast<const uint8_t*>(fw) < from) nvec = 0;   // never read in front of the block's first byte
-      for (uint32_t v = lane; v < nvec; v += 32) {
-        const uint32_t* q = fw + v * 4;
-        const uint32_t x0 = __ldg(q), x1 = __ldg(q + 1), x2 = __ldg(q + 2), x3 = __ldg(q + 3), x4 = __ldg(q + 4);
-        uint4 val;
-        val.x = __funnelshift_r(x0, x1, sh);
-        val.y = __funnelshift_r(x1, x2, sh);
-        val.z = __funnelshift_r(x2, x3, sh);
-        val.w = __funnelshift_r(x3, x4, sh);
-        reinterpret_cast<uint4*>(o)[v] = val;
-      }
-      for (uint32_t k = (nvec << 4) + lane; k < rest; k += 32) o[k] = __ldg(f + k);
-    }
     __syncthreads();
+  }
+}
+
+// moves every block to its final place in the frame: header word + bytes (staged compressed bytes, or the raw input
+// for stored blocks). A warp per block; 16-byte stores, source words funnel-shifted to the destination's alignment.
+__global__ void __launch_bounds__(256) lz4_scatter_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes,
+                                                          const uint8_t* __restrict__ staging, uint8_t* __restrict__ dst,
+                                                          uint32_t nblocks, const unsigned long long* __restrict__ offsets) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t wpb = blockDim.x >> 5;
+  const uint8_t* idx = dst + kSkippableHeaderBytes + sizeof(SqybIndexHeader);
+  const unsigned long long first = lz4_prefix_bytes(nblocks);
+  for (uint32_t b = blockIdx.x * wpb + (threadIdx.x >> 5); b < nblocks; b += gridDim.x * wpb) {
+    const uint8_t* p = idx + 4ull * b;
+    const uint32_t word = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    const uint32_t nbytes = word & 0x7FFFFFFFu;
+    const uint8_t* from = (word & kLz4StoredFlag) ? src + (uint64_t)b * kB : staging + (uint64_t)b * kB;
+    uint8_t* g = dst + first + offsets[b];
+    if (lane < 4) g[lane] = (uint8_t)(word >> (8 * lane));
+    g += 4;
+    uint32_t head = (uint32_t)((16 - ((uintptr_t)g & 15)) & 15);
+    if (head > nbytes) head = nbytes;
+    if ((uint32_t)lane < head) g[lane] = __ldg(from + lane);
+    const uint8_t* f = from + head;
+    uint8_t* o = g + head;
+    const uint32_t rest = nbytes - head;
+    uint32_t nvec = rest >= 24 ? (rest - 8) >> 4 : 0;   // keeps the 5-word read inside the block's bytes
+    const uint32_t sh = ((uintptr_t)f & 3) * 8;
+    const uint32_t* fw = reinterpret_cast<const uint32_t*>((uintptr_t)f & ~(uintptr_t)3);
+    if (reinterpret_cast<const uint8_t*>(fw) < from) nvec = 0;   // never read in front of the block's first byte
+    for (uint32_t v = lane; v < nvec; v += 32) {
+      const uint32_t* q = fw + v * 4;
+      const uint32_t x0 = __ldg(q), x1 = __ldg(q + 1), x2 = __ldg(q + 2), x3 = __ldg(q + 3), x4 = __ldg(q + 4);
+      uint4 val;
+      val.x = __funnelshift_r(x0, x1, sh);
+      val.y = __funnelshift_r(x1, x2, sh);
+      val.z = __funnelshift_r(x2, x3, sh);
+      val.w = __funnelshift_r(x3, x4, sh);
+      reinterpret_cast<uint4*>(o)[v] = val;
+    }
+    for (uint32_t k = (nvec << 4) + lane; k < rest; k += 32) o[k] = __ldg(f + k);
   }
 }
 
@@ -735,7 +739,7 @@ __global__ void lz4_write_prefix_kernel(uint8_t* dst, uint64_t raw_bytes, uint32
 
 size_t k_lz4_encode_workspace_bytes(uint64_t raw_bytes) {
   const uint64_t nb = lz4_nblocks(raw_bytes);
-  return 256 + 8 * nb + 256 + nb * (uint64_t)kB + 256;   // control | tile sums (8 B per 1024 blocks; sized 8 B per block) | staging (one slot per block)
+  return 256 + 8 * nb + 8 * (nb / kEncTile + 2) + 256 + nb * (uint64_t)kB + 256;   // control | block offsets | tile sums | staging (one slot per block)
 }
 
 // workspace layout: [0,8) payload bytes (u64) | [16,28) block-kind counters | [256, 256+8*nblocks) offsets | staging
@@ -747,7 +751,7 @@ int k_lz4_encode(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* wor
   SQYB_CUDA_OK(cudaMemsetAsync(ws, 0, 64, st));
   unsigned long long* payload = reinterpret_cast<unsigned long long*>(ws);
   unsigned long long* offsets = reinterpret_cast<unsigned long long*>(ws + 256);
-  uint8_t* staging = ws + ((256 + 8ull * nblocks + 255) & ~255ull);
+  uint8_t* staging = ws + ((256 + 8ull * nblocks + 8ull * (nblocks / kEncTile + 2) + 255) & ~255ull);
   lz4_write_prefix_kernel<<<1, 32, 0, st>>>(dst, raw_bytes, nblocks, payload);
   SQYB_COUNT_LAUNCH(1);
   if (nblocks) {
@@ -756,9 +760,12 @@ int k_lz4_encode(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* wor
                                                                     reinterpret_cast<uint32_t*>(ws + 16));
     const uint32_t ntiles = (nblocks + kEncTile - 1) / kEncTile;
     const uint32_t tile_grid = ntiles < (uint32_t)kNumSMs * 8 ? ntiles : (uint32_t)kNumSMs * 8;
-    lz4_tile_sums_kernel<<<tile_grid, 256, 0, st>>>(dst, nblocks, offsets);
-    lz4_scatter_kernel<<<tile_grid, 256, 0, st>>>(src, raw_bytes, staging, dst, nblocks, offsets, payload);
-    SQYB_COUNT_LAUNCH(3);
+    unsigned long long* tile_sums = offsets + nblocks;
+    lz4_tile_sums_kernel<<<tile_grid, 256, 0, st>>>(dst, nblocks, tile_sums);
+    lz4_block_offsets_kernel<<<tile_grid, 256, 0, st>>>(dst, nblocks, tile_sums, offsets, payload);
+    const uint32_t scatter_blocks = (nblocks + 7) / 8 < (uint32_t)kNumSMs * 8 ? (nblocks + 7) / 8 : (uint32_t)kNumSMs * 8;
+    lz4_scatter_kernel<<<scatter_blocks, 256, 0, st>>>(src, raw_bytes, staging, dst, nblocks, offsets);
+    SQYB_COUNT_LAUNCH(4);
   }
   return (int)cudaGetLastError();
 }

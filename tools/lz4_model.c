@@ -12,6 +12,7 @@ static int ext_bytes(int v) { return v < 15 ? 0 : 1 + (v - 15) / 255; }
 static uint32_t ld4(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 
 /* candidates: cand[i] = position or -1. round-based table (positions of earlier rounds) + short offsets */
+static int g_cut = 1 << 30;
 static void find_candidates(const uint8_t* d, int n, int round, int hashlog, int mode, int* cand) {
   int tsize = 1 << hashlog;
   int* tab = malloc(sizeof(int) * tsize);
@@ -57,7 +58,7 @@ static void find_candidates(const uint8_t* d, int n, int round, int hashlog, int
           if (l >= 5) found = i - dd;
         }
         noshort[i] = found < 0;
-        if (found < 0 && c >= 0 && ld4(d + c) == v && !(mode & 128)) found = c; /* 128: short offsets only */
+        if (found < 0 && c >= 0 && ld4(d + c) == v && !(mode & 128) && !((mode & 256) && c / g_cut != i / g_cut)) found = c; /* 256: same sub-block only */ /* 128: short offsets only */
       }
       cand[i] = found;
     }
@@ -74,6 +75,7 @@ static void find_candidates(const uint8_t* d, int n, int round, int hashlog, int
 
 static long encode_block_size(const uint8_t* d, int n, int round, int cut, int hashlog, int mode, long* nseq_out) {
   int* cand = malloc(sizeof(int) * (n + 16));
+  g_cut = cut;
   find_candidates(d, n, round, hashlog, mode, cand);
   long out = 0;
   int anchor = 0, pos = 0;
