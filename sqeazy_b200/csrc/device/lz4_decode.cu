@@ -495,7 +495,9 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
           if (k < mlen) {
             // may be negative in a linked frame; a short period (only possible when the match starts in front of
             // the block) repeats the pattern [op-offset, op) so that no lane reads a byte written in this step
-            const long long sp = (long long)op - offset + (offset < 32u ? k % offset : k);
+            uint32_t kk = k;
+            if (offset < 32u) kk = k % offset;
+            const long long sp = (long long)op - offset + kk;
             uint8_t v;
             if (sp >= (long long)O.flushed) v = SQYB_W((uint32_t)sp);   // unflushed tail
             else v = __ldcg(O.d + sp);
@@ -543,24 +545,25 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
       my_q = q - ip;                                   // where the next token starts, relative to ip (simple: < 31+2+269+2+2)
       my_simple = my_simple && q <= ringend && (my_fin || q < end);
     }
-    const uint32_t my_pack = (my_q & 0x1ffu) | (((my_lit + my_mlen) & 0x7ffu) << 9) | (my_simple ? 1u << 20 : 0u) | (my_fin ? 1u << 21 : 0u);
-    uint32_t c = 0, o = op, n = 0, pnext = 0;
-    bool last = false;
-    uint32_t owners = 0;
+    // chain word: next-token lane (511 for the final sequence: ends the chain) | output bytes (2047 when not simple:
+    // fails the batch-size test); match word: offset | length
+    const uint32_t my_chain = (my_fin ? 511u : (my_q & 0x1ffu)) | ((my_simple ? my_lit + my_mlen : 2047u) << 9);
+    const uint32_t my_match = my_off | (my_mlen << 16);
+    uint32_t c = 0, o = op, owners = 0;
     while (c < 32u) {
-      const uint32_t pk = __shfl_sync(0xffffffffu, my_pack, c);
-      const uint32_t tot = (pk >> 9) & 0x7ffu;
-      if (!(pk & (1u << 20)) || o - op + tot > kBatchOut) break;
+      const uint32_t pk = __shfl_sync(0xffffffffu, my_chain, c);
+      const uint32_t tot = pk >> 9;
+      if (o - op + tot > kBatchOut) break;
       if ((uint32_t)lane == c) my_mo = o + my_lit;
       owners |= 1u << c;
       o += tot;
-      n++;
-      pnext = pk & 0x1ffu;
-      if (pk & (1u << 21)) { last = true; break; }
-      c = pnext;
+      c = pk & 0x1ffu;
     }
-    if (n > 0u) {
+    if (owners) {
       if (o > O.dcap) { err = kErrBadBlock; return op; }
+      const int hi = 31 - __clz(owners);               // the batch's last sequence
+      const uint32_t pnext = __shfl_sync(0xffffffffu, my_q, hi);
+      const bool last = __shfl_sync(0xffffffffu, my_fin ? 1u : 0u, hi) != 0u;
       // literals: the owner lane of every sequence copies up to 16 of them itself; longer runs (noisy data) are copied
       // by the whole warp, 32 bytes per step
       const bool mine = (owners >> lane) & 1u;
@@ -577,23 +580,33 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
         for (uint32_t k = lane; k < lit; k += 32u) SQYB_W(to + k) = (uint8_t)SQYB_RB(from + k);
       }
       __syncwarp();
-      // matches, in stream order (= lane order of the owners)
-      uint32_t todo = owners;
-      if (last) todo &= ~(0x80000000u >> __clz(owners));   // the final sequence has no match
+      // matches, in stream order (= lane order of the owners). Inside a batch no flush is needed and a match has at
+      // most 273 bytes, so the near copies are plain loops over the output ring.
+      uint32_t todo = last ? owners & ~(1u << hi) : owners;   // the block's final sequence has no match
       while (todo) {
         const int i = __ffs(todo) - 1;
         todo &= todo - 1u;
-        const uint32_t mo = __shfl_sync(0xffffffffu, my_mo, i), offset = __shfl_sync(0xffffffffu, my_off, i),
-                       mlen = __shfl_sync(0xffffffffu, my_mlen, i);
-        bad |= offset == 0;
-        if (offset <= kNear && offset <= mo && mlen <= 32u) {
-          // the common case, in one step: k mod offset only matters when the match overlaps itself
-          uint32_t k = lane;
-          if (offset < mlen) {
-            if ((offset & (offset - 1u)) == 0u) k = lane & (offset - 1u);
-            else k = lane - offset * (uint32_t)__float2int_rz(((float)lane + 0.5f) * __frcp_rn((float)offset));
+        const uint32_t mw = __shfl_sync(0xffffffffu, my_match, i), mo = __shfl_sync(0xffffffffu, my_mo, i);
+        const uint32_t offset = mw & 0xffffu, mlen = mw >> 16;
+        bad |= offset == 0u;
+        if (offset <= kNear && offset <= mo) {
+          const uint32_t base = mo - offset;
+          if (offset >= mlen || offset >= 32u) {
+            // a 32-byte step never reads a byte it writes; later steps may read what earlier ones wrote
+            if ((uint32_t)lane < mlen) SQYB_W(mo + lane) = SQYB_W(base + lane);
+            for (uint32_t k = lane + 32u; k < mlen + lane; k += 32u) {   // (same trip count on every lane)
+              __syncwarp();
+              if (k < mlen) SQYB_W(mo + k) = SQYB_W(base + k);
+            }
+          } else if ((offset & (offset - 1u)) == 0u) {
+            // period 1, 2, 4, 8, 16: every byte comes from the pattern in front of the match
+            const uint32_t om = offset - 1u;
+            for (uint32_t k = lane; k < mlen; k += 32u) SQYB_W(mo + k) = SQYB_W(base + (k & om));
+          } else {
+            const float inv = __frcp_rn((float)offset);
+            for (uint32_t k = lane; k < mlen; k += 32u)   // k < 512: the quotient is exact
+              SQYB_W(mo + k) = SQYB_W(base + (k - offset * (uint32_t)__float2int_rz(((float)k + 0.5f) * inv)));
           }
-          if ((uint32_t)lane < mlen) SQYB_W(mo + lane) = SQYB_W(mo - offset + k);
         } else if (!do_match(mo, offset, mlen)) {
           return op;
         }
