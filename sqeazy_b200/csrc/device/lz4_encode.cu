@@ -312,7 +312,19 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
       C1 |= S.segHC1[tid];
       uint32_t Sel = 0;
       unsigned long long lens = 0;       // lengths of the long matches of this segment, 11 bits each, in order
+      // First guess of where the parse enters this segment: if the previous segment ends inside a run with period d
+      // (its last five bytes continue one), the match that covers them runs on to the end of the ones of E_d here. A
+      // segment in the middle of a long run then has nothing to parse (and nothing to measure: every lane of a run
+      // scanning to its end was 5 % of the kernel), and half of the repair parses of the cascade disappear. A wrong
+      // guess is corrected like any other moved entry point.
       int entry = 0, exit_abs = seg_lo + 32;
+      if (lane > 0) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const uint32_t prevE = S.E[d][tid - 1], curE = S.E[d][tid];
+          if ((prevE >> 27) == 31u) entry = max(entry, curE == 0xffffffffu ? 32 : __ffs(~curE) - 1);
+        }
+      }
       bool need = true;
       while (true) {                     // cascade rounds
         int pos = entry, nlong = 0, pj = 0, plen = 0;
