@@ -5,16 +5,23 @@
 // of block-LINKED 256 KiB blocks, encoders/lz4_utils.hpp:99-173).
 //
 // Stages (all on the GPU, no host round trip):
-//   directory : one CTA parses the stream. Our index frame -> block table by a parallel prefix sum;
-//               foreign frames -> thread 0 walks the 4-byte block headers.
+//   directory : one CTA parses the frame structure. A stream that is exactly one frame of this library (the common
+//               case) is handed to lz4_tile_sums_kernel + lz4_expand_kernel, which build the block table from the
+//               index frame with many CTAs; other index frames are scanned in place; foreign frames -> thread 0
+//               walks the 4-byte block headers.
 //   sizes     : only for foreign blocks whose decoded size is not implied (last block of a frame):
 //               a warp per block walks the tokens without copying.
-//   offsets   : one CTA prefix-sums decoded sizes into output offsets and validates the total.
-//   decode    : persistent grid, a warp per block of any size. The last 2 KiB of output live in a
-//               shared-memory ring (match sources), the compressed stream in a 1 KiB ring; complete
-//               512-byte chunks are flushed with 16-byte stores. Far matches and bytes in front of a
-//               linked block are read back from global memory; linked blocks wait on their
-//               predecessor's flag only when a match reaches in front of the block.
+//   offsets   : one CTA prefix-sums decoded sizes into output offsets and validates the total (skipped on the fast path).
+//   classify  : a warp per block: stored blocks are copied, closed-form run blocks filled (16-byte stores); the rest
+//               is queued for the block decoders.
+//   decode    : persistent grid, a warp per block of any size. Sequence headers are parsed 32 at a time (every lane
+//               parses the bytes at ip+lane as if a token started there, the real chain is followed with one shuffle
+//               per sequence), literals are copied by the lanes that own them, matches are replayed in order. The
+//               last 2 KiB of output live in a shared-memory ring (match sources), the compressed stream in a 1 KiB
+//               ring; complete 512-byte chunks are flushed with 16-byte stores. Far matches and bytes in front of a
+//               linked block are read back from global memory; linked blocks wait on their predecessor's flag only
+//               when a match reaches in front of the block.
+//   (lanes)   : optional one-block-per-THREAD decoder (lz4_lane.inl), off by default — see lane_max_bytes().
 #include "common.cuh"
 #include "kernels.h"
 #include "lz4_format.h"

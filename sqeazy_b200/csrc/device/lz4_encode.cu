@@ -13,15 +13,16 @@
 //             bytes after the 4-byte match give a 2-bit length code; a warp's 32 positions are one segment,
 //             so three ballots leave candidate mask + code planes per 32-byte segment
 //   phase B : every THREAD parses its own 32-byte segment greedily with bit operations only (no shuffles,
-//             no shared memory for matches shorter than 7); a match may overshoot into later segments of the
-//             warp's 1 KiB sub-block, whose entry points move until the warp's parse is stable
+//             no shared memory for matches shorter than 7), starting where a run that crosses the segment border
+//             would end; a match may overshoot into later segments of the warp's 1 KiB sub-block, whose entry
+//             points move until the warp's parse is stable (2.7 rounds per warp on bit planes, measured)
 //   phase C : warp scans chain literal carries and encoded sizes (segments without a match hand their
 //             literals to the next sequence)
 //   phase D : every thread emits its own sequences; trailing literals are copied by the thread that owns
 //             the bytes into the sequence that owns them
-//   store   : single-pass decoupled look-back over block sizes gives the final byte offset; the CTA
-//             writes its block header + bytes once, coalesced, straight into the frame (no
-//             remove_blanks pass, no strided scratch)
+//   hand-off: size word into the index frame + compressed bytes into a per-block staging slot (no CTA waits for
+//             another); lz4_tile_sums_kernel + lz4_block_offsets_kernel prefix-sum the sizes over many CTAs and
+//             lz4_scatter_kernel moves every block to its final offset (replaces remove_blanks)
 #include "common.cuh"
 #include "kernels.h"
 #include "lz4_format.h"
