@@ -74,6 +74,17 @@ long sqyx_lz4_bound(long nbytes);
 int sqyx_lz4_encode(const void* d_src, long nbytes, void* d_dst, long dst_capacity, long* payload_bytes, void* stream);
 int sqyx_lz4_decode(const void* d_src, long nbytes, void* d_dst, long dst_bytes, long* decoded_bytes, void* stream);
 
+/* ---- uint8 volumes (the *_UI8 entry points of sqeazy.h on device pointers) ----
+ * pipelines: bitswap1|2|4, remove_background(threshold=N) (alias rmbkrd) -> lz4 | pass_through [-> lz4]
+ * reference: src/sqeazy.cpp:72-106 (encode), :309-335 (decode); encoders/bitplane_reorder_scalar.hpp:27-116 with
+ * raw_type = uint8_t; encoders/remove_background_scheme_impl.hpp:73-95 */
+int sqyx_encode_device_UI8(const char* pipeline, const void* d_src, const long* shape, unsigned shape_size, void* d_dst,
+                           long dst_capacity, long* dst_bytes, void* stream);
+int sqyx_decode_device_UI8(const void* d_blob, long blob_bytes, void* d_dst, long dst_capacity, void* stream);
+int sqyx_bitswap_encode_UI8(int w, const void* d_src, void* d_dst, long n, int threshold, void* stream);
+int sqyx_bitswap_decode_UI8(int w, const void* d_src, void* d_dst, long n, void* stream);
+int sqyx_remove_background_UI8(const void* d_src, void* d_dst, long n, int threshold, void* stream);
+
 /* ---- bookkeeping ---- */
 int sqyx_device_count(void);
 /* makes `device` current for the calling thread inside this library's CUDA runtime instance (one process

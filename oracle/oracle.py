@@ -72,6 +72,24 @@ class Port:
         self.lib.orc_remove_background(_p(a), _p(out), c_uint64(a.size), c_uint16(threshold & 0xFFFF))
         return out
 
+    def bitswap8_encode(self, w: int, a: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint8).ravel()
+        out = np.empty_like(a)
+        assert self.lib.orc_bitswap8_encode(c_int(w), _p(a), _p(out), c_uint64(a.size)) == 0
+        return out
+
+    def bitswap8_decode(self, w: int, a: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint8).ravel()
+        out = np.empty_like(a)
+        assert self.lib.orc_bitswap8_decode(c_int(w), _p(a), _p(out), c_uint64(a.size)) == 0
+        return out
+
+    def remove_background8(self, a: np.ndarray, threshold: int) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        out = np.empty_like(a)
+        self.lib.orc_remove_background8(_p(a), _p(out), c_uint64(a.size), ctypes.c_uint8(threshold & 0xFF))
+        return out
+
     def histogram(self, a: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(a, dtype=np.uint16)
         h = np.zeros(65536, dtype=np.uint32)
@@ -178,6 +196,24 @@ class Ref:
         a = np.ascontiguousarray(a, dtype=np.uint16)
         out = np.zeros_like(a)
         assert self.lib.ref_remove_background(c_int(threshold), _p(a), _p(out), c_long(a.size), c_int(nthreads)) == 0
+        return out
+
+    def bitswap8_encode(self, w, a):
+        a = np.ascontiguousarray(a, dtype=np.uint8).ravel()
+        out = np.zeros_like(a)
+        assert self.lib.ref_bitswap8_encode(c_int(w), _p(a), _p(out), c_long(a.size)) == 0
+        return out
+
+    def bitswap8_decode(self, w, a):
+        a = np.ascontiguousarray(a, dtype=np.uint8).ravel()
+        out = np.zeros_like(a)
+        assert self.lib.ref_bitswap8_decode(c_int(w), _p(a), _p(out), c_long(a.size)) == 0
+        return out
+
+    def remove_background8(self, a, threshold):
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        out = np.zeros_like(a)
+        assert self.lib.ref_remove_background8(c_int(threshold), _p(a), _p(out), c_long(a.size)) == 0
         return out
 
     def darkest_face_supports(self, vol):

@@ -68,6 +68,28 @@ int ref_bitswap_decode(int w, const uint16_t* in, uint16_t* out, long n) {
   return 2;
 }
 
+// ---- uint8 volumes: the same templates instantiated for raw_type = uint8_t (dypeline<uint8_t>, src/sqeazy.cpp:72-106).
+// One thread: the scalar encode read-modify-writes shared output words (bitplane_reorder_scalar.hpp:45-69).
+int ref_bitswap8_encode(int w, const uint8_t* in, uint8_t* out, long n) {
+  uint8_t* end = nullptr;
+  if (w == 1) { sqy::bitswap_scheme<uint8_t, 1> s; s.set_n_threads(1); end = s.encode(in, out, (std::size_t)n); }
+  else if (w == 2) { sqy::bitswap_scheme<uint8_t, 2> s; s.set_n_threads(1); end = s.encode(in, out, (std::size_t)n); }
+  else if (w == 4) { sqy::bitswap_scheme<uint8_t, 4> s; s.set_n_threads(1); end = s.encode(in, out, (std::size_t)n); }
+  else return 2;
+  return end == out + n ? 0 : 1;
+}
+int ref_bitswap8_decode(int w, const uint8_t* in, uint8_t* out, long n) {
+  if (w == 1) { sqy::bitswap_scheme<uint8_t, 1> s; return s.decode(in, out, (std::size_t)n); }
+  if (w == 2) { sqy::bitswap_scheme<uint8_t, 2> s; return s.decode(in, out, (std::size_t)n); }
+  if (w == 4) { sqy::bitswap_scheme<uint8_t, 4> s; return s.decode(in, out, (std::size_t)n); }
+  return 2;
+}
+int ref_remove_background8(int threshold, const uint8_t* in, uint8_t* out, long n) {
+  sqy::remove_background_scheme<uint8_t> s("threshold=" + std::to_string(threshold));
+  s.set_n_threads(1);
+  return s.encode(in, out, (std::size_t)n) == out + n ? 0 : 1;
+}
+
 // ---- background removal --------------------------------------------------
 int ref_remove_background(int threshold, const uint16_t* in, uint16_t* out, long n, int nthreads) {
   sqy::remove_background_scheme<uint16_t> s("threshold=" + std::to_string(threshold));

@@ -61,6 +61,50 @@ int orc_bitswap_decode(int w, const uint16_t* in, uint16_t* out, uint64_t n) {
   return 0;
 }
 
+/* uint8 volumes (dypeline<uint8_t>, src/sqeazy.cpp:72-106): the same scalar template with raw_type = uint8_t
+ * (type_width 8; bitswap_scheme_impl.hpp:106-121 excludes the SSE path for sizeof(raw_type) == 1) */
+int orc_bitswap8_encode(int w, const uint8_t* in, uint8_t* out, uint64_t n) {
+  if (w != 1 && w != 2 && w != 4) return 1;
+  const uint64_t P = 8 / (uint64_t)w;
+  const uint64_t np = n - (n % P);
+  const uint64_t S = np / P;
+  const uint32_t mask = (1u << w) - 1u;
+  for (uint64_t i = 0; i < np; ++i) out[i] = 0;
+  for (uint64_t i = 0; i < np; ++i) {
+    const uint32_t v = in[i];
+    const uint64_t g = i / P, j = i % P;
+    for (uint64_t p = 0; p < P; ++p) {
+      const uint32_t field = (v >> (p * w)) & mask;
+      out[(P - 1 - p) * S + g] |= (uint8_t)(field << ((8 - w) - j * w));
+    }
+  }
+  for (uint64_t i = np; i < n; ++i) out[i] = in[i];
+  return 0;
+}
+
+int orc_bitswap8_decode(int w, const uint8_t* in, uint8_t* out, uint64_t n) {
+  if (w != 1 && w != 2 && w != 4) return 1;
+  const uint64_t P = 8 / (uint64_t)w;
+  const uint64_t np = n - (n % P);
+  const uint64_t S = np / P;
+  const uint32_t mask = (1u << w) - 1u;
+  for (uint64_t i = 0; i < np; ++i) {
+    const uint64_t g = i / P, j = i % P;
+    uint32_t v = 0;
+    for (uint64_t p = 0; p < P; ++p) {
+      const uint32_t word = in[(P - 1 - p) * S + g];
+      v |= ((word >> ((8 - w) - j * w)) & mask) << (p * w);
+    }
+    out[i] = (uint8_t)v;
+  }
+  for (uint64_t i = np; i < n; ++i) out[i] = in[i];
+  return 0;
+}
+
+void orc_remove_background8(const uint8_t* in, uint8_t* out, uint64_t n, uint8_t threshold) {
+  for (uint64_t i = 0; i < n; ++i) out[i] = in[i] > threshold ? (uint8_t)(in[i] - threshold) : 0;
+}
+
 /* ------------------------------------------------------------------------------------------
  * remove_background — encoders/remove_background_scheme_impl.hpp:73-95
  * ------------------------------------------------------------------------------------------ */

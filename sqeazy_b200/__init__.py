@@ -34,7 +34,8 @@ SQYX_SYMBOLS = [
     "sqyx_quantiser_luts", "sqyx_lut_apply_UI16", "sqyx_lut_decode_UI16", "sqyx_lz4_bound", "sqyx_lz4_encode",
     "sqyx_lz4_decode", "sqyx_device_count", "sqyx_kernel_launches", "sqyx_last_lz4_stats", "sqyx_host_l2_bytes",
     "sqyx_release_scratch", "sqyx_set_lz4_lane_max", "sqyx_set_device", "sqyx_enable_stage_timing", "sqyx_stage_ms", "sqyx_histogram_support",
-    "sqyx_rmest_frame_portion",
+    "sqyx_rmest_frame_portion", "sqyx_encode_device_UI8", "sqyx_decode_device_UI8", "sqyx_bitswap_encode_UI8",
+    "sqyx_bitswap_decode_UI8", "sqyx_remove_background_UI8",
 ]
 
 _lib = None
@@ -104,6 +105,47 @@ def encode(pipeline: str, volume: np.ndarray, nthreads: int = 1, out: np.ndarray
     if rc != 0:
         raise SqeazyError(f"SQY_PipelineEncode_UI16({pipeline!r}) returned {rc}")
     return out[: n.value]
+
+
+def max_compressed_length_u8(pipeline: str, raw_bytes: int) -> int:
+    p = pipeline.encode("latin-1")
+    n = c_long(raw_bytes)
+    if lib().SQY_Pipeline_Max_Compressed_Length_UI8(p, c_long(len(p)), ctypes.byref(n)) != 0:
+        raise SqeazyError(f"invalid uint8 pipeline {pipeline!r}")
+    return n.value
+
+
+def max_compressed_length_3d_u8(pipeline: str, shape) -> int:
+    p = pipeline.encode("latin-1")
+    shp = (c_long * len(shape))(*shape)
+    n = c_long(len(p))
+    if lib().SQY_Pipeline_Max_Compressed_Length_3D_UI8(p, shp, c_uint(len(shape)), ctypes.byref(n)) != 0:
+        raise SqeazyError(f"invalid uint8 pipeline {pipeline!r}")
+    return n.value
+
+
+def encode_u8(pipeline: str, volume: np.ndarray, nthreads: int = 1) -> np.ndarray:
+    """SQY_PipelineEncode_UI8: uint8 volume (any rank, C order) -> blob bytes (uint8 array)."""
+    vol = np.ascontiguousarray(volume, dtype=np.uint8)
+    out = np.empty(max_compressed_length_u8(pipeline, vol.nbytes), dtype=np.uint8)
+    shp = (c_long * vol.ndim)(*vol.shape)
+    n = c_long(0)
+    rc = lib().SQY_PipelineEncode_UI8(pipeline.encode("latin-1"), _vp(vol), shp, c_uint(vol.ndim), _vp(out), ctypes.byref(n),
+                                      c_int(nthreads))
+    if rc != 0:
+        raise SqeazyError(f"SQY_PipelineEncode_UI8({pipeline!r}) returned {rc}")
+    return out[: n.value]
+
+
+def decode_u8(blob: np.ndarray, nthreads: int = 1) -> np.ndarray:
+    """SQY_Decode_UI8: blob -> uint8 volume of the shape stored in the header."""
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    shape = decompressed_shape(blob)
+    out = np.empty(decompressed_length(blob), dtype=np.uint8)
+    rc = lib().SQY_Decode_UI8(_vp(blob), c_long(blob.size), _vp(out), c_int(nthreads))
+    if rc != 0:
+        raise SqeazyError(f"SQY_Decode_UI8 returned {rc}")
+    return out.reshape(shape) if shape else out
 
 
 def header_size(blob: np.ndarray) -> int:
@@ -219,6 +261,55 @@ def remove_background_device(src, dst, threshold: int, stream=None):
     rc = lib().sqyx_remove_background_UI16(_dp(src), _dp(dst), c_long(src.numel()), c_int(threshold), _stream_handle(stream))
     if rc != 0:
         raise SqeazyError("sqyx_remove_background_UI16 failed")
+    return dst
+
+
+def encode_device_u8(pipeline: str, volume, out=None, stream=None):
+    """sqyx_encode_device_UI8. volume: CUDA tensor of 8-bit voxels (any rank); returns a uint8 CUDA view of the blob."""
+    import torch
+    assert volume.is_cuda and volume.element_size() == 1 and volume.is_contiguous()
+    cap = max_compressed_length_u8(pipeline, volume.numel())
+    if out is None or out.numel() < cap:
+        out = torch.empty(cap, dtype=torch.uint8, device=volume.device)
+    shp = (c_long * volume.dim())(*volume.shape)
+    n = c_long(0)
+    with torch.cuda.device(volume.device):
+        rc = lib().sqyx_encode_device_UI8(pipeline.encode("latin-1"), _dp(volume), shp, c_uint(volume.dim()), _dp(out),
+                                          c_long(out.numel()), ctypes.byref(n), _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError(f"sqyx_encode_device_UI8({pipeline!r}) returned {rc}")
+    return out[: n.value]
+
+
+def decode_device_u8(blob, out, stream=None):
+    import torch
+    assert blob.is_cuda and out.is_cuda and blob.is_contiguous() and out.is_contiguous()
+    with torch.cuda.device(blob.device):
+        rc = lib().sqyx_decode_device_UI8(_dp(blob), c_long(blob.numel()), _dp(out), c_long(out.numel() * out.element_size()),
+                                          _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError(f"sqyx_decode_device_UI8 returned {rc}")
+    return out
+
+
+def bitswap_encode_device_u8(w: int, src, dst, threshold: int = 0, stream=None):
+    rc = lib().sqyx_bitswap_encode_UI8(c_int(w), _dp(src), _dp(dst), c_long(src.numel()), c_int(threshold), _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError("sqyx_bitswap_encode_UI8 failed")
+    return dst
+
+
+def bitswap_decode_device_u8(w: int, src, dst, stream=None):
+    rc = lib().sqyx_bitswap_decode_UI8(c_int(w), _dp(src), _dp(dst), c_long(src.numel()), _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError("sqyx_bitswap_decode_UI8 failed")
+    return dst
+
+
+def remove_background_device_u8(src, dst, threshold: int, stream=None):
+    rc = lib().sqyx_remove_background_UI8(_dp(src), _dp(dst), c_long(src.numel()), c_int(threshold), _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError("sqyx_remove_background_UI8 failed")
     return dst
 
 

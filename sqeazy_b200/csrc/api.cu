@@ -177,11 +177,15 @@ int estimate_background(Arena& A, const uint16_t* d_src, uint64_t Z, uint64_t Y,
 }
 
 // ---- encode ----
-int encode_device_impl(Arena& A, const Pipeline& pl_in, const uint16_t* d_src, const std::vector<uint64_t>& shape, uint8_t* d_dst,
+int encode_device_impl(Arena& A, const Pipeline& pl_in, const void* d_src_any, const std::vector<uint64_t>& shape, uint8_t* d_dst,
                        uint64_t dst_cap, uint64_t* dst_bytes, const uint32_t* d_global_hist, cudaStream_t st) {
   Pipeline pl = pl_in;
   const uint64_t N = shape_product(shape);
-  const uint64_t raw_bytes = 2 * N;
+  const bool u8 = pl.elem == 1;                       // dypeline<uint8_t>: bitswap / remove_background / lz4 / pass_through only
+  const uint64_t raw_bytes = (uint64_t)pl.elem * N;
+  const uint16_t* d_src = static_cast<const uint16_t*>(d_src_any);   // (typed per stage below)
+  auto b8 = [](const uint16_t* q) { return reinterpret_cast<const uint8_t*>(q); };
+  auto m8 = [](uint16_t* q) { return reinterpret_cast<uint8_t*>(q); };
   const size_t reserve = header_reserve_bytes(pl, shape);
   uint8_t* payload = d_dst + reserve;
   if (dst_cap < reserve) return 1;
@@ -217,14 +221,19 @@ int encode_device_impl(Arena& A, const Pipeline& pl_in, const uint16_t* d_src, c
       }
       if (next_buf(&out)) return 1;
       if (i + 1 < pl.head.size() && pl.head[i + 1].kind == StageKind::Bitswap && t > 0) {
-        CKK(k_bitswap_encode(pl.head[i + 1].w, cur, out, N, t, st));  // filter fused into the transpose
+        // filter fused into the transpose
+        if (u8) CKK(k_bitswap8_encode(pl.head[i + 1].w, b8(cur), m8(out), N, t, st));
+        else CKK(k_bitswap_encode(pl.head[i + 1].w, cur, out, N, t, st));
         ++i;
+      } else if (u8) {
+        CKK(k_remove_background8(b8(cur), m8(out), N, t, st));
       } else {
         CKK(k_remove_background(cur, out, N, t, st));
       }
     } else {  // Bitswap
       if (next_buf(&out)) return 1;
-      CKK(k_bitswap_encode(s.w, cur, out, N, 0, st));
+      if (u8) CKK(k_bitswap8_encode(s.w, b8(cur), m8(out), N, 0, st));
+      else CKK(k_bitswap_encode(s.w, cur, out, N, 0, st));
     }
     cur = out;
   }
@@ -267,6 +276,7 @@ int encode_device_impl(Arena& A, const Pipeline& pl_in, const uint16_t* d_src, c
       payload_bytes = raw_bytes;
     }
   } else {  // Quantiser
+    if (u8) return 1;   // (the planner never builds it for uint8)
     void* sp = nullptr;
     if (A.get(kSlotSmall, 4 * 65536 * sizeof(uint32_t) + 4096, &sp)) return 1;
     uint32_t* d_hist = static_cast<uint32_t*>(sp);
@@ -308,7 +318,7 @@ int encode_device_impl(Arena& A, const Pipeline& pl_in, const uint16_t* d_src, c
   }
 
   // header, right-aligned in its slot (leading blanks are what header::pack itself pads with)
-  const std::string hdr = pack_header("uint16", 2, shape, pl.canonical(), payload_bytes);
+  const std::string hdr = pack_header(pl.type_name(), pl.elem, shape, pl.canonical(), payload_bytes);
   if (hdr.size() > reserve) {
     std::fprintf(stderr, "[sqeazy_b200] header (%zu B) exceeds its slot (%zu B)\n", hdr.size(), reserve);
     return 1;
@@ -348,9 +358,11 @@ int lz4_decode_checked(Arena& A, const uint8_t* src, uint64_t nbytes, uint8_t* d
 }
 
 int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const uint8_t* d_payload, uint64_t payload_bytes,
-                       uint16_t* d_dst, uint64_t dst_cap, cudaStream_t st) {
+                       void* d_dst_any, uint64_t dst_cap, cudaStream_t st) {
   const uint64_t N = shape_product(hdr.shape);
-  const uint64_t raw_bytes = 2 * N;
+  const bool u8 = pl.elem == 1;
+  const uint64_t raw_bytes = (uint64_t)pl.elem * N;
+  uint16_t* d_dst = static_cast<uint16_t*>(d_dst_any);
   if (dst_cap < raw_bytes) return 1;
   if (N == 0) return 0;
 
@@ -395,6 +407,7 @@ int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const ui
         CK(cudaMemcpyAsync(out, d_payload, raw_bytes, cudaMemcpyDeviceToDevice, st));
       }
     } else {  // Quantiser
+      if (u8) return 11;
       if (!pl.sink.has_decode_lut) {
         std::fprintf(stderr, "[sqeazy_b200] quantiser stage without decode_lut_string in the header\n");
         return 11;
@@ -439,7 +452,9 @@ int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const ui
     }
     {
       ScopedStageTimer tm(kTSwapDec, st);
-      if (k_bitswap_decode(swaps[k], cur, out, N, st)) return 100 + 1;
+      if (u8 ? k_bitswap8_decode(swaps[k], reinterpret_cast<const uint8_t*>(cur), reinterpret_cast<uint8_t*>(out), N, st)
+             : k_bitswap_decode(swaps[k], cur, out, N, st))
+        return 100 + 1;
     }
     cur = out;
   }
@@ -564,6 +579,63 @@ int sqyx_decode_device_UI16(const void* d_blob, long blob_bytes, void* d_dst, lo
   } catch (...) {
     return 1;
   }
+}
+
+int sqyx_encode_device_UI8(const char* pipeline, const void* d_src, const long* shape, unsigned shape_size, void* d_dst,
+                           long dst_capacity, long* dst_bytes, void* stream) {
+  try {
+    if (!pipeline || !shape || !d_dst || !dst_bytes || dst_capacity < 0) return 1;
+    Pipeline pl;
+    if (!build_pipeline_u8(pipeline, pl) || pl.empty()) return 1;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Arena* A = nullptr;
+    if (current_arena(&A)) return 1;
+    uint64_t out = 0;
+    const int rc = encode_device_impl(*A, pl, d_src, to_shape(shape, shape_size), static_cast<uint8_t*>(d_dst), (uint64_t)dst_capacity,
+                                      &out, nullptr, static_cast<cudaStream_t>(stream));
+    if (rc == 0) *dst_bytes = (long)out;
+    return rc;
+  } catch (...) {
+    return 1;
+  }
+}
+
+int sqyx_decode_device_UI8(const void* d_blob, long blob_bytes, void* d_dst, long dst_capacity, void* stream) {
+  try {
+    if (!d_blob || blob_bytes <= 0 || !d_dst || dst_capacity < 0) return 1;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Arena* A = nullptr;
+    if (current_arena(&A)) return 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Header hdr;
+    if (parse_blob_header_device(static_cast<const uint8_t*>(d_blob), (uint64_t)blob_bytes, hdr, st)) return 1;
+    if (sizeof_typename(hdr.raw_type) != 1) return 1;
+    Pipeline pl;
+    if (!build_pipeline_u8(hdr.pipeline, pl) || pl.empty()) {
+      std::fprintf(stderr, "[sqeazy]\t%s cannot be build with this version of sqeazy\n", hdr.pipeline.c_str());
+      return 1;
+    }
+    return decode_device_impl(*A, hdr, pl, static_cast<const uint8_t*>(d_blob) + hdr.size, (uint64_t)blob_bytes - hdr.size, d_dst,
+                              (uint64_t)dst_capacity, st);
+  } catch (...) {
+    return 1;
+  }
+}
+
+int sqyx_bitswap_encode_UI8(int w, const void* d_src, void* d_dst, long n, int threshold, void* stream) {
+  if (n < 0) return 1;
+  return k_bitswap8_encode(w, static_cast<const uint8_t*>(d_src), static_cast<uint8_t*>(d_dst), (uint64_t)n, threshold,
+                           static_cast<cudaStream_t>(stream)) ? 1 : 0;
+}
+int sqyx_bitswap_decode_UI8(int w, const void* d_src, void* d_dst, long n, void* stream) {
+  if (n < 0) return 1;
+  return k_bitswap8_decode(w, static_cast<const uint8_t*>(d_src), static_cast<uint8_t*>(d_dst), (uint64_t)n,
+                           static_cast<cudaStream_t>(stream)) ? 1 : 0;
+}
+int sqyx_remove_background_UI8(const void* d_src, void* d_dst, long n, int threshold, void* stream) {
+  if (n < 0) return 1;
+  return k_remove_background8(static_cast<const uint8_t*>(d_src), static_cast<uint8_t*>(d_dst), (uint64_t)n, threshold,
+                              static_cast<cudaStream_t>(stream)) ? 1 : 0;
 }
 
 int sqyx_bitswap_encode_UI16(int w, const void* d_src, void* d_dst, long n, int threshold, void* stream) {
@@ -734,9 +806,15 @@ bool SQY_Pipeline_Possible_UI16(const char* pipeline) {
     return false;
   }
 }
-bool SQY_Pipeline_Possible_UI8(const char*) { return false; }  // uint8 volumes: outside the accelerated path
-bool SQY_Pipeline_Possible(const char* pipeline, int sizeofpixel) {
-  return sizeofpixel == 2 ? SQY_Pipeline_Possible_UI16(pipeline) : false;
+bool SQY_Pipeline_Possible_UI8(const char* pipeline) {
+  try {
+    return pipeline ? pipeline_possible_u8(pipeline) : false;
+  } catch (...) {
+    return false;
+  }
+}
+bool SQY_Pipeline_Possible(const char* pipeline, int sizeofpixel) {   // src/sqeazy.cpp:254-268
+  return sizeofpixel == 2 ? SQY_Pipeline_Possible_UI16(pipeline) : (sizeofpixel == 1 ? SQY_Pipeline_Possible_UI8(pipeline) : false);
 }
 
 int SQY_Pipeline_Max_Compressed_Length_UI16(const char* pipeline, long pipeline_length, long* length) {
@@ -765,22 +843,42 @@ int SQY_Pipeline_Max_Compressed_Length_3D_UI16(const char* pipeline, long* shape
   }
 }
 
-int SQY_Pipeline_Max_Compressed_Length_UI8(const char*, long, long*) { return 1; }
-int SQY_Pipeline_Max_Compressed_Length_3D_UI8(const char*, long*, unsigned, long*) { return 1; }
+int SQY_Pipeline_Max_Compressed_Length_UI8(const char* pipeline, long pipeline_length, long* length) {   // src/sqeazy.cpp:144-163
+  try {
+    if (!pipeline || !length || pipeline_length < 0 || *length < 0) return 1;
+    Pipeline pl;
+    if (!build_pipeline_u8(std::string(pipeline, (size_t)pipeline_length), pl) || pl.empty()) return 1;
+    *length = (long)max_encoded_size_u16(pl, (uint64_t)*length);
+    return 0;
+  } catch (...) {
+    return 1;
+  }
+}
+int SQY_Pipeline_Max_Compressed_Length_3D_UI8(const char* pipeline, long* shape, unsigned shape_size, long* length) {   // :209-231
+  try {
+    if (!pipeline || !length || !shape || *length < 0) return 1;
+    Pipeline pl;
+    if (!build_pipeline_u8(std::string(pipeline, (size_t)*length), pl) || pl.empty()) return 1;
+    uint64_t n = 1;
+    for (unsigned i = 0; i < shape_size; ++i) n *= (uint64_t)shape[i];
+    *length = (long)max_encoded_size_u16(pl, n);
+    return 0;
+  } catch (...) {
+    return 1;
+  }
+}
 
-int SQY_PipelineEncode_UI16(const char* pipeline, const char* src, long* shape, unsigned shape_size, char* dst, long* dstlength,
-                            int nthreads) {
-  (void)nthreads;  // accepted for compatibility; the GPU path has no thread knob
+static int host_encode(int elem, const char* pipeline, const char* src, long* shape, unsigned shape_size, char* dst, long* dstlength) {
   try {
     if (!pipeline || !src || !shape || !dst || !dstlength) return 1;
     Pipeline pl;
-    if (!build_pipeline_u16(pipeline, pl)) return 1;
+    if (!(elem == 1 ? build_pipeline_u8(pipeline, pl) : build_pipeline_u16(pipeline, pl))) return 1;
     if (pl.empty()) {
       std::fprintf(stderr, "[sqeazy]\t received pipeline of size 0, cannot encode buffer\n");
       return 1;
     }
     const std::vector<uint64_t> shp = to_shape(shape, shape_size);
-    const uint64_t N = shape_product(shp), raw_bytes = 2 * N;
+    const uint64_t N = shape_product(shp), raw_bytes = (uint64_t)elem * N;
     const uint64_t cap = max_encoded_size_u16(pl, raw_bytes);
     std::lock_guard<std::mutex> lk(g_mu);
     Arena* A = nullptr;
@@ -790,7 +888,7 @@ int SQY_PipelineEncode_UI16(const char* pipeline, const char* src, long* shape, 
     cudaStream_t st = nullptr;
     if (raw_bytes) CK(cudaMemcpyAsync(d_in, src, raw_bytes, cudaMemcpyHostToDevice, st));
     uint64_t out = 0;
-    const int rc = encode_device_impl(*A, pl, static_cast<const uint16_t*>(d_in), shp, static_cast<uint8_t*>(d_out), cap, &out,
+    const int rc = encode_device_impl(*A, pl, d_in, shp, static_cast<uint8_t*>(d_out), cap, &out,
                                       nullptr, st);
     if (rc) return 1;
     CK(cudaMemcpyAsync(dst, d_out, out, cudaMemcpyDeviceToHost, st));
@@ -802,14 +900,13 @@ int SQY_PipelineEncode_UI16(const char* pipeline, const char* src, long* shape, 
   }
 }
 
-int SQY_Decode_UI16(const char* src, long srclength, char* dst, int nthreads) {
-  (void)nthreads;
+static int host_decode(int elem, const char* src, long srclength, char* dst) {
   try {
     if (!src || !dst || srclength <= 0) return 1;
     const Header hdr = unpack_header(src, (size_t)srclength);
     if (!hdr.valid) return 1;
     Pipeline pl;
-    if (!build_pipeline_u16(hdr.pipeline, pl)) {
+    if (!(elem == 1 ? build_pipeline_u8(hdr.pipeline, pl) : build_pipeline_u16(hdr.pipeline, pl))) {
       std::fprintf(stderr, "[sqeazy]\t%s cannot be build with this version of sqeazy\n", hdr.pipeline.c_str());
       return 1;
     }
@@ -817,8 +914,8 @@ int SQY_Decode_UI16(const char* src, long srclength, char* dst, int nthreads) {
       std::fprintf(stderr, "[sqeazy]\t received pipeline of size 0, no decoding possible\n");
       return 1;
     }
-    if (sizeof_typename(hdr.raw_type) != 2) return 1;
-    const uint64_t raw_bytes = 2 * shape_product(hdr.shape);
+    if (sizeof_typename(hdr.raw_type) != (unsigned)elem) return 1;
+    const uint64_t raw_bytes = (uint64_t)elem * shape_product(hdr.shape);
     std::lock_guard<std::mutex> lk(g_mu);
     Arena* A = nullptr;
     if (current_arena(&A)) return 1;
@@ -828,7 +925,7 @@ int SQY_Decode_UI16(const char* src, long srclength, char* dst, int nthreads) {
     if (A->get(kSlotIn, payload_bytes + 256, &d_in) || A->get(kSlotOut, raw_bytes, &d_out)) return 1;
     cudaStream_t st = nullptr;
     if (payload_bytes) CK(cudaMemcpyAsync(d_in, src + hdr.size, payload_bytes, cudaMemcpyHostToDevice, st));
-    const int rc = decode_device_impl(*A, hdr, pl, static_cast<const uint8_t*>(d_in), payload_bytes, static_cast<uint16_t*>(d_out),
+    const int rc = decode_device_impl(*A, hdr, pl, static_cast<const uint8_t*>(d_in), payload_bytes, d_out,
                                       raw_bytes, st);
     if (rc) return rc;
     if (raw_bytes) CK(cudaMemcpyAsync(dst, d_out, raw_bytes, cudaMemcpyDeviceToHost, st));
@@ -839,12 +936,31 @@ int SQY_Decode_UI16(const char* src, long srclength, char* dst, int nthreads) {
   }
 }
 
+int SQY_PipelineEncode_UI16(const char* pipeline, const char* src, long* shape, unsigned shape_size, char* dst, long* dstlength,
+                            int nthreads) {
+  (void)nthreads;  // accepted for compatibility; the GPU path has no thread knob
+  return host_encode(2, pipeline, src, shape, shape_size, dst, dstlength);
+}
+
+int SQY_Decode_UI16(const char* src, long srclength, char* dst, int nthreads) {
+  (void)nthreads;
+  return host_decode(2, src, srclength, dst);
+}
+
 int SQY_PipelineDecode_UI16(const char* src, long srclength, char* dst, int nthreads) {
   return SQY_Decode_UI16(src, srclength, dst, nthreads);
 }
 
-int SQY_PipelineEncode_UI8(const char*, const char*, long*, unsigned, char*, long*, int) { return 1; }
-int SQY_Decode_UI8(const char*, long, char*, int) { return 1; }
+// uint8 volumes (src/sqeazy.cpp:72-106, 309-335)
+int SQY_PipelineEncode_UI8(const char* pipeline, const char* src, long* shape, unsigned shape_size, char* dst, long* dstlength,
+                           int nthreads) {
+  (void)nthreads;
+  return host_encode(1, pipeline, src, shape, shape_size, dst, dstlength);
+}
+int SQY_Decode_UI8(const char* src, long srclength, char* dst, int nthreads) {
+  (void)nthreads;
+  return host_decode(1, src, srclength, dst);
+}
 
 int SQY_h5_query_sizeof(const char*, const char*, unsigned*) { return 1; }
 int SQY_h5_query_dtype(const char*, const char*, unsigned*) { return 1; }

@@ -18,6 +18,11 @@ int k_bitswap_encode(int w, const uint16_t* in, uint16_t* out, uint64_t n, int t
 int k_bitswap_decode(int w, const uint16_t* in, uint16_t* out, uint64_t n, cudaStream_t st);
 int k_remove_background(const uint16_t* in, uint16_t* out, uint64_t n, int threshold, cudaStream_t st);
 
+// bitswap8.cu (uint8 volumes)
+int k_bitswap8_encode(int w, const uint8_t* in, uint8_t* out, uint64_t n, int threshold, cudaStream_t st);
+int k_bitswap8_decode(int w, const uint8_t* in, uint8_t* out, uint64_t n, cudaStream_t st);
+int k_remove_background8(const uint8_t* in, uint8_t* out, uint64_t n, int threshold, cudaStream_t st);
+
 // quantise.cu
 int k_histogram_u16(const uint16_t* in, uint64_t n, uint32_t* hist /* 65536 x u32, accumulated into */, cudaStream_t st);
 int k_lut_apply(const uint16_t* in, uint8_t* out, uint64_t n, const uint8_t* lut_dev /* 65536 */, cudaStream_t st);

@@ -99,13 +99,13 @@ static bool parse_float_like(const std::string& s, float& out) {
   return e && e != s.c_str();
 }
 
-static bool make_stage(const std::string& name, const std::string& args, Stage& st) {
+static bool make_stage(const std::string& name, const std::string& args, Stage& st, int elem) {
   const std::map<std::string, std::string> kv = minors(args);
   if (name.rfind("bitswap", 0) == 0) {
     st.kind = StageKind::Bitswap;
     st.w = std::atoi(name.c_str() + 7);
     // bitswap1(num_bits_per_plane=4) only warns in the reference and stays at the static width
-    return st.w == 1 || st.w == 2 || st.w == 4 || st.w == 8;
+    return st.w == 1 || st.w == 2 || st.w == 4 || (st.w == 8 && elem == 2);
   }
   if (name == "remove_background" || name == "rmbkrd") {
     st.kind = StageKind::RemoveBackground;
@@ -115,13 +115,14 @@ static bool make_stage(const std::string& name, const std::string& args, Stage& 
       char* e = nullptr;
       const long v = std::strtol(f->second.c_str(), &e, 10);
       if (!e || e == f->second.c_str()) return false;  // std::stoi would throw in the reference
-      st.threshold = (int)(uint16_t)v;                 // stored as raw_type (uint16)
+      st.threshold = elem == 1 ? (int)(uint8_t)v : (int)(uint16_t)v;   // stored as raw_type
     }
     return true;
   }
-  if (name == "rmestbkrd") { st.kind = StageKind::RmEstBkrd; return true; }
+  if (name == "rmestbkrd") { st.kind = StageKind::RmEstBkrd; return elem == 2; }
   if (name == "pass_through") { st.kind = StageKind::PassThrough; return true; }
   if (name == "quantiser") {
+    if (elem != 2) return false;
     st.kind = StageKind::Quantiser;
     st.kv = kv;
     auto w = kv.find("weighting_function");
@@ -162,7 +163,7 @@ static bool make_stage(const std::string& name, const std::string& args, Stage& 
   return false;
 }
 
-static bool plan(const std::string& s, Pipeline* out) {
+static bool plan(const std::string& s, Pipeline* out, int elem = 2) {
   if (s.empty()) return false;
   const auto pairs = to_pairs(s);
   if (pairs.empty()) return false;
@@ -171,17 +172,18 @@ static bool plan(const std::string& s, Pipeline* out) {
   for (auto& p : pairs) rebuilt += p.first.size() + (p.second.empty() ? 0 : 2 + p.second.size());
   if (rebuilt != s.size()) return false;
   Pipeline pl;
+  pl.elem = elem;
   for (auto& p : pairs) {
     Stage st;
     if (!pl.has_sink && is_head_name(p.first)) {
-      if (!make_stage(p.first, p.second, st)) return false;
+      if (!make_stage(p.first, p.second, st, elem)) return false;
       pl.head.push_back(st);
     } else if (!pl.has_sink && is_sink_name(p.first)) {
-      if (!make_stage(p.first, p.second, st)) return false;
+      if (!make_stage(p.first, p.second, st, elem)) return false;
       pl.sink = st;
       pl.has_sink = true;
     } else if (pl.has_sink && !pl.has_tail && is_tail_name(p.first) && pl.sink.kind != StageKind::Lz4) {
-      if (!make_stage(p.first, p.second, st)) return false;
+      if (!make_stage(p.first, p.second, st, elem)) return false;
       pl.tail = st;
       pl.has_tail = true;
     } else {
@@ -194,6 +196,8 @@ static bool plan(const std::string& s, Pipeline* out) {
 
 bool pipeline_possible_u16(const std::string& s) { return plan(s, nullptr); }
 bool build_pipeline_u16(const std::string& s, Pipeline& out) { return plan(s, &out); }
+bool pipeline_possible_u8(const std::string& s) { return plan(s, nullptr, 1); }
+bool build_pipeline_u8(const std::string& s, Pipeline& out) { return plan(s, &out, 1); }
 
 // ------------------------------------------------------------------------------------------------
 // bounds
@@ -225,7 +229,7 @@ static uint64_t lz4_stage_bound(const Stage& st, uint64_t bytes) {
 
 uint64_t max_encoded_size_u16(const Pipeline& p, uint64_t raw_bytes) {
   // header of the bound query: rank-1 shape {raw_bytes}, payload = 2*raw_bytes (sqeazy_header.hpp:216-241)
-  const std::string hdr = pack_header("uint16", 2, {raw_bytes}, p.canonical(), raw_bytes * 2);
+  const std::string hdr = pack_header(p.type_name(), p.elem, {raw_bytes}, p.canonical(), raw_bytes * 2);
   uint64_t stage_max = 0;
   if (!p.head.empty()) stage_max = std::max<uint64_t>(stage_max, raw_bytes);
   uint64_t ours = raw_bytes;  // what this implementation can actually emit
@@ -260,7 +264,7 @@ size_t header_reserve_bytes(const Pipeline& p, const std::vector<uint64_t>& shap
     // decode_lut_string=<verbatim> 684 base64 chars </verbatim>, every '/' doubled by JSON escaping
     extra = 32 + 2 * 684 + 32;
   }
-  const std::string h = pack_header("uint16", 2, shape, name, UINT64_MAX);
+  const std::string h = pack_header(p.type_name(), p.elem, shape, name, UINT64_MAX);
   size_t n = h.size() + extra + name.size() / 8 + 64;
   return (n + 255) & ~size_t(255);
 }

@@ -32,7 +32,9 @@ struct Stage {
 };
 
 struct Pipeline {
-  std::vector<Stage> head;        // uint16 -> uint16 filters
+  int elem = 2;                   // bytes per voxel: 2 (dypeline<uint16_t>) or 1 (dypeline<uint8_t>, the *_UI8 entry points)
+  const char* type_name() const { return elem == 1 ? "uint8" : "uint16"; }
+  std::vector<Stage> head;        // raw_type -> raw_type filters
   bool has_sink = false;
   Stage sink;                     // lz4 | quantiser | pass_through
   bool has_tail = false;
@@ -45,6 +47,11 @@ struct Pipeline {
 bool pipeline_possible_u16(const std::string& s);
 // builds the plan; false if the string is not valid / not supported
 bool build_pipeline_u16(const std::string& s, Pipeline& out);
+
+// the same for dypeline<uint8_t> (src/sqeazy.cpp:72-106,144-163,209-231,243-251,309-335), restricted to the stages
+// with uint8 kernels: bitswap1|2|4, remove_background (alias rmbkrd) -> lz4 | pass_through [-> lz4]
+bool pipeline_possible_u8(const std::string& s);
+bool build_pipeline_u8(const std::string& s, Pipeline& out);
 
 // bound of the encoded payload for raw_bytes of input, and of the whole blob (2*header + max(stage bounds))
 uint64_t max_encoded_size_u16(const Pipeline& p, uint64_t raw_bytes);

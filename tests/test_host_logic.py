@@ -38,7 +38,7 @@ def test_version_triple(sq):
 def test_pipeline_possible(sq, p, ok):
     """tests/test_pipeline_interface.cpp:28-61 ; names outside the accelerated stages are refused (documented)"""
     assert sq.pipeline_possible(p) is ok
-    assert sq.pipeline_possible(p, 1) is False
+    assert sq.pipeline_possible(p, 4) is False
     if ok or p in ("", "bswap1_lz4", "bitswap1->lz4!!", "bitswap1 ->lz4"):
         assert orc.can_be_built_from(p) is ok  # same verdict as the restated reference rule
 
@@ -111,11 +111,31 @@ def test_host_l2_probe_matches_compass(sq, ref):
     assert sq.host_l2_bytes() == ref.l2_cache_bytes()
 
 
-def test_uint8_and_hdf5_entry_points_fail_cleanly(sq):
+def test_hdf5_entry_points_fail_cleanly(sq):
     L = sq.lib()
-    n = ctypes.c_long(10)
-    assert L.SQY_Pipeline_Max_Compressed_Length_UI8(b"lz4", ctypes.c_long(3), ctypes.byref(n)) == 1
     assert L.SQY_h5_query_ndims(b"a.h5", b"d", None) == 1
+
+
+@pytest.mark.parametrize("p,ok", [
+    ("bitswap1->lz4", True), ("lz4", True), ("bitswap1", True), ("bitswap4->lz4", True), ("pass_through", True), ("pass_through->lz4", True),
+    ("remove_background(threshold=7)->bitswap1->lz4", True), ("rmbkrd(threshold=7)->lz4", True),
+    # stages without uint8 kernels here: refused (documented), like every other unaccelerated stage name
+    ("rmestbkrd->lz4", False), ("quantiser->lz4", False), ("bitswap8->lz4", False), ("", False), ("lz4->lz4", False),
+])
+def test_pipeline_possible_uint8(sq, p, ok):
+    """dypeline<uint8_t>::can_be_built_from, src/sqeazy.cpp:243-268"""
+    assert bool(sq.lib().SQY_Pipeline_Possible_UI8(p.encode())) is ok
+    assert sq.pipeline_possible(p, 1) is ok
+
+
+def test_max_compressed_length_uint8(sq):
+    """src/sqeazy.cpp:144-163, 209-231: sizes in bytes of uint8 voxels"""
+    raw = 8 * 8 * 8
+    assert sq.max_compressed_length_u8("bitswap1->lz4", raw) > raw
+    assert sq.max_compressed_length_3d_u8("bitswap1->lz4", (8, 8, 8)) == sq.max_compressed_length_u8("bitswap1->lz4", raw)
+    assert sq.max_compressed_length_u8("lz4", 1 << 27) >= sq.lz4_bound(1 << 27)
+    with pytest.raises(sq.SqeazyError):
+        sq.max_compressed_length_u8("quantiser->lz4", 10)
 
 
 def test_compute_without_gpu_fails_loudly(sq):

@@ -190,3 +190,33 @@ def test_header_roundtrip():
     assert len(h) % 2 == 0 and h.endswith(orc.HEADER_DELIM)
     u = orc.unpack_header(h.encode() + b"\x00\xffgarbage|01307#!")
     assert u["pipeline"] == name and u["shape"] == [3, 5, 7] and u["bytes"] == 42 and u["size"] == len(h)
+
+
+# ------------------------------------------------------------------------------------------------ uint8 volumes
+@pytest.mark.parametrize("w", [1, 2, 4])
+def test_bitswap8_kat_and_ref_live(port, ref, w):
+    """the scalar template of bitplane_reorder_scalar.hpp:27-116 with raw_type = uint8_t: first element of a group in the
+    most significant field, most significant plane first; the C port equals the reference's own instantiation"""
+    a = np.arange(8, dtype=np.uint8)
+    e = port.bitswap8_encode(w, a)
+    if w == 1:   # planes 7..3 empty; bit 2 of 0..7 = 00001111, bit 1 = 00110011, bit 0 = 01010101
+        assert e.tolist() == [0, 0, 0, 0, 0, 0x0F, 0x33, 0x55]
+    if w == 4:   # P = 2: high nibbles first, then low nibbles, pairs packed first-element-high
+        assert e.tolist() == [0x00, 0x00, 0x00, 0x00, 0x01, 0x23, 0x45, 0x67]
+    rng = np.random.default_rng(w)
+    for n in (0, 1, 7, 8, 9, 64, 1000, 4099):
+        x = rng.integers(0, 256, n, dtype=np.uint8)
+        y = port.bitswap8_encode(w, x)
+        assert np.array_equal(port.bitswap8_decode(w, y), x)
+        if ref.available:
+            assert np.array_equal(ref.bitswap8_encode(w, x), y)
+            assert np.array_equal(ref.bitswap8_decode(w, y), x)
+
+
+def test_remove_background8_vs_ref_live(port, ref):
+    x = np.random.default_rng(5).integers(0, 256, 5000, dtype=np.uint8)
+    for t in (0, 1, 100, 255, 300):   # 300 is stored as uint8 (44), remove_background_scheme_impl.hpp:41-44
+        y = port.remove_background8(x, t)
+        assert np.array_equal(y, np.where(x > (t & 0xFF), x - (t & 0xFF), 0).astype(np.uint8))
+        if ref.available:
+            assert np.array_equal(ref.remove_background8(x, t), y)
