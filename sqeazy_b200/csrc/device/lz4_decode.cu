@@ -614,7 +614,13 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
             for (uint32_t k = lane; k < mlen; k += 32u)   // k < 512: the quotient is exact
               SQYB_W(mo + k) = SQYB_W(base + (k - offset * (uint32_t)__float2int_rz(((float)k + 0.5f) * inv)));
           }
-        } else if (!do_match(mo, offset, mlen)) {
+        } else if (offset <= mo) {
+          // far source inside this block: it ends at least 1199 bytes in front of the match (offset > kNear, mlen <= 273)
+          // while everything up to 1023 bytes in front of it was flushed after the previous batch, so it is read back
+          // from global memory (L2) without any window bookkeeping
+          const uint8_t* from = O.d + (mo - offset);
+          for (uint32_t k = lane; k < mlen; k += 32u) SQYB_W(mo + k) = __ldcg(from + k);
+        } else if (!do_match(mo, offset, mlen)) {   // reaches in front of a linked block
           return op;
         }
         __syncwarp();
