@@ -17,7 +17,9 @@ HDRS      := $(wildcard $(CSRC)/device/*.h $(CSRC)/device/*.cuh $(CSRC)/host/*.h
 REF       := /root/reference/src/cpp/src
 LZ4SO     := /usr/lib/x86_64-linux-gnu/liblz4.so.1
 
-all: $(LIB) oracle
+SQY       := sqeazy_b200/bin/sqy
+
+all: $(LIB) $(SQY) oracle
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(dir $@)
@@ -29,6 +31,11 @@ $(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDRS)
 
 $(LIB): $(CU_OBJS) $(CPP_OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static
+
+# ---- sqy command line tool: a plain C++ client of the C ABI (no CUDA in this translation unit)
+$(SQY): $(CSRC)/cli/sqy.cpp $(CSRC)/cli/tiff_min.hpp include/sqeazy.h $(LIB)
+	@mkdir -p $(dir $@)
+	$(CXX) -O2 -std=c++17 -Wall -o $@ $(CSRC)/cli/sqy.cpp -Lsqeazy_b200 -lsqeazy -Wl,-rpath,'$$ORIGIN/..'
 
 # ---- test-only oracle: C restatement (always) and the compiled reference stages (when /root/reference exists)
 oracle: oracle/_build/libsqyoracle.so oracle_ref
@@ -46,6 +53,6 @@ oracle/_ref/libsqyref.so: oracle/ref_harness.cpp $(wildcard oracle/refshim/*.hpp
 	    -Ioracle/refshim -Ioracle/refshim/lz4inc -I$(REF) -I$(REF)/encoders oracle/ref_harness.cpp $(LZ4SO) -o $@
 
 clean:
-	rm -rf build $(LIB) oracle/_build oracle/_ref/libsqyref.so
+	rm -rf build $(LIB) sqeazy_b200/bin oracle/_build oracle/_ref/libsqyref.so
 
 .PHONY: all oracle oracle_ref clean
