@@ -321,6 +321,32 @@ def main():
             traffic = json.load(f).get(args.workload, {}).get("lz4_encode_kernel_dram_bytes_per_launch")
     except Exception:
         pass
+    # split of the dominant kernel into its closed-form path (all-equal blocks: load, compare, 75 bytes out) and
+    # the general path. The closed-form rate is measured on an all-zero buffer of the same size; the general rate follows
+    # from the block counts: t_general = t_kernel - constant_bytes / constant_rate.
+    split = None
+    try:
+        zeros = torch.zeros(lz4_in_bytes, dtype=torch.uint8, device=dev)
+        zbuf = torch.empty(sq.lz4_bound(lz4_in_bytes), dtype=torch.uint8, device=dev)
+        sq.lz4_encode_device(zeros, out=zbuf)
+        zev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        zev[0].record()
+        for _ in range(3):
+            sq.lz4_encode_device(zeros, out=zbuf)
+        zev[1].record()
+        zev[1].synchronize()
+        const_gbs = lz4_in_bytes / (zev[0].elapsed_time(zev[1]) / 3 / 1e3) / 1e9
+        nb = stats["general_blocks"] + stats["constant_blocks"] + stats["stored_blocks"]
+        const_bytes = lz4_in_bytes * stats["constant_blocks"] / max(nb, 1)
+        t_const = const_bytes / (const_gbs * 1e9)
+        t_general = max(stage["lz4_encode"] / 1e3 - t_const, 1e-9)
+        split = {"constant_blocks_share": stats["constant_blocks"] / max(nb, 1), "constant_path_gbs": const_gbs,
+                 "constant_path_frac_of_peak": const_gbs / peak,
+                 "general_path_gbs": (lz4_in_bytes - const_bytes) / t_general / 1e9,
+                 "general_path_frac_of_peak": (lz4_in_bytes - const_bytes) / t_general / 1e9 / peak}
+        del zeros, zbuf
+    except Exception as exc:
+        split = {"error": repr(exc)}
     roofline = {"bound": "hbm", "kernel": "lz4_encode_kernel", "achieved": achieved, "peak": peak, "peak_source": peak_kind + " copy bandwidth",
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": lz4_in_bytes + payload_bytes, "kernel_ms": stage["lz4_encode"],
@@ -328,7 +354,7 @@ def main():
                 "stage_gbs": {"filter_bitswap_encode(4B/voxel)": (2 * raw_bytes / (stage["filter_bitswap_encode"] / 1e3) / 1e9) if stage["filter_bitswap_encode"] else None,
                               "bitswap_decode(4B/voxel)": (2 * raw_bytes / (stage["bitswap_decode"] / 1e3) / 1e9) if stage["bitswap_decode"] else None,
                               "lz4_decode(C+B)": ((lz4_in_bytes + payload_bytes) / (stage["lz4_decode"] / 1e3) / 1e9) if stage["lz4_decode"] else None},
-                "lz4_blocks": stats}
+                "lz4_blocks": stats, "path_split": split}
 
     # ---- e2e: host buffers through SQY_PipelineEncode_UI16 / SQY_Decode_UI16 ----
     e2e = None
