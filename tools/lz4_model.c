@@ -57,8 +57,8 @@ static void find_candidates(const uint8_t* d, int n, int round, int hashlog, int
           while (l < 5 && i + l < n - 5 && d[i + l] == d[i + l - dd]) l++;
           if (l >= 5) found = i - dd;
         }
-        noshort[i] = found < 0;
-        if (found < 0 && c >= 0 && ld4(d + c) == v && !(mode & 128) && !((mode & 256) && c / g_cut != i / g_cut)) found = c; /* 256: same sub-block only */ /* 128: short offsets only */
+        noshort[i] = found < 0 && !((mode & 512) && i > 0 && d[i] == d[i - 1]); /* 512: look up / insert only where a run breaks */
+        if (found < 0 && noshort[i] && c >= 0 && ld4(d + c) == v && !(mode & 128) && !((mode & 256) && c / g_cut != i / g_cut)) found = c; /* 256: same sub-block only */ /* 128: short offsets only */
       }
       cand[i] = found;
     }
