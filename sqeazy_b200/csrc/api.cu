@@ -822,7 +822,7 @@ int SQY_Pipeline_Max_Compressed_Length_UI16(const char* pipeline, long pipeline_
     if (!pipeline || !length || pipeline_length < 0 || *length < 0) return 1;
     Pipeline pl;
     if (!build_pipeline_u16(std::string(pipeline, (size_t)pipeline_length), pl) || pl.empty()) return 1;
-    *length = (long)max_encoded_size_u16(pl, (uint64_t)*length);
+    *length = (long)max_encoded_size(pl, (uint64_t)*length);
     return 0;
   } catch (...) {
     return 1;
@@ -836,7 +836,7 @@ int SQY_Pipeline_Max_Compressed_Length_3D_UI16(const char* pipeline, long* shape
     if (!build_pipeline_u16(std::string(pipeline, (size_t)*length), pl) || pl.empty()) return 1;
     uint64_t n = 1;
     for (unsigned i = 0; i < shape_size; ++i) n *= (uint64_t)shape[i];  // 64-bit, unlike the reference
-    *length = (long)max_encoded_size_u16(pl, 2 * n);
+    *length = (long)max_encoded_size(pl, 2 * n);
     return 0;
   } catch (...) {
     return 1;
@@ -848,7 +848,7 @@ int SQY_Pipeline_Max_Compressed_Length_UI8(const char* pipeline, long pipeline_l
     if (!pipeline || !length || pipeline_length < 0 || *length < 0) return 1;
     Pipeline pl;
     if (!build_pipeline_u8(std::string(pipeline, (size_t)pipeline_length), pl) || pl.empty()) return 1;
-    *length = (long)max_encoded_size_u16(pl, (uint64_t)*length);
+    *length = (long)max_encoded_size(pl, (uint64_t)*length);
     return 0;
   } catch (...) {
     return 1;
@@ -861,7 +861,7 @@ int SQY_Pipeline_Max_Compressed_Length_3D_UI8(const char* pipeline, long* shape,
     if (!build_pipeline_u8(std::string(pipeline, (size_t)*length), pl) || pl.empty()) return 1;
     uint64_t n = 1;
     for (unsigned i = 0; i < shape_size; ++i) n *= (uint64_t)shape[i];
-    *length = (long)max_encoded_size_u16(pl, n);
+    *length = (long)max_encoded_size(pl, n);
     return 0;
   } catch (...) {
     return 1;
@@ -879,7 +879,7 @@ static int host_encode(int elem, const char* pipeline, const char* src, long* sh
     }
     const std::vector<uint64_t> shp = to_shape(shape, shape_size);
     const uint64_t N = shape_product(shp), raw_bytes = (uint64_t)elem * N;
-    const uint64_t cap = max_encoded_size_u16(pl, raw_bytes);
+    const uint64_t cap = max_encoded_size(pl, raw_bytes);
     std::lock_guard<std::mutex> lk(g_mu);
     Arena* A = nullptr;
     if (current_arena(&A)) return 1;

@@ -227,7 +227,7 @@ static uint64_t lz4_stage_bound(const Stage& st, uint64_t bytes) {
   return ref;
 }
 
-uint64_t max_encoded_size_u16(const Pipeline& p, uint64_t raw_bytes) {
+uint64_t max_encoded_size(const Pipeline& p, uint64_t raw_bytes) {
   // header of the bound query: rank-1 shape {raw_bytes}, payload = 2*raw_bytes (sqeazy_header.hpp:216-241)
   const std::string hdr = pack_header(p.type_name(), p.elem, {raw_bytes}, p.canonical(), raw_bytes * 2);
   uint64_t stage_max = 0;

@@ -54,7 +54,7 @@ bool pipeline_possible_u8(const std::string& s);
 bool build_pipeline_u8(const std::string& s, Pipeline& out);
 
 // bound of the encoded payload for raw_bytes of input, and of the whole blob (2*header + max(stage bounds))
-uint64_t max_encoded_size_u16(const Pipeline& p, uint64_t raw_bytes);
+uint64_t max_encoded_size(const Pipeline& p, uint64_t raw_bytes);   // raw_bytes = voxels * p.elem
 
 // bytes reserved for the (right-aligned) header in front of the payload for this pipeline/shape
 size_t header_reserve_bytes(const Pipeline& p, const std::vector<uint64_t>& shape);

@@ -13,7 +13,10 @@ assert ref.available
 torch.cuda.set_device(0); sq.set_device(0)
 vol = numpy_volume(shape, "scmos", index=0)
 name = "bitswap1(num_bits_per_plane=1)->lz4(accel=1,blocksize_kb=256,framestep_kb=256,n_chunks_of_input=0)"
-for label, nthreads in (("serial/linked", 1), ("parallel/framed", os.cpu_count())):
+modes = (("serial/linked", 1), ("parallel/framed", os.cpu_count()))
+if len(sys.argv) > 2:
+    modes = tuple(m for m in modes if m[0].startswith(sys.argv[2]))
+for label, nthreads in modes:
     payload, t_enc = ref.pipeline_encode_stages(0, vol, nthreads)
     h = orc.pack_header(vol.shape, name, payload.size, version="0.5.2", headref="4c45a9b")
     blob = torch.from_numpy(np.concatenate([np.frombuffer(h.encode(), dtype=np.uint8), payload])).cuda()
