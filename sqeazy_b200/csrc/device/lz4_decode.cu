@@ -965,21 +965,26 @@ __global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSM) lz4_decode_lanes
   }
 }
 
+// `classified`: lz4_classify_kernel ran first (only when the lane-serial decoder is switched on) and this kernel takes
+// the blocks it left. Otherwise every block is taken here and the stored / closed-form blocks are handled inline: their
+// 16-byte-store fills are memory-bound and hide under the issue-bound decoding of the other warps, whereas a separate
+// classification pass in front of this kernel cost 0.63 ms per 4 GiB.
 __global__ void __launch_bounds__(kWinWarps * 32, 5) lz4_decode_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
-                                                                        uint8_t* __restrict__ dst, DecCtl* ctl, DecTables T) {
+                                                                        uint8_t* __restrict__ dst, DecCtl* ctl, DecTables T,
+                                                                        int classified) {
   extern __shared__ __align__(16) unsigned char dsm[];
   if (ctl->error) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t* win = dsm + (size_t)warp * kWinWarpSmem;
   uint8_t* ring8 = win + kWin;
   const uint32_t nblocks = ctl->nblocks;
-  if (ctl->nwarp == 0) return;
+  if (classified && ctl->nwarp == 0) return;
   while (true) {
     uint32_t b = 0;
     if (lane == 0) b = atomicAdd(&ctl->ticket_decode, 1u);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= nblocks) return;
-    if (T.kind[b] != kKindWarp) continue;
+    if (classified && T.kind[b] != kKindWarp) continue;
     const uint32_t word = T.word[b];
     const uint32_t csize = word & 0x7FFFFFFFu;
     const uint32_t dsize = T.dsize[b];
@@ -1096,16 +1101,17 @@ int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t 
   lz4_expand_kernel<<<tile_grid, 256, 0, st>>>(src, ctl, T, tile_sums, dst_bytes);
   lz4_sizes_kernel<<<kNumSMs * 4, kDecThreads, 0, st>>>(src, ctl, T);
   lz4_offsets_kernel<<<1, kDirThreads, 0, st>>>(ctl, T, dst_bytes);
-  lz4_classify_kernel<<<kNumSMs * 8, 256, 0, st>>>(src, dst, ctl, T, lane_max_bytes());
-  const size_t lane_smem = 32 * sizeof(uint32_t) * kLaneThreads;
-  SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_decode_lanes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  if (lane_max_bytes() > 0) {
+  const bool lanes = lane_max_bytes() > 0;
+  if (lanes) {
+    lz4_classify_kernel<<<kNumSMs * 8, 256, 0, st>>>(src, dst, ctl, T, lane_max_bytes());
+    const size_t lane_smem = 32 * sizeof(uint32_t) * kLaneThreads;
+    SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_decode_lanes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     lz4_decode_lanes_kernel<<<kNumSMs * kLaneCtasPerSM, kLaneThreads, lane_smem, st>>>(src, src_bytes, dst, ctl, T);
-    SQYB_COUNT_LAUNCH(1);
+    SQYB_COUNT_LAUNCH(2);
   }
   const size_t win_smem = kWinWarps * kWinWarpSmem;
-  lz4_decode_kernel<<<kNumSMs * 5, kWinWarps * 32, win_smem, st>>>(src, src_bytes, dst, ctl, T);
-  SQYB_COUNT_LAUNCH(7);
+  lz4_decode_kernel<<<kNumSMs * 5, kWinWarps * 32, win_smem, st>>>(src, src_bytes, dst, ctl, T, lanes ? 1 : 0);
+  SQYB_COUNT_LAUNCH(6);
   return (int)cudaGetLastError();
 }
 
