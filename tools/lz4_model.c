@@ -13,6 +13,18 @@ static uint32_t ld4(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; 
 
 /* candidates: cand[i] = position or -1. round-based table (positions of earlier rounds) + short offsets */
 static int g_cut = 1 << 30;
+static long g_lookups = 0, g_lookup_segs = 0;
+static int seg_has_short(const uint8_t* d, int n, int seg) {
+  static const int ds[4] = {1, 2, 4, 3};
+  for (int i = seg * 32; i < seg * 32 + 32 && i + 12 <= n; ++i)
+    for (int q = 0; q < 4; ++q) {
+      int dd = ds[q], l = 0;
+      if (i < dd) continue;
+      while (l < 5 && i + l < n - 5 && d[i + l] == d[i + l - dd]) l++;
+      if (l >= 5) return 1;
+    }
+  return 0;
+}
 static void find_candidates(const uint8_t* d, int n, int round, int hashlog, int mode, int* cand) {
   int tsize = 1 << hashlog;
   int* tab = malloc(sizeof(int) * tsize);
@@ -57,11 +69,13 @@ static void find_candidates(const uint8_t* d, int n, int round, int hashlog, int
           while (l < 5 && i + l < n - 5 && d[i + l] == d[i + l - dd]) l++;
           if (l >= 5) found = i - dd;
         }
-        noshort[i] = found < 0 && !((mode & 512) && i > 0 && d[i] == d[i - 1]); /* 512: look up / insert only where a run breaks */
+        noshort[i] = found < 0 && !((mode & 512) && i > 0 && d[i] == d[i - 1]) && !((mode & 1024) && (i & 3) && !seg_has_short(d, n, i / 32)) && !((mode & 2048) && ((i / 32) & 3) && !seg_has_short(d, n, i / 32)); /* 2048: run-free segments look up only in every 4th segment */ /* 512: look up / insert only where a run breaks */
         if (found < 0 && noshort[i] && c >= 0 && ld4(d + c) == v && !(mode & 128) && !((mode & 256) && c / g_cut != i / g_cut)) found = c; /* 256: same sub-block only */ /* 128: short offsets only */
       }
       cand[i] = found;
+      if (mode & 64) { g_lookups += noshort[i]; }
     }
+    if (mode & 64) for (int sg = r0 / 32; sg < (r1 + 31) / 32; ++sg) { int any = 0; for (int i = sg * 32; i < sg * 32 + 32 && i < r1; ++i) any |= noshort[i]; g_lookup_segs += any; }
     for (int i = r0; i < r1; ++i) {
       if (i + 4 > n) continue;
       if ((mode & 64) && !noshort[i]) continue;
@@ -126,5 +140,6 @@ int main(int argc, char** argv) {
   }
   printf("block=%d round=%d cut=%d hashlog=%d mode=%d: %ld -> %ld ratio %.3f seqs %ld (%.1f B/seq)\n", block, round, cut, hashlog, mode,
          total, out, (double)total / out, nseq, nseq ? (double)total / nseq : 0.0);
+  fprintf(stderr, "lookups %ld (%.1f%% of bytes), segments with lookups %ld (%.1f%% of segments)\n", g_lookups, 100.0 * g_lookups / total, g_lookup_segs, 100.0 * g_lookup_segs / (total / 32.0));
   return 0;
 }
