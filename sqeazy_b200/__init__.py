@@ -418,6 +418,11 @@ def host_l2_bytes() -> int:
 STAGE_NAMES = ("filter_bitswap_encode", "lz4_encode", "histogram", "lut_apply", "lz4_decode", "lut_decode", "bitswap_decode")
 
 
+def release_scratch():
+    """frees the library's cached device scratch on the current device"""
+    lib().sqyx_release_scratch()
+
+
 def enable_stage_timing(on: bool = True):
     lib().sqyx_enable_stage_timing(c_int(1 if on else 0))
 

@@ -11,7 +11,7 @@
 // delta-swap stages (a PxP transpose of w-bit atoms in registers), and stores W consecutive
 // 32-bit words per plane, so a warp writes 128*W contiguous bytes per plane. The optional
 // threshold filter (remove_background, encoders/remove_background_scheme_impl.hpp:82-89) is
-// fused into the load as one __vsubus2 per two voxels.
+// fused into the load (sat_sub_u16x2, common.cuh).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -74,7 +74,7 @@ __device__ __forceinline__ void st256(void* p, const uint32_t* r) {
 // ---- encode: n32 = number of 32-voxel chunks, S = words per segment --------------------------
 template <int W, bool SUB>
 __global__ void __launch_bounds__(256) bitswap_encode_fast(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
-                                                            uint64_t n32, uint64_t S, uint32_t thr2) {
+                                                            uint64_t n32, uint64_t S, uint32_t thr /* threshold, < 65536 */) {
   constexpr int P = Geo<W>::P;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n32; t += stride) {
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) bitswap_encode_fast(const uint16_t* __res
     ld256(in + t * 32 + 16, L + 8);
     if (SUB) {
 #pragma unroll
-      for (int k = 0; k < 16; ++k) L[k] = __vsubus2(L[k], thr2);
+      for (int k = 0; k < 16; ++k) L[k] = sat_sub_u16x2(L[k], thr);
     }
     uint32_t reg[16];
 #pragma unroll
@@ -231,7 +231,7 @@ int launch_encode(const uint16_t* in, uint16_t* out, uint64_t n, int threshold, 
   if (fast_ok(in, out, n)) {
     const uint64_t n32 = n / 32, S = n / P;
     const int g = grid_for(n32, 256);
-    if (sub) bitswap_encode_fast<W, true><<<g, 256, 0, st>>>(in, out, n32, S, thr | (thr << 16));
+    if (sub) bitswap_encode_fast<W, true><<<g, 256, 0, st>>>(in, out, n32, S, thr);
     else bitswap_encode_fast<W, false><<<g, 256, 0, st>>>(in, out, n32, S, 0);
   } else {
     const int g = grid_for(n / P + 1, 256);
@@ -263,10 +263,9 @@ __global__ void __launch_bounds__(256) remove_background_kernel(const uint16_t* 
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
   const uint64_t nv = aligned ? n / 8 : 0;
-  const uint32_t thr2 = thr | (thr << 16);
   for (uint64_t i = tid; i < nv; i += stride) {
     uint4 v = ld_stream(reinterpret_cast<const uint4*>(in) + i);
-    v.x = __vsubus2(v.x, thr2); v.y = __vsubus2(v.y, thr2); v.z = __vsubus2(v.z, thr2); v.w = __vsubus2(v.w, thr2);
+    v.x = sat_sub_u16x2(v.x, thr); v.y = sat_sub_u16x2(v.y, thr); v.z = sat_sub_u16x2(v.z, thr); v.w = sat_sub_u16x2(v.w, thr);
     st_stream(reinterpret_cast<uint4*>(out) + i, v);
   }
   for (uint64_t i = nv * 8 + tid; i < n; i += stride) {

@@ -49,12 +49,10 @@ __device__ __forceinline__ unsigned long long transpose_atoms(unsigned long long
   return x;
 }
 
-__device__ __forceinline__ uint32_t sat_sub_u8x4(uint32_t v, uint32_t thr4) { return __vsubus4(v, thr4); }
-
 // n32 = number of 32-byte chunks, S = bytes per segment
 template <int W, bool SUB>
 __global__ void __launch_bounds__(256) bitswap8_encode_fast(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t n32,
-                                                             uint64_t S, uint32_t thr4) {
+                                                             uint64_t S, uint32_t thr /* threshold, < 256 */) {
   constexpr int P = 8 / W;          // planes = bytes per group
   constexpr int G = 32 / P;         // groups per thread = output bytes per plane per thread
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -62,8 +60,8 @@ __global__ void __launch_bounds__(256) bitswap8_encode_fast(const uint8_t* __res
     uint4 a = ld_stream(reinterpret_cast<const uint4*>(in + t * 32));
     uint4 b = ld_stream(reinterpret_cast<const uint4*>(in + t * 32) + 1);
     if (SUB) {
-      a.x = sat_sub_u8x4(a.x, thr4); a.y = sat_sub_u8x4(a.y, thr4); a.z = sat_sub_u8x4(a.z, thr4); a.w = sat_sub_u8x4(a.w, thr4);
-      b.x = sat_sub_u8x4(b.x, thr4); b.y = sat_sub_u8x4(b.y, thr4); b.z = sat_sub_u8x4(b.z, thr4); b.w = sat_sub_u8x4(b.w, thr4);
+      a.x = sat_sub_u8x4(a.x, thr); a.y = sat_sub_u8x4(a.y, thr); a.z = sat_sub_u8x4(a.z, thr); a.w = sat_sub_u8x4(a.w, thr);
+      b.x = sat_sub_u8x4(b.x, thr); b.y = sat_sub_u8x4(b.y, thr); b.z = sat_sub_u8x4(b.z, thr); b.w = sat_sub_u8x4(b.w, thr);
     }
     unsigned long long c[4] = {((unsigned long long)a.y << 32) | a.x, ((unsigned long long)a.w << 32) | a.z,
                                ((unsigned long long)b.y << 32) | b.x, ((unsigned long long)b.w << 32) | b.z};
@@ -191,7 +189,7 @@ int launch_encode8(const uint8_t* in, uint8_t* out, uint64_t n, int threshold, c
   if (fast_ok8(in, out, n)) {
     const uint64_t n32 = n / 32, S = n / P;
     const int g = grid_for8(n32, 256);
-    if (sub) bitswap8_encode_fast<W, true><<<g, 256, 0, st>>>(in, out, n32, S, thr * 0x01010101u);
+    if (sub) bitswap8_encode_fast<W, true><<<g, 256, 0, st>>>(in, out, n32, S, thr);
     else bitswap8_encode_fast<W, false><<<g, 256, 0, st>>>(in, out, n32, S, 0);
   } else {
     const int g = grid_for8(n / P + 1, 256);
@@ -223,10 +221,9 @@ __global__ void __launch_bounds__(256) remove_background8_kernel(const uint8_t* 
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
   const uint64_t nv = aligned ? n / 16 : 0;
-  const uint32_t thr4 = thr * 0x01010101u;
   for (uint64_t i = tid; i < nv; i += stride) {
     uint4 v = ld_stream(reinterpret_cast<const uint4*>(in) + i);
-    v.x = __vsubus4(v.x, thr4); v.y = __vsubus4(v.y, thr4); v.z = __vsubus4(v.z, thr4); v.w = __vsubus4(v.w, thr4);
+    v.x = sat_sub_u8x4(v.x, thr); v.y = sat_sub_u8x4(v.y, thr); v.z = sat_sub_u8x4(v.z, thr); v.w = sat_sub_u8x4(v.w, thr);
     st_stream(reinterpret_cast<uint4*>(out) + i, v);
   }
   for (uint64_t i = nv * 16 + tid; i < n; i += stride) {

@@ -32,6 +32,23 @@ __device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) {
   asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Saturating subtraction of a threshold (remove_background, encoders/remove_background_scheme_impl.hpp:82-89) from
+// packed unsigned fields, written with plain integer operations on purpose. ptxas 12.9 miscompiles the emulation of
+// __vsubus2 when the loop around it is unrolled: the unrolled copies rebuild the packed constant -thr and one of them
+// gets the two's-complement +1 in only one halfword (SASS: `VIADD.16x2 R0, ~thr2, 0x0` next to `VIADD.16x2 R2, ~thr2,
+// 0x10001`, merged by PRMT), so every other voxel lost thr+1 in all grid-stride sweeps of the unrolled body — invisible
+// below ~39 M voxels, found by tests/test_gpu_fullsize.py.
+__device__ __forceinline__ uint32_t sat_sub_u16x2(uint32_t v, uint32_t thr) {
+  const int lo = (int)(v & 0xffffu) - (int)thr, hi = (int)(v >> 16) - (int)thr;
+  return (uint32_t)max(lo, 0) | ((uint32_t)max(hi, 0) << 16);
+}
+__device__ __forceinline__ uint32_t sat_sub_u8x4(uint32_t v, uint32_t thr) {
+  uint32_t r = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r |= (uint32_t)max((int)((v >> (8 * k)) & 0xffu) - (int)thr, 0) << (8 * k);
+  return r;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 }  // namespace sqyb

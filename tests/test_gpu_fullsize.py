@@ -1,0 +1,109 @@
+"""BASELINE.json's full sizes, checked through size-independent properties (the oracle cannot run 4-8 GiB in test time):
+the pipeline's result must equal what the single-stage kernels — a different code path — produce, lossless pipelines must
+return their input, and the 2^31 / 2^32 voxel boundaries (where the reference's 32-bit sizes give up) must hold."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def roomy(sq, cuda):
+    free, _ = cuda.cuda.mem_get_info()
+    if free < 60 << 30:
+        pytest.skip("needs ~60 GB of free device memory")
+    yield
+    sq.release_scratch()
+    cuda.cuda.empty_cache()
+
+
+def test_cfg2_full_size(sq, cuda, roomy):
+    """rmestbkrd->bitswap1->lz4 on 2048x2048x512 uint16 = 2^31 voxels, 4 GiB"""
+    from sqeazy_b200.synth import torch_volume
+
+    shape = (512, 2048, 2048)
+    vol = torch_volume(shape, "scmos", index=0)
+    assert vol.numel() == 1 << 31
+    # expected voxels from the stage kernels: threshold estimate + stand-alone remove_background (not the fused transpose)
+    _, thr = sq.estimate_background_device(vol)
+    assert 90 < thr < 130
+    expect = cuda.empty_like(vol)
+    sq.remove_background_device(vol.view(-1), expect.view(-1), thr)
+    blob = sq.encode_device("rmestbkrd->bitswap1->lz4", vol)
+    assert blob.numel() <= sq.max_compressed_length("rmestbkrd->bitswap1->lz4", vol.numel() * 2)
+    st = sq.last_lz4_stats()
+    assert st["constant_blocks"] + st["general_blocks"] + st["stored_blocks"] == (vol.numel() * 2) // 16384
+    assert st["constant_blocks"] > st["general_blocks"] > 0      # the upper planes of a background-removed stack are empty
+    out = cuda.empty_like(vol)
+    sq.decode_device(blob, out)
+    assert cuda.equal(out, expect)
+    ratio = vol.numel() * 2 / blob.numel()
+    assert 10 < ratio < 40
+    # idempotence of the lossy filter + a lossless pipeline on the result returns it unchanged
+    blob2 = sq.encode_device("bitswap1->lz4", out)
+    back = cuda.empty_like(vol)
+    sq.decode_device(blob2, back)
+    assert cuda.equal(back, expect)
+    del blob, blob2, back, out, expect, vol
+
+
+def test_cfg3_full_size(sq, cuda, roomy):
+    """quantiser->lz4 on 2048x2048x1024 uint16 = 2^32 voxels, 8 GiB raw, 4 GiB of 8-bit codes"""
+    from sqeazy_b200.synth import torch_volume
+
+    shape = (1024, 2048, 2048)
+    vol = torch_volume(shape, "scmos", index=1)
+    assert vol.numel() == 1 << 32
+    hist = cuda.zeros(65536, dtype=cuda.int32, device="cuda")
+    sq.histogram_device(vol, hist)
+    cuda.cuda.synchronize()
+    h = hist.cpu().numpy().view(np.uint32)
+    assert int(h.astype(np.uint64).sum()) == (1 << 32) % (1 << 64) and int(h.max()) < (1 << 32)
+    enc, dec = sq.quantiser_luts(h)
+    codes = cuda.empty(vol.numel(), dtype=cuda.uint8, device="cuda")
+    sq.lut_apply_device(vol, codes, enc)
+    expect = cuda.empty_like(vol)
+    sq.lut_decode_device(codes, expect.view(-1), dec)
+    del codes
+    blob = sq.encode_device("quantiser->lz4", vol)
+    out = cuda.empty_like(vol)
+    sq.decode_device(blob, out)
+    assert cuda.equal(out, expect)
+    assert 1.9 < vol.numel() * 2 / blob.numel() < 4
+    del blob, out, expect, vol
+
+
+@pytest.mark.parametrize("bits", [16, 8])
+def test_threshold_kernels_over_many_grid_sweeps(sq, cuda, bits):
+    """Regression: the packed saturating subtraction must hold in every grid-stride sweep. With __vsubus2, ptxas 12.9
+    unrolled the sweep loop by four and rebuilt the packed constant wrongly in the unrolled copies: beyond ~39 M voxels
+    every other voxel lost threshold+1 (stand-alone remove_background only; found by test_cfg2_full_size). Sizes here give
+    every thread of the capped grid more than eight sweeps; the expected values come from torch arithmetic."""
+    n = 120_000_000 if bits == 16 else 200_000_000
+    g = cuda.Generator(device="cuda")
+    g.manual_seed(bits)
+    if bits == 16:
+        v = cuda.randint(0, 400, (n,), generator=g, device="cuda", dtype=cuda.int32).to(cuda.int16)
+        thr = 106
+        ref = (v.to(cuda.int32) - thr).clamp_(min=0).to(cuda.int16)
+        out = cuda.empty_like(v)
+        sq.remove_background_device(v, out, thr)
+        assert cuda.equal(out, ref)
+        n128 = n - n % 128
+        planes = cuda.empty(n128, dtype=cuda.int16, device="cuda")
+        sq.bitswap_encode_device(1, v[:n128], planes, threshold=thr)
+        sq.bitswap_decode_device(1, planes, out[:n128])
+        assert cuda.equal(out[:n128], ref[:n128])
+    else:
+        v = cuda.randint(0, 256, (n,), generator=g, device="cuda", dtype=cuda.uint8)
+        thr = 19
+        ref = (v.to(cuda.int16) - thr).clamp_(min=0).to(cuda.uint8)
+        out = cuda.empty_like(v)
+        sq.remove_background_device_u8(v, out, thr)
+        assert cuda.equal(out, ref)
+        n128 = n - n % 128
+        planes = cuda.empty(n128, dtype=cuda.uint8, device="cuda")
+        for w in (1, 4):
+            sq.bitswap_encode_device_u8(w, v[:n128], planes, threshold=thr)
+            sq.bitswap_decode_device_u8(w, planes, out[:n128])
+            assert cuda.equal(out[:n128], ref[:n128])
