@@ -377,9 +377,15 @@ def main():
                 sq.decode(b, out=np_out)
             torch.cuda.synchronize()
             t_e2e = max_over_ranks(time.perf_counter() - t0)
+            # the host-pointer path must deliver the same voxels as the device-resident path (64-bit checksums)
+            host_sum = int(np_out.astype(np.uint64).sum()) if np_out.size < (1 << 28) else int(
+                sum(int(np_out[i: i + (1 << 27)].astype(np.uint64).sum()) for i in range(0, np_out.size, 1 << 27)))
+            flat = out.view(-1)
+            dev_sum = sum(int((flat[i: i + (1 << 28)].to(torch.int64) & 0xFFFF).sum().item()) for i in range(0, flat.numel(), 1 << 28))
+            e2e_ok = host_sum == dev_sum
             e2e = {"value": world * raw_bytes * e_steps / t_e2e / 1e9, "unit": "GB/s", "steps": e_steps,
                    "h2d_bytes_per_step": raw_bytes + int(b.size), "d2h_bytes_per_step": int(b.size) + raw_bytes,
-                   "api": "SQY_PipelineEncode_UI16 + SQY_Decode_UI16, pinned host buffers"}
+                   "api": "SQY_PipelineEncode_UI16 + SQY_Decode_UI16, pinned host buffers", "same_voxels_as_device_path": e2e_ok}
             del h_vol, h_blob, h_out
         except Exception as exc:  # pinned allocation can fail on small hosts; report instead of dying
             e2e = {"value": None, "unit": "GB/s", "error": repr(exc), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
