@@ -250,18 +250,21 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
       C0 = (L6 ^ L7 ^ L8) & Ms;                          // code = number of the planes L6,L7,L8 that are set: 5,6,7,>=8 bytes
       C1 = L7 & Ms;
       S.segHM[tid] = ~Ms & valid;                        // positions that still want a hash candidate
+      S.segHC0[tid] = 0;                                 // (a segment nobody looks up in keeps HM = wants = 0 and these zeros)
+      S.segHC1[tid] = 0;
     }
     __syncthreads();
 
     // ---------------- phase A2: hash candidates for the positions without a short-offset match ----------------
-    // 32 rounds of 512 positions against a 4096-entry table of earlier positions; a warp whose segment is fully covered
-    // by short-offset matches skips the round. Only the positions that look up are inserted.
+    // 32 rounds of 512 positions against a 4096-entry table of earlier positions. This warp covers segment 16 r + warp in
+    // round r; `myrounds` has the rounds in which that segment looks anything up (a quarter of them on bit planes), in the
+    // others the warp only meets the round's barrier. Only the positions that look up are inserted.
+    const uint32_t myrounds = __ballot_sync(0xffffffffu, S.segHM[lane * kWarps + warp] != 0u);
     int nfound = Ms != 0;
     for (int r = 0; r < kB / kThreads; ++r) {
-      const int seg = r * kWarps + warp;   // this warp covers exactly one segment per round
-      const uint32_t ns = S.segHM[seg];
-      uint32_t HM = 0, HC0 = 0, HC1 = 0;
-      if (ns) {
+      if ((myrounds >> r) & 1u) {
+        const int seg = r * kWarps + warp;
+        const uint32_t ns = S.segHM[seg];
         const int i = r * kThreads + tid;
         bool found = false;
         int code = 0;
@@ -287,16 +290,16 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
           }
           S.htab[h] = (uint16_t)i;
         }
-        HM = __ballot_sync(0xffffffffu, found);
-        HC0 = __ballot_sync(0xffffffffu, found && (code & 1));
-        HC1 = __ballot_sync(0xffffffffu, found && (code & 2));
+        const uint32_t HM = __ballot_sync(0xffffffffu, found);
+        const uint32_t HC0 = __ballot_sync(0xffffffffu, found && (code & 1));
+        const uint32_t HC1 = __ballot_sync(0xffffffffu, found && (code & 2));
+        if (lane == 0) {
+          S.segHM[seg] = HM;
+          S.segHC0[seg] = HC0;
+          S.segHC1[seg] = HC1;
+        }
+        nfound |= HM != 0;
       }
-      if (lane == 0) {
-        S.segHM[seg] = HM;
-        S.segHC0[seg] = HC0;
-        S.segHC1[seg] = HC1;
-      }
-      nfound |= HM != 0;
       __syncthreads();   // one barrier per round keeps the warps within a round of each other
     }
     const int any_found = __syncthreads_or(nfound);
