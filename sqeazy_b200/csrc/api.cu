@@ -164,12 +164,15 @@ int estimate_background(Arena& A, const uint16_t* d_src, uint64_t Z, uint64_t Y,
       if (zs[k] >= Z) continue;  // Z < 3: the reference would read out of bounds; we skip those rows
       CKK(k_histogram_u16(d_src + zs[k] * frame + ys[i] * X, X, d_h + (2 + i) * 65536, st));
     }
-  std::vector<uint32_t> h(4 * 65536);
-  CK(cudaMemcpyAsync(h.data(), d_h, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  // support index of the four histograms on the device; 64 bytes come back instead of 1 MiB of bins
+  uint32_t* d_idx = d_h + 4 * 65536;
+  CKK(k_support_index(d_h, 4, 0.99f, d_idx, st));
+  uint32_t idx[16];
+  CK(cudaMemcpyAsync(idx, d_idx, sizeof(idx), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   float mn = 0.f;
   for (int i = 0; i < 4; ++i) {
-    supports[i] = histogram_support(h.data() + i * 65536, 0.99f);
+    supports[i] = support_from_index(idx[4 * i], idx[4 * i + 1], idx[4 * i + 2]);
     if (i == 0 || supports[i] < mn) mn = supports[i];
   }
   *threshold = (int)(uint16_t)mn;  // remove_background_scheme(raw_type) ctor truncates

@@ -25,6 +25,9 @@ int k_remove_background8(const uint8_t* in, uint8_t* out, uint64_t n, int thresh
 
 // quantise.cu
 int k_histogram_u16(const uint16_t* in, uint64_t n, uint32_t* hist /* 65536 x u32, accumulated into */, cudaStream_t st);
+// per histogram h: out[4h] = first bin whose cumulative share exceeds `threshold` (65536: none), out[4h+1] = bins[m],
+// out[4h+2] = bins[m-1] (hist_impl.hpp:63-84,359-381)
+int k_support_index(const uint32_t* hist_dev, int nhist, float threshold, uint32_t* out_dev, cudaStream_t st);
 int k_lut_apply(const uint16_t* in, uint8_t* out, uint64_t n, const uint8_t* lut_dev /* 65536 */, cudaStream_t st);
 int k_lut_decode(const uint8_t* in, uint16_t* out, uint64_t n, const uint16_t* lut_dev /* 256 */, cudaStream_t st);
 

@@ -57,6 +57,65 @@ __global__ void histogram_u16_small_kernel(const uint16_t* __restrict__ in, uint
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(&hist[in[i]], 1u);
 }
 
+// calc_support (hist_impl.hpp:359-381) + support_index (:63-84) for one 65536-bin histogram per CTA: the first bin m
+// whose cumulative share exceeds `thr`, and the two bin counts the support value is interpolated from. The sums are
+// integers below 2^53, so the double-precision running sums of the reference are reproduced exactly in any order; the
+// int-typed total wraps like std::accumulate(..., 0) does. out[4*h .. 4*h+3] = {m (65536 = none), bins[m], bins[m-1], 0}.
+__global__ void __launch_bounds__(1024) support_index_kernel(const uint32_t* __restrict__ hist, float thr, uint32_t* __restrict__ out) {
+  __shared__ unsigned long long ws64[32];
+  __shared__ uint32_t ws32[32];
+  __shared__ uint32_t best;
+  const uint32_t* bins = hist + (size_t)blockIdx.x * 65536;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned long long s64 = 0;
+  uint32_t s32 = 0;
+  const uint4* mine = reinterpret_cast<const uint4*>(bins + tid * 64);
+#pragma unroll 4
+  for (int k = 0; k < 16; ++k) {
+    const uint4 v = mine[k];
+    s64 += (unsigned long long)v.x + v.y + v.z + v.w;
+    s32 += v.x + v.y + v.z + v.w;
+  }
+  unsigned long long inc = s64;
+  uint32_t tot = s32;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+    tot += __shfl_xor_sync(0xffffffffu, tot, d);
+  }
+  if (lane == 31) ws64[warp] = inc;
+  if (lane == 0) ws32[warp] = tot;
+  if (tid == 0) best = 65536u;
+  __syncthreads();
+  unsigned long long running = inc - s64;
+  uint32_t isum = 0;
+  for (int w = 0; w < 32; ++w) {
+    if (w < warp) running += ws64[w];
+    isum += ws32[w];
+  }
+  const double total = (double)(int)isum;
+  const double limit = (double)thr;
+  // only the thread whose 64 bins cross the limit has to walk them (the shares grow monotonically for total > 0; for a
+  // wrapped, non-positive total every thread walks, as the reference's loop would)
+  const bool may_cross = !(total > 0.0) || ((double)(running + s64) / total) > limit;
+  if (may_cross) {
+#pragma unroll 1
+    for (int k = 0; k < 64; ++k) {
+      running += bins[tid * 64 + k];
+      if (((double)running / total) > limit) { atomicMin(&best, (uint32_t)(tid * 64 + k)); break; }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t m = best & 0xffffu;   // (uint16_t)support: 65536 -> 0
+    out[4 * blockIdx.x + 0] = best;
+    out[4 * blockIdx.x + 1] = m ? bins[m] : 0u;
+    out[4 * blockIdx.x + 2] = m ? bins[m - 1] : 0u;
+    out[4 * blockIdx.x + 3] = 0u;
+  }
+}
+
 // u16 -> u8 through a 65536-entry table staged in shared memory (64 KiB)
 __global__ void __launch_bounds__(512) lut_apply_kernel(const uint16_t* __restrict__ in, uint8_t* __restrict__ out,
                                                         uint64_t n, const uint8_t* __restrict__ lut) {
@@ -118,6 +177,13 @@ int k_histogram_u16(const uint16_t* in, uint64_t n, uint32_t* hist, cudaStream_t
   const size_t smem = kSmemBins * sizeof(uint32_t);
   SQYB_CUDA_OK(cudaFuncSetAttribute(histogram_u16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   histogram_u16_kernel<<<kNumSMs, kHistThreads, smem, st>>>(in, n, hist);
+  SQYB_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+int k_support_index(const uint32_t* hist_dev, int nhist, float threshold, uint32_t* out_dev, cudaStream_t st) {
+  if (nhist <= 0) return 0;
+  support_index_kernel<<<nhist, 1024, 0, st>>>(hist_dev, threshold, out_dev);
   SQYB_COUNT_LAUNCH(1);
   return (int)cudaGetLastError();
 }

@@ -90,11 +90,15 @@ float histogram_support(const uint32_t* bins, float threshold) {
     if ((running / total) > threshold) { support = i; break; }
   }
   const uint16_t m = (uint16_t)support;  // 65536 -> 0
-  if (m > 0) {
-    const uint32_t num = bins[m] * (uint32_t)m + bins[m - 1] * (uint32_t)(m - 1);  // u32 wrap-around
-    result = float(num) / float(bins[m - 1] + bins[m]);
-  }
-  return result;
+  return support_from_index(support, m ? bins[m] : 0u, m ? bins[m - 1] : 0u);
+}
+
+// hist_impl.hpp:63-84: interpolation between the two bins around the support index (products and sum in uint32)
+float support_from_index(uint32_t support, uint32_t bin_m, uint32_t bin_m1) {
+  const uint16_t m = (uint16_t)support;  // 65536 -> 0
+  if (m == 0) return 0.f;
+  const uint32_t num = bin_m * (uint32_t)m + bin_m1 * (uint32_t)(m - 1);  // u32 wrap-around
+  return float(num) / float(bin_m1 + bin_m);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@ namespace sqyb {
 void quantiser_luts_from_histogram(const uint32_t* hist, uint8_t* enc, uint16_t* dec);
 
 // calc_support(0.99f) of a 65536-bin u32 histogram exactly as the reference computes it.
+float support_from_index(uint32_t support, uint32_t bin_m, uint32_t bin_m1);
 float histogram_support(const uint32_t* bins, float threshold);
 
 // L2 cache size in bytes as compass::runtime::size::cache::level(2) reports it on this host;
