@@ -118,3 +118,49 @@ def test_large_ragged_frame_uses_the_tiled_table_build(sq, cuda):
     assert sq.lz4_decode_device(payload, out[:n]) == n
     assert cuda.equal(out[:n], a)
     assert bool((out[n:] == 0x77).all())
+
+
+def _mixed_content(rng, n):
+    """runs, short and long periods, text-like low-entropy bytes, noise, long literal stretches — in random order"""
+    parts, total = [], 0
+    while total < n:
+        kind = rng.integers(0, 7)
+        m = int(rng.integers(1, 6000))
+        if kind == 0:
+            p = np.full(m, rng.integers(0, 256), np.uint8)
+        elif kind == 1:
+            per = int(rng.integers(1, 40))
+            p = np.tile(rng.integers(0, 256, per, dtype=np.uint8), m // per + 1)[:m]
+        elif kind == 2:
+            per = int(rng.integers(40, 5000))
+            p = np.tile(rng.integers(0, 256, per, dtype=np.uint8), m // per + 2)[:m]
+        elif kind == 3:
+            p = rng.integers(0, 4, m, dtype=np.uint8) * 17
+        elif kind == 4:
+            p = rng.integers(0, 256, m, dtype=np.uint8)
+        elif kind == 5 and parts:
+            src = parts[int(rng.integers(0, len(parts)))]
+            p = np.tile(src, m // max(src.size, 1) + 1)[:m].copy()        # far repeat of something seen earlier
+            if p.size > 10:
+                p[rng.integers(0, p.size, max(1, p.size // 50))] ^= 1    # with sparse differences
+        else:
+            p = (rng.random(m) < 0.06).astype(np.uint8) * rng.integers(1, 256, m, dtype=np.uint8)
+        parts.append(p)
+        total += p.size
+    return np.concatenate(parts)[:n]
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_mixed_streams_from_liblz4_and_own_encoder(sq, cuda, ref, decoder, seed):
+    """the batch walk, the single-sequence path, near / far / overlapping copies and the length chains of both decoders
+    on streams with every kind of sequence: liblz4 frames (64 KiB and 256 KiB blocks, linked and independent) and our own"""
+    rng = np.random.default_rng(1000 + seed)
+    a = _mixed_content(rng, int(rng.integers(200_000, 900_000)))
+    configs = ((1, b""), (4, b""), (2, b"blocksize_kb=64,framestep_kb=64"), (3, b"n_chunks_of_input=3"))
+    nthreads, config = configs[seed % len(configs)]
+    for payload in (ref.lz4_encode(a, nthreads=nthreads, config=config), sq.lz4_encode_device(dev(cuda, a)).cpu().numpy()):
+        out = cuda.full((a.size + 32,), 0x42, dtype=cuda.uint8, device="cuda")
+        assert sq.lz4_decode_device(dev(cuda, payload), out[: a.size]) == a.size
+        h = out.cpu().numpy()
+        assert np.array_equal(h[: a.size], a)
+        assert np.all(h[a.size:] == 0x42)

@@ -438,3 +438,30 @@ def test_large_volume_roundtrip_properties(sq, cuda):
     assert int((out.to(cuda.int32) & 0xFFFF).max()) <= int((vol.to(cuda.int32) & 0xFFFF).max())
     st = sq.last_lz4_stats()
     assert st["constant_blocks"] + st["general_blocks"] + st["stored_blocks"] == 256 * 512 * 512 * 2 // 16384
+
+
+def test_concurrent_callers(sq, cuda, port):
+    """the reference's entry points are re-entrant; here concurrent host threads are serialised inside the
+    library: four threads encode and decode different volumes through the host-pointer API at the same time"""
+    import threading
+
+    vols = [numpy_volume((8, 64, 96), "scmos", index=40 + i) for i in range(4)]
+    results, errors = [None] * 4, []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                blob = sq.encode("rmestbkrd->bitswap1->lz4" if i % 2 else "bitswap1->lz4", vols[i])
+                results[i] = sq.decode(blob)
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
+    for i in range(4):
+        expect = port.rmestbkrd(vols[i], sq.host_l2_bytes())[0] if i % 2 else vols[i]
+        assert np.array_equal(results[i], expect)
