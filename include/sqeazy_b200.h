@@ -32,6 +32,16 @@ int sqyx_encode_device_ex_UI16(const char* pipeline, const void* d_src, const lo
 /* d_blob: [header][payload] in device memory; d_dst: device buffer of dst_capacity bytes (>= raw bytes). */
 int sqyx_decode_device_UI16(const void* d_blob, long blob_bytes, void* d_dst, long dst_capacity, void* stream);
 
+/* ---- batches of independent stacks: a time-lapse or a set of stacks (BASELINE cfg4, cfg5; the reference loops over files,
+ * src/cpp/src/verbs/compress.hpp:204-338, one stack after the other). Up to 8 stacks are in flight on streams and scratch
+ * of their own, so the block decoders / encoders of different stacks share the SMs (a single stack of few large LZ4
+ * blocks is bound by the serial chain of its slowest block). All stacks of an encode batch share pipeline and shape.
+ * rcs (may be NULL) receives the per-stack return codes; the call returns 0 when all of them are 0. Synchronous. */
+int sqyx_decode_batch_device_UI16(int n, const void* const* d_blobs, const long* blob_bytes, void* const* d_dsts,
+                                  const long* dst_capacities, int* rcs);
+int sqyx_encode_batch_device_UI16(int n, const char* pipeline, const void* const* d_srcs, const long* shape, unsigned shape_size,
+                                  void* const* d_dsts, const long* dst_capacities, long* dst_bytes, int* rcs);
+
 /* ---- single stages (what the parity tests drive) ---- */
 
 /* bitswapN, w in {1,2,4,8}; threshold > 0 fuses remove_background(threshold) into the load.

@@ -35,7 +35,7 @@ SQYX_SYMBOLS = [
     "sqyx_lz4_decode", "sqyx_device_count", "sqyx_kernel_launches", "sqyx_last_lz4_stats", "sqyx_host_l2_bytes",
     "sqyx_release_scratch", "sqyx_set_lz4_lane_max", "sqyx_set_device", "sqyx_enable_stage_timing", "sqyx_stage_ms", "sqyx_histogram_support",
     "sqyx_rmest_frame_portion", "sqyx_encode_device_UI8", "sqyx_decode_device_UI8", "sqyx_bitswap_encode_UI8",
-    "sqyx_bitswap_decode_UI8", "sqyx_remove_background_UI8",
+    "sqyx_bitswap_decode_UI8", "sqyx_remove_background_UI8", "sqyx_decode_batch_device_UI16", "sqyx_encode_batch_device_UI16",
 ]
 
 _lib = None
@@ -241,6 +241,50 @@ def decode_device(blob, out, stream=None):
     if rc != 0:
         raise SqeazyError(f"sqyx_decode_device_UI16 returned {rc}")
     return out
+
+
+
+def decode_batch_device(blobs, outs):
+    """sqyx_decode_batch_device_UI16: a batch of independent stacks (time-lapse, cfg4) decoded concurrently, up to 8 in
+    flight on streams and scratch of their own. blobs / outs: lists of CUDA tensors. Synchronous."""
+    import torch
+    n = len(blobs)
+    assert n == len(outs) and all(b.is_cuda and b.is_contiguous() for b in blobs) and all(o.is_cuda and o.is_contiguous() for o in outs)
+    torch.cuda.current_stream().synchronize()   # the batch runs on the library's own streams
+    bp = (c_void_p * n)(*[b.data_ptr() for b in blobs])
+    bn = (c_long * n)(*[b.numel() for b in blobs])
+    op = (c_void_p * n)(*[o.data_ptr() for o in outs])
+    on = (c_long * n)(*[o.numel() * o.element_size() for o in outs])
+    rcs = (c_int * n)()
+    rc = lib().sqyx_decode_batch_device_UI16(c_int(n), bp, bn, op, on, rcs)
+    if rc != 0:
+        raise SqeazyError(f"sqyx_decode_batch_device_UI16 returned {list(rcs)}")
+    return outs
+
+
+def encode_batch_device(pipeline: str, volumes, outs=None):
+    """sqyx_encode_batch_device_UI16: stacks of one shape through one pipeline, up to 8 in flight. Returns uint8 CUDA views."""
+    import torch
+    n = len(volumes)
+    if n == 0:
+        return []
+    v0 = volumes[0]
+    assert all(v.is_cuda and v.element_size() == 2 and v.is_contiguous() and v.shape == v0.shape for v in volumes)
+    cap = max_compressed_length(pipeline, v0.numel() * 2)
+    if outs is None:
+        outs = [torch.empty(cap, dtype=torch.uint8, device=v0.device) for _ in range(n)]
+    assert len(outs) == n and all(o.numel() >= cap for o in outs)
+    torch.cuda.current_stream().synchronize()
+    shp = (c_long * v0.dim())(*v0.shape)
+    sp = (c_void_p * n)(*[v.data_ptr() for v in volumes])
+    op = (c_void_p * n)(*[o.data_ptr() for o in outs])
+    on = (c_long * n)(*[o.numel() for o in outs])
+    nb = (c_long * n)()
+    rcs = (c_int * n)()
+    rc = lib().sqyx_encode_batch_device_UI16(c_int(n), pipeline.encode("latin-1"), sp, shp, c_uint(v0.dim()), op, on, nb, rcs)
+    if rc != 0:
+        raise SqeazyError(f"sqyx_encode_batch_device_UI16({pipeline!r}) returned {list(rcs)}")
+    return [o[: nb[i]] for i, o in enumerate(outs)]
 
 
 def bitswap_encode_device(w: int, src, dst, threshold: int = 0, stream=None):

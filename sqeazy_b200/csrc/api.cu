@@ -5,12 +5,14 @@
 // every compute entry point fails with 1.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sqeazy.h"
@@ -20,6 +22,7 @@
 #include "host/numerics.hpp"
 #include "host/pipeline.hpp"
 #include "host/text.hpp"
+#include "staging.hpp"
 
 using namespace sqyb;
 
@@ -84,6 +87,11 @@ struct Arena {
 
 std::mutex g_mu;
 Arena g_arena[16];
+// batch entry points (sqyx_*_batch_device_*): every lane of a batch has its own stream and scratch, so the kernels of
+// different stacks share the SMs instead of queueing behind each other's tails
+constexpr int kBatchLanes = 8;
+Arena g_batch_arena[16][kBatchLanes];
+cudaStream_t g_batch_stream[16][kBatchLanes] = {};
 
 // ---- optional per-stage CUDA-event timing (sqyx_enable_stage_timing) ----
 enum StageTimer { kTFilterSwap = 0, kTLz4Enc, kTHist, kTLutApply, kTLz4Dec, kTLutDec, kTSwapDec, kNumTimers };
@@ -334,6 +342,40 @@ int encode_device_impl(Arena& A, const Pipeline& pl_in, const void* d_src_any, c
   return 0;
 }
 
+// ---- shared by the streamed host paths (host_encode_streamed below, the host sink of decode_device_impl) ----
+constexpr uint64_t kStreamSlabBytes = uint64_t(256) << 20;
+constexpr uint64_t kStreamMinBytes = uint64_t(512) << 20;
+constexpr uint64_t kStreamGrainVoxels = 131072;   // a 16 KiB block of a 1-bit plane covers 131072 voxels (8192 * P for wider atoms)
+cudaStream_t g_copy_stream[16] = {};
+
+int copy_stream(cudaStream_t* cs) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev >= 16) return 1;
+  if (!g_copy_stream[dev]) CK(cudaStreamCreateWithFlags(&g_copy_stream[dev], cudaStreamNonBlocking));
+  *cs = g_copy_stream[dev];
+  return 0;
+}
+
+struct EventList {
+  std::vector<cudaEvent_t> ev;
+  ~EventList() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+  int next(cudaEvent_t* out) {
+    cudaEvent_t e = nullptr;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ev.push_back(e);
+    *out = e;
+    return 0;
+  }
+};
+
+// where decode_device_impl may deliver the volume slab by slab while the last inverse transpose is still running
+struct HostSink {
+  char* dst;
+  int nthreads;
+  bool done = false;
+};
+
 // ---- decode ----
 int lz4_decode_checked(Arena& A, const uint8_t* src, uint64_t nbytes, uint8_t* dst, uint64_t dst_bytes, uint64_t* decoded,
                        cudaStream_t st) {
@@ -361,7 +403,7 @@ int lz4_decode_checked(Arena& A, const uint8_t* src, uint64_t nbytes, uint8_t* d
 }
 
 int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const uint8_t* d_payload, uint64_t payload_bytes,
-                       void* d_dst_any, uint64_t dst_cap, cudaStream_t st) {
+                       void* d_dst_any, uint64_t dst_cap, cudaStream_t st, HostSink* host = nullptr) {
   const uint64_t N = shape_product(hdr.shape);
   const bool u8 = pl.elem == 1;
   const uint64_t raw_bytes = (uint64_t)pl.elem * N;
@@ -453,6 +495,29 @@ int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const ui
       // pick the scratch buffer that does not hold `cur`
       if (scratch(cur == bufs[0] ? 1 : 0, &out)) return 1;
     }
+    if (remaining == 0 && host && !u8 && raw_bytes >= kStreamMinBytes && N % 128 == 0 && !g_timing.load() &&
+        ((((uintptr_t)cur) | ((uintptr_t)out)) & 31) == 0) {
+      // last stage of a host call: transpose back slab by slab, every slab leaves for the host as soon as it is done
+      cudaStream_t cs = nullptr;
+      if (copy_stream(&cs)) return 1;
+      EventList events;
+      const uint64_t slab = kStreamSlabBytes / 2;
+      for (uint64_t first = 0; first < N; first += slab) {
+        if (k_bitswap_decode_range(swaps[k], cur, out, N, first, std::min(slab, N - first), st)) return 100 + 1;
+        cudaEvent_t e = nullptr;
+        if (events.next(&e)) return 1;
+        CK(cudaEventRecord(e, st));
+      }
+      size_t i = 0;
+      for (uint64_t first = 0; first < N; first += slab, ++i) {
+        CK(cudaStreamWaitEvent(cs, events.ev[i], 0));
+        CK((cudaError_t)staged_d2h(host->dst + 2 * first, out + first, 2 * std::min(slab, N - first), host->nthreads, cs));
+      }
+      CK(cudaStreamSynchronize(cs));
+      host->done = true;
+      cur = out;
+      continue;
+    }
     {
       ScopedStageTimer tm(kTSwapDec, st);
       if (u8 ? k_bitswap8_decode(swaps[k], reinterpret_cast<const uint8_t*>(cur), reinterpret_cast<uint8_t*>(out), N, st)
@@ -534,6 +599,10 @@ int sqyx_release_scratch(void) {
   if (current_arena(&A)) return 1;
   cudaDeviceSynchronize();
   A->release();
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev < 16)
+    for (int l = 0; l < kBatchLanes; ++l) g_batch_arena[dev][l].release();
+  staging_release();
   return 0;
 }
 
@@ -582,6 +651,82 @@ int sqyx_decode_device_UI16(const void* d_blob, long blob_bytes, void* d_dst, lo
   } catch (...) {
     return 1;
   }
+}
+
+// ---- batches of independent stacks (time-lapse, cfg4/cfg5): lanes of one stack each, run concurrently ----
+extern "C++" {
+namespace {
+template <class Fn>
+int run_batch(int n, int* rcs, Fn&& one) {
+  if (n < 0) return 1;
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_mu);
+  Arena* A0 = nullptr;
+  if (current_arena(&A0)) return 1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev >= 16) return 1;
+  const int lanes = n < kBatchLanes ? n : kBatchLanes;
+  for (int l = 0; l < lanes; ++l)
+    if (!g_batch_stream[dev][l] && cudaStreamCreateWithFlags(&g_batch_stream[dev][l], cudaStreamNonBlocking) != cudaSuccess) return 1;
+  const int timing = g_timing.exchange(0);   // the stage timers are per call, not per lane
+  std::vector<int> rc((size_t)n, 1);
+  std::vector<std::thread> th;
+  for (int l = 0; l < lanes; ++l)
+    th.emplace_back([&, l] {
+      if (cudaSetDevice(dev) != cudaSuccess) return;
+      for (int i = l; i < n; i += lanes) {
+        try {
+          rc[(size_t)i] = one(i, g_batch_arena[dev][l], g_batch_stream[dev][l]);
+        } catch (...) {
+          rc[(size_t)i] = 1;
+        }
+      }
+    });
+  for (auto& t : th) t.join();
+  g_timing.store(timing);
+  int bad = 0;
+  for (int i = 0; i < n; ++i) {
+    if (rcs) rcs[i] = rc[(size_t)i];
+    bad |= rc[(size_t)i] != 0;
+  }
+  return bad ? 1 : 0;
+}
+}  // namespace
+}  // extern "C++"
+
+int sqyx_decode_batch_device_UI16(int n, const void* const* d_blobs, const long* blob_bytes, void* const* d_dsts,
+                                  const long* dst_capacities, int* rcs) {
+  if (n > 0 && (!d_blobs || !blob_bytes || !d_dsts || !dst_capacities)) return 1;
+  return run_batch(n, rcs, [&](int i, Arena& A, cudaStream_t st) -> int {
+    if (!d_blobs[i] || blob_bytes[i] <= 0 || !d_dsts[i] || dst_capacities[i] < 0) return 1;
+    Header hdr;
+    if (parse_blob_header_device(static_cast<const uint8_t*>(d_blobs[i]), (uint64_t)blob_bytes[i], hdr, st)) return 1;
+    if (sizeof_typename(hdr.raw_type) != 2) return 1;
+    Pipeline pl;
+    if (!build_pipeline_u16(hdr.pipeline, pl) || pl.empty()) return 1;
+    return decode_device_impl(A, hdr, pl, static_cast<const uint8_t*>(d_blobs[i]) + hdr.size, (uint64_t)blob_bytes[i] - hdr.size,
+                              d_dsts[i], (uint64_t)dst_capacities[i], st);
+  });
+}
+
+int sqyx_encode_batch_device_UI16(int n, const char* pipeline, const void* const* d_srcs, const long* shape, unsigned shape_size,
+                                  void* const* d_dsts, const long* dst_capacities, long* dst_bytes, int* rcs) {
+  if (!pipeline || !shape || (n > 0 && (!d_srcs || !d_dsts || !dst_capacities || !dst_bytes))) return 1;
+  Pipeline pl;
+  try {
+    if (!build_pipeline_u16(pipeline, pl) || pl.empty()) return 1;
+  } catch (...) {
+    return 1;
+  }
+  const std::vector<uint64_t> shp = to_shape(shape, shape_size);
+  return run_batch(n, rcs, [&](int i, Arena& A, cudaStream_t st) -> int {
+    if (!d_dsts[i] || dst_capacities[i] < 0) return 1;
+    uint64_t out = 0;
+    const int rc = encode_device_impl(A, pl, d_srcs[i], shp, static_cast<uint8_t*>(d_dsts[i]), (uint64_t)dst_capacities[i], &out,
+                                      nullptr, st);
+    if (rc == 0) dst_bytes[i] = (long)out;
+    return rc;
+  });
 }
 
 int sqyx_encode_device_UI8(const char* pipeline, const void* d_src, const long* shape, unsigned shape_size, void* d_dst,
@@ -871,7 +1016,98 @@ int SQY_Pipeline_Max_Compressed_Length_3D_UI8(const char* pipeline, long* shape,
   }
 }
 
-static int host_encode(int elem, const char* pipeline, const char* src, long* shape, unsigned shape_size, char* dst, long* dstlength) {
+// ---- streamed host paths: the PCIe hop of a large stack overlaps the kernels ----
+// `[remove_background | rmestbkrd ->] bitswapN -> lz4` on uint16 (the headline pipelines): the stack arrives in z-slabs on a
+// copy stream; as soon as a slab is there it is filtered + transposed into its place in the plane-major buffer and the
+// 16 KiB LZ4 blocks it completes in each of the 16/N bit planes are compressed, while the next slab is still on the bus.
+// Only the last slab's kernels, the offset scan and the compaction remain after the last byte has arrived. Decode: the final
+// inverse transpose runs slab by slab and every slab leaves for the host as soon as it is done.
+bool streamable_encode(const Pipeline& pl, const std::vector<uint64_t>& shape, uint64_t N) {
+  if (pl.elem != 2 || !pl.has_sink || pl.sink.kind != StageKind::Lz4 || pl.has_tail) return false;
+  if (2 * N < kStreamMinBytes || N % kStreamGrainVoxels) return false;
+  if (pl.head.size() == 1) return pl.head[0].kind == StageKind::Bitswap;
+  if (pl.head.size() != 2 || pl.head[1].kind != StageKind::Bitswap) return false;
+  if (pl.head[0].kind == StageKind::RmEstBkrd) return shape.size() == 3 && shape[0] >= 3;
+  return pl.head[0].kind == StageKind::RemoveBackground;
+}
+
+// returns 0 and the blob size, or an error; the caller has checked streamable_encode()
+int host_encode_streamed(Arena& A, const Pipeline& pl, const char* src, const std::vector<uint64_t>& shape, uint64_t N, char* dst,
+                         uint64_t cap, uint64_t* out_bytes, int nthreads) {
+  const uint64_t raw_bytes = 2 * N;
+  cudaStream_t st = nullptr, cs = nullptr;
+  if (copy_stream(&cs)) return 1;
+  void *d_in_v = nullptr, *d_out_v = nullptr, *d_planes_v = nullptr, *ws = nullptr;
+  if (A.get(kSlotIn, raw_bytes, &d_in_v) || A.get(kSlotOut, cap, &d_out_v) || A.get(kSlotA, raw_bytes, &d_planes_v) ||
+      A.get(kSlotWs, k_lz4_encode_workspace_bytes(raw_bytes), &ws))
+    return 1;
+  uint16_t* d_in = static_cast<uint16_t*>(d_in_v);
+  uint16_t* d_planes = static_cast<uint16_t*>(d_planes_v);
+  uint8_t* d_out = static_cast<uint8_t*>(d_out_v);
+  const size_t reserve = header_reserve_bytes(pl, shape);
+  if (cap < reserve || cap - reserve < lz4_payload_bound(raw_bytes)) return 1;
+  uint8_t* payload = d_out + reserve;
+  const Stage& swap = pl.head.back();
+  const int P = 16 / swap.w;
+
+  int thr = 0;
+  if (pl.head.size() == 2) {
+    thr = pl.head[0].threshold;
+    if (pl.head[0].kind == StageKind::RmEstBkrd) {
+      // the estimate samples the two z faces and six border rows: those voxels go first
+      const uint64_t Z = shape[0], Y = shape[1], X = shape[2], frame = Y * X;
+      const uint64_t portion = rmest_frame_portion(frame, host_l2_cache_bytes());
+      const uint16_t* h = reinterpret_cast<const uint16_t*>(src);
+      CK(cudaMemcpyAsync(d_in, h, 2 * portion, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(d_in + (Z - 1) * frame, h + (Z - 1) * frame, 2 * portion, cudaMemcpyHostToDevice, st));
+      const uint64_t zs[3] = {1, Z / 2, Z - 2}, ys[2] = {0, Y - 1};
+      for (uint64_t z : zs)
+        for (uint64_t y : ys) CK(cudaMemcpyAsync(d_in + z * frame + y * X, h + z * frame + y * X, 2 * X, cudaMemcpyHostToDevice, st));
+      float sup[4];
+      ScopedStageTimer tm(kTFilterSwap, st);
+      if (estimate_background(A, d_in, Z, Y, X, -1, sup, &thr, st)) return 1;
+    }
+  }
+
+  CKK(k_lz4_encode_begin(raw_bytes, payload, ws, st));
+  const uint64_t slab_voxels = kStreamSlabBytes / 2;          // a multiple of the grain
+  const uint32_t blocks_per_plane = (uint32_t)(raw_bytes / P / kLz4BlockBytes);
+  EventList events;
+  for (uint64_t first = 0; first < N; first += slab_voxels) {
+    const uint64_t count = std::min(slab_voxels, N - first);
+    CK((cudaError_t)staged_h2d(d_in + first, src + 2 * first, 2 * count, nthreads, cs));
+    cudaEvent_t arrived = nullptr;
+    if (events.next(&arrived)) return 1;
+    CK(cudaEventRecord(arrived, cs));
+    CK(cudaStreamWaitEvent(st, arrived, 0));
+    CKK(k_bitswap_encode_range(swap.w, d_in, d_planes, N, first, count, thr, st));
+    // plane piece of this slab: bytes [2*first/P, 2*(first+count)/P) of every plane
+    CKK(k_lz4_encode_blocks(reinterpret_cast<const uint8_t*>(d_planes), raw_bytes, payload, ws,
+                            (uint32_t)(2 * first / P / kLz4BlockBytes), (uint32_t)(2 * count / P / kLz4BlockBytes), (uint32_t)P,
+                            blocks_per_plane, st));
+  }
+  CKK(k_lz4_encode_end(reinterpret_cast<const uint8_t*>(d_planes), raw_bytes, payload, ws, st));
+  unsigned long long hres[4] = {0, 0, 0, 0};
+  CK(cudaMemcpyAsync(hres, ws, 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const uint64_t payload_bytes = hres[0];
+  const uint32_t* stats = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(hres) + 16);
+  A.last_stats[0] = stats[0]; A.last_stats[1] = stats[1]; A.last_stats[2] = stats[2]; A.last_stats[3] = (long)payload_bytes;
+
+  Pipeline named = pl;
+  const std::string hdr = pack_header(named.type_name(), named.elem, shape, named.canonical(), payload_bytes);
+  if (hdr.size() > reserve) return 1;
+  std::string slot(reserve - hdr.size(), ' ');
+  slot += hdr;
+  CK(cudaMemcpyAsync(d_out, slot.data(), slot.size(), cudaMemcpyHostToDevice, st));
+  CK((cudaError_t)staged_d2h(dst, d_out, reserve + payload_bytes, nthreads, st));
+  CK(cudaStreamSynchronize(st));
+  *out_bytes = reserve + payload_bytes;
+  return 0;
+}
+
+static int host_encode(int elem, const char* pipeline, const char* src, long* shape, unsigned shape_size, char* dst, long* dstlength,
+                       int nthreads) {
   try {
     if (!pipeline || !src || !shape || !dst || !dstlength) return 1;
     Pipeline pl;
@@ -886,15 +1122,21 @@ static int host_encode(int elem, const char* pipeline, const char* src, long* sh
     std::lock_guard<std::mutex> lk(g_mu);
     Arena* A = nullptr;
     if (current_arena(&A)) return 1;
+    if (streamable_encode(pl, shp, N) && !g_timing.load()) {
+      uint64_t out = 0;
+      if (host_encode_streamed(*A, pl, src, shp, N, dst, cap, &out, nthreads)) return 1;
+      *dstlength = (long)out;
+      return 0;
+    }
     void *d_in = nullptr, *d_out = nullptr;
     if (A->get(kSlotIn, raw_bytes, &d_in) || A->get(kSlotOut, cap, &d_out)) return 1;
     cudaStream_t st = nullptr;
-    if (raw_bytes) CK(cudaMemcpyAsync(d_in, src, raw_bytes, cudaMemcpyHostToDevice, st));
+    CK((cudaError_t)staged_h2d(d_in, src, raw_bytes, nthreads, st));   // pageable buffers: nthreads host threads feed a pinned ring
     uint64_t out = 0;
     const int rc = encode_device_impl(*A, pl, d_in, shp, static_cast<uint8_t*>(d_out), cap, &out,
                                       nullptr, st);
     if (rc) return 1;
-    CK(cudaMemcpyAsync(dst, d_out, out, cudaMemcpyDeviceToHost, st));
+    CK((cudaError_t)staged_d2h(dst, d_out, out, nthreads, st));
     CK(cudaStreamSynchronize(st));
     *dstlength = (long)out;
     return 0;
@@ -903,7 +1145,7 @@ static int host_encode(int elem, const char* pipeline, const char* src, long* sh
   }
 }
 
-static int host_decode(int elem, const char* src, long srclength, char* dst) {
+static int host_decode(int elem, const char* src, long srclength, char* dst, int nthreads) {
   try {
     if (!src || !dst || srclength <= 0) return 1;
     const Header hdr = unpack_header(src, (size_t)srclength);
@@ -927,11 +1169,12 @@ static int host_decode(int elem, const char* src, long srclength, char* dst) {
     // the payload is staged at a 256-byte aligned device address, whatever the header length was
     if (A->get(kSlotIn, payload_bytes + 256, &d_in) || A->get(kSlotOut, raw_bytes, &d_out)) return 1;
     cudaStream_t st = nullptr;
-    if (payload_bytes) CK(cudaMemcpyAsync(d_in, src + hdr.size, payload_bytes, cudaMemcpyHostToDevice, st));
+    CK((cudaError_t)staged_h2d(d_in, src + hdr.size, payload_bytes, nthreads, st));
+    HostSink sink{dst, nthreads};
     const int rc = decode_device_impl(*A, hdr, pl, static_cast<const uint8_t*>(d_in), payload_bytes, d_out,
-                                      raw_bytes, st);
+                                      raw_bytes, st, &sink);
     if (rc) return rc;
-    if (raw_bytes) CK(cudaMemcpyAsync(dst, d_out, raw_bytes, cudaMemcpyDeviceToHost, st));
+    if (!sink.done) CK((cudaError_t)staged_d2h(dst, d_out, raw_bytes, nthreads, st));
     CK(cudaStreamSynchronize(st));
     return 0;
   } catch (...) {
@@ -941,13 +1184,12 @@ static int host_decode(int elem, const char* src, long srclength, char* dst) {
 
 int SQY_PipelineEncode_UI16(const char* pipeline, const char* src, long* shape, unsigned shape_size, char* dst, long* dstlength,
                             int nthreads) {
-  (void)nthreads;  // accepted for compatibility; the GPU path has no thread knob
-  return host_encode(2, pipeline, src, shape, shape_size, dst, dstlength);
+  // nthreads: host threads that stage a pageable caller buffer (staging.hpp); the kernels have no thread knob
+  return host_encode(2, pipeline, src, shape, shape_size, dst, dstlength, nthreads);
 }
 
 int SQY_Decode_UI16(const char* src, long srclength, char* dst, int nthreads) {
-  (void)nthreads;
-  return host_decode(2, src, srclength, dst);
+  return host_decode(2, src, srclength, dst, nthreads);
 }
 
 int SQY_PipelineDecode_UI16(const char* src, long srclength, char* dst, int nthreads) {
@@ -957,12 +1199,10 @@ int SQY_PipelineDecode_UI16(const char* src, long srclength, char* dst, int nthr
 // uint8 volumes (src/sqeazy.cpp:72-106, 309-335)
 int SQY_PipelineEncode_UI8(const char* pipeline, const char* src, long* shape, unsigned shape_size, char* dst, long* dstlength,
                            int nthreads) {
-  (void)nthreads;
-  return host_encode(1, pipeline, src, shape, shape_size, dst, dstlength);
+  return host_encode(1, pipeline, src, shape, shape_size, dst, dstlength, nthreads);
 }
 int SQY_Decode_UI8(const char* src, long srclength, char* dst, int nthreads) {
-  (void)nthreads;
-  return host_decode(1, src, srclength, dst);
+  return host_decode(1, src, srclength, dst, nthreads);
 }
 
 int SQY_h5_query_sizeof(const char*, const char*, unsigned*) { return 1; }

@@ -274,7 +274,53 @@ __global__ void __launch_bounds__(256) remove_background_kernel(const uint16_t* 
   }
 }
 
+// voxel range [first, first+count) of a volume of n voxels: same kernels, same plane-major destination (segment stride n/P),
+// pointers moved to the range. Ranges are cut at multiples of 128 voxels of 32-byte aligned buffers (fast kernels only).
+template <int W>
+int launch_encode_range(const uint16_t* in, uint16_t* out, uint64_t n, uint64_t first, uint64_t count, int threshold, cudaStream_t st) {
+  constexpr int P = Geo<W>::P;
+  if (count == 0) return 0;
+  if (!fast_ok(in, out, n) || first % 128 || count % 128 || first + count > n) return -3;
+  const uint64_t n32 = count / 32, S = n / P;
+  const int g = grid_for(n32, 256);
+  if (threshold > 0) bitswap_encode_fast<W, true><<<g, 256, 0, st>>>(in + first, out + first / P, n32, S, (uint32_t)threshold & 0xffffu);
+  else bitswap_encode_fast<W, false><<<g, 256, 0, st>>>(in + first, out + first / P, n32, S, 0);
+  SQYB_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+template <int W>
+int launch_decode_range(const uint16_t* in, uint16_t* out, uint64_t n, uint64_t first, uint64_t count, cudaStream_t st) {
+  constexpr int P = Geo<W>::P;
+  if (count == 0) return 0;
+  if (!fast_ok(in, out, n) || first % 128 || count % 128 || first + count > n) return -3;
+  bitswap_decode_fast<W><<<grid_for(count / 32, 256), 256, 0, st>>>(in + first / P, out + first, count / 32, n / P);
+  SQYB_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace
+
+int k_bitswap_encode_range(int w, const uint16_t* in, uint16_t* out, uint64_t n, uint64_t first, uint64_t count, int threshold,
+                           cudaStream_t st) {
+  switch (w) {
+    case 1: return launch_encode_range<1>(in, out, n, first, count, threshold, st);
+    case 2: return launch_encode_range<2>(in, out, n, first, count, threshold, st);
+    case 4: return launch_encode_range<4>(in, out, n, first, count, threshold, st);
+    case 8: return launch_encode_range<8>(in, out, n, first, count, threshold, st);
+  }
+  return -1;
+}
+
+int k_bitswap_decode_range(int w, const uint16_t* in, uint16_t* out, uint64_t n, uint64_t first, uint64_t count, cudaStream_t st) {
+  switch (w) {
+    case 1: return launch_decode_range<1>(in, out, n, first, count, st);
+    case 2: return launch_decode_range<2>(in, out, n, first, count, st);
+    case 4: return launch_decode_range<4>(in, out, n, first, count, st);
+    case 8: return launch_decode_range<8>(in, out, n, first, count, st);
+  }
+  return -1;
+}
 
 int k_bitswap_encode(int w, const uint16_t* in, uint16_t* out, uint64_t n, int threshold, cudaStream_t st) {
   switch (w) {

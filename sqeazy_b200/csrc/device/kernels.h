@@ -17,6 +17,11 @@ extern std::atomic<long> g_kernel_launches;
 int k_bitswap_encode(int w, const uint16_t* in, uint16_t* out, uint64_t n, int threshold, cudaStream_t st);
 int k_bitswap_decode(int w, const uint16_t* in, uint16_t* out, uint64_t n, cudaStream_t st);
 int k_remove_background(const uint16_t* in, uint16_t* out, uint64_t n, int threshold, cudaStream_t st);
+// voxels [first, first+count) of an n-voxel volume (in/out = whole-volume base pointers; multiples of 128 voxels): lets the
+// host entry points transpose a z-slab as soon as it has arrived / ship a slab as soon as it is transposed back
+int k_bitswap_encode_range(int w, const uint16_t* in, uint16_t* out, uint64_t n, uint64_t first, uint64_t count, int threshold,
+                           cudaStream_t st);
+int k_bitswap_decode_range(int w, const uint16_t* in, uint16_t* out, uint64_t n, uint64_t first, uint64_t count, cudaStream_t st);
 
 // bitswap8.cu (uint8 volumes)
 int k_bitswap8_encode(int w, const uint8_t* in, uint8_t* out, uint64_t n, int threshold, cudaStream_t st);
@@ -35,6 +40,13 @@ int k_lut_decode(const uint8_t* in, uint16_t* out, uint64_t n, const uint16_t* l
 size_t k_lz4_encode_workspace_bytes(uint64_t raw_bytes);
 // workspace[0..8) receives the payload size (u64) when the stream has drained; [16,28) block-kind counters
 int k_lz4_encode(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, cudaStream_t st);
+// the same in three steps, for input that becomes available piece by piece: begin (frame prefix), any number of block
+// sets — `nsets` sets of `count` consecutive 16 KiB blocks, set j starting at block first + j * set_stride (the pieces of
+// the 16/w bit planes that one z-slab contributes) —, end (offsets + compaction). Every block exactly once.
+int k_lz4_encode_begin(uint64_t raw_bytes, uint8_t* dst, void* workspace, cudaStream_t st);
+int k_lz4_encode_blocks(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, uint32_t first, uint32_t count,
+                        uint32_t nsets, uint32_t set_stride, cudaStream_t st);
+int k_lz4_encode_end(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, cudaStream_t st);
 
 // lz4_decode.cu
 size_t k_lz4_decode_workspace_bytes(uint64_t dst_bytes);

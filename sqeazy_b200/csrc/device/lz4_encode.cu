@@ -39,6 +39,8 @@ constexpr int kPad = 256;
 constexpr uint32_t kNone = 0xFFFFu;
 constexpr int kHashLog = 12;
 constexpr int kInf = 0x7FFFFFFF;
+constexpr int kEarlyRounds = 8;          // early-store test after the hash rounds of the first 4 KiB ...
+constexpr int kEarlyMin = 128;           // ... a block with fewer candidates than this is stored
 
 static_assert(kSegs == kThreads, "one segment per thread");
 
@@ -56,6 +58,7 @@ struct __align__(16) EncSmem {
   uint32_t segHM[kSegs], segHC0[kSegs], segHC1[kSegs];   // per segment: hash-candidate mask and 2-bit length code planes
   int w_T[kWarps], w_has[kWarps], w_carry_in[kWarps], w_size[kWarps], w_off[kWarps], w_first[kWarps], w_next[kWarps];
   int final_off, final_lit, total;
+  int early;                             // candidates seen by the early-store test
 };
 
 __device__ __forceinline__ int ext_bytes(int v) {
@@ -114,14 +117,434 @@ __device__ __forceinline__ void store_bytes(uint8_t* __restrict__ g, const uint3
   if (tid < nbytes - done) g[done + tid] = sb[done + tid];
 }
 
+// The general path of a block (phases A0..D on the bytes in S.data), kept out of line: the closed-form path of all-equal
+// blocks — 56 % of a background-removed stack, bound by bytes in flight — then keeps the short prologue and the register
+// allocation of a kernel that does nothing else. Returns the encoded size; `stored` when the block does not shrink.
+#ifndef SQYB_INLINE_GENERAL
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+int encode_general(EncSmem& S, const int n, bool& stored_out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint8_t* data8 = reinterpret_cast<uint8_t*>(S.data);
+  uint8_t* out8 = reinterpret_cast<uint8_t*>(S.out);
+  int csize = 0;
+  bool stored = false;
+  // (set here and not beside the block load: one more shared-memory store in the prologue cost the closed-form path of
+  //  all-equal blocks 7 %, 3.31 instead of 3.55 TB/s; two barriers lie between this store and the first atomicAdd)
+  if (tid == 0) S.early = 0;
+  // ---------------- phase A0: byte-equality bit masks for the offsets 1..4 ----------------
+  // In bit-plane data runs and 2/4-byte periods carry the long matches. A thread compares its 32-byte segment with
+  // itself shifted by d bytes (__vcmpeq4 on 8 words) and keeps one bit per position; a match of length L at i with
+  // offset d is then simply L consecutive ones in E_d starting at bit i — found, measured and extended with shifts,
+  // ANDs and ffs on registers, never touching the bytes again.
+  const int seg_lo = tid * 32;
+  {
+    uint32_t W[9];
+    W[0] = tid > 0 ? S.data[8 * tid - 1] : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) W[k + 1] = S.data[8 * tid + k];
+    const int lim = n - kLz4LastLiterals - seg_lo;     // match bytes never touch the last 5 bytes of the block
+    const uint32_t tailmask = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : (1u << lim) - 1u);
+#pragma unroll
+    for (int d = 1; d <= 4; ++d) {
+      uint32_t e = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t prev = d == 4 ? W[k] : __funnelshift_r(W[k], W[k + 1], 32 - 8 * d);   // bytes 4k-d .. 4k-d+3
+        const uint32_t eq = __vcmpeq4(W[k + 1], prev);
+        e |= (((eq & 0x08040201u) * 0x01010101u) >> 24) << (4 * k);
+      }
+      if (tid == 0) e &= ~((1u << d) - 1u);            // no source in front of the block
+      S.E[d - 1][tid] = e & tailmask;
+    }
+    if (tid < 4) S.E[tid][kSegs] = 0;
+  }
+  __syncthreads();
+
+  // ---------------- phase A1: short-offset candidates of this thread's segment (registers only) ----------------
+  uint32_t Ms = 0, D0 = 0, D1 = 0, C0 = 0, C1 = 0;     // candidate mask, offset-1 planes, length code planes
+  {
+    uint32_t L6 = 0, L7 = 0, L8 = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int d = q == 0 ? 1 : (q == 1 ? 2 : (q == 2 ? 4 : 3));   // priority order
+      // matches never cross the warp's 1 KiB sub-block: the last segment sees no successor
+      const unsigned long long e =
+          (unsigned long long)S.E[d - 1][tid] | ((unsigned long long)(lane == 31 ? 0u : S.E[d - 1][tid + 1]) << 32);
+      const unsigned long long r5 = e & (e >> 1) & (e >> 2) & (e >> 3) & (e >> 4);
+      const unsigned long long r6 = r5 & (e >> 5), r7 = r6 & (e >> 6), r8 = r7 & (e >> 7);
+      const uint32_t sel = (uint32_t)r5 & ~Ms;         // at least 5 bytes and no better-ranked offset yet
+      Ms |= sel;
+      L6 |= sel & (uint32_t)r6;
+      L7 |= sel & (uint32_t)r7;
+      L8 |= sel & (uint32_t)r8;
+      if ((d - 1) & 1) D0 |= sel;
+      if ((d - 1) & 2) D1 |= sel;
+    }
+    const int lim = n - kLz4MFLimit + 1 - seg_lo;      // a match starts at most 12 bytes before the block end
+    const uint32_t valid = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : (1u << lim) - 1u);
+    Ms &= valid;
+    C0 = (L6 ^ L7 ^ L8) & Ms;                          // code = number of the planes L6,L7,L8 that are set: 5,6,7,>=8 bytes
+    C1 = L7 & Ms;
+    S.segHM[tid] = ~Ms & valid;                        // positions that still want a hash candidate
+    S.segHC0[tid] = 0;                                 // (a segment nobody looks up in keeps HM = wants = 0 and these zeros)
+    S.segHC1[tid] = 0;
+  }
+#ifdef SQYB_NO_EARLY
+  int ncand = 0;
+  __syncthreads();
+  const int rich = 1;
+#else
+  int ncand = __reduce_add_sync(0xffffffffu, __popc(Ms));   // this warp's candidates so far (warp-uniform)
+  // (the barrier between A1 and A2 carries the one bit the early-store test needs first: a warp that is already rich in
+  //  short-offset candidates — every compressible bit-plane block — settles it for the CTA at no cost)
+  const int rich = __syncthreads_or(ncand >= kEarlyMin);
+#endif
+
+  // ---------------- phase A2: hash candidates for the positions without a short-offset match ----------------
+  // 32 rounds of 512 positions against a 4096-entry table of earlier positions. This warp covers segment 16 r + warp in
+  // round r; `myrounds` has the rounds in which that segment looks anything up (a quarter of them on bit planes), in the
+  // others the warp only meets the round's barrier. Only the positions that look up are inserted.
+  const uint32_t myrounds = __ballot_sync(0xffffffffu, S.segHM[lane * kWarps + warp] != 0u);
+  int nfound = Ms != 0;
+  // Early store: a block whose candidates (short-offset ones of the whole block + hash candidates of the first
+  // kEarlyRounds rounds = 4 KiB) are fewer than one per 32 sampled bytes is noise — camera-noise bit planes, 8-bit
+  // quantiser codes — and would shrink by < 3 % (tools/lz4_model.c: such blocks have < 70 candidates and end at
+  // 0.97..1.00 of their size, everything that compresses to <= 0.82 has > 600). It is stored without the remaining
+  // rounds, the parse and the emission, which is also what makes its decode a plain copy.
+  bool early_stored = false;
+  auto hash_round = [&](int r) {
+    if ((myrounds >> r) & 1u) {
+      const int seg = r * kWarps + warp;
+      const uint32_t ns = S.segHM[seg];
+      const int i = r * kThreads + tid;
+      bool found = false;
+      int code = 0;
+      if ((ns >> lane) & 1u) {
+        const uint32_t v = load4(S.data, i);
+        const uint32_t h = (v * 2654435761u) >> (32 - kHashLog);
+        // the table is read and written without a barrier in between: an entry may already belong to this round
+        // (any earlier position with the same 4 bytes is a valid source; c < i and the compare make it safe)
+        const uint32_t c = S.htab[h];
+        if (c < (uint32_t)i && load4(S.data, (int)c) == v) {
+          const int maxlen = min((i & ~(kSub - 1)) + kSub, n - kLz4LastLiterals) - i;
+          const uint32_t x = load4(S.data, i + 4) ^ load4(S.data, (int)c + 4);
+          int len = 4 + (x ? ((__ffs(x) - 1) >> 3) : 4);
+          if (len > maxlen) len = maxlen;
+          // 4-byte matches save one byte and cost a sequence on both ends of the codec: dropping them keeps the ratio
+          // within ~1 % on bit planes, improves it on background-removed stacks and matches liblz4 on noisy 8-bit
+          // codes (tools/lz4_model.c), while halving the number of sequences
+          if (len >= 5) {
+            found = true;
+            code = len - 5 < 3 ? len - 5 : 3;   // 0,1,2: exact length 5,6,7; 3: at least 8, extended in phase B
+            S.cand[i] = (uint16_t)c;
+          }
+        }
+        S.htab[h] = (uint16_t)i;
+      }
+      const uint32_t HM = __ballot_sync(0xffffffffu, found);
+      const uint32_t HC0 = __ballot_sync(0xffffffffu, found && (code & 1));
+      const uint32_t HC1 = __ballot_sync(0xffffffffu, found && (code & 2));
+      if (lane == 0) {
+        S.segHM[seg] = HM;
+        S.segHC0[seg] = HC0;
+        S.segHC1[seg] = HC1;
+      }
+      nfound |= HM != 0;
+      ncand += __popc(HM);
+    }
+    __syncthreads();   // one barrier per round keeps the warps within a round of each other
+  };
+  int r0 = 0, r1 = (rich || n <= kEarlyRounds * kThreads) ? kB / kThreads : kEarlyRounds;
+  while (true) {
+#pragma unroll 1
+    for (int r = r0; r < r1; ++r) hash_round(r);
+    if (r1 == kB / kThreads) break;
+    if (lane == 0 && ncand) atomicAdd(&S.early, ncand);
+    __syncthreads();
+    early_stored = S.early < kEarlyMin;
+    if (early_stored) break;
+    r0 = r1;
+    r1 = kB / kThreads;
+  }
+  const int any_found = early_stored ? 0 : __syncthreads_or(nfound);
+
+  if (!any_found) {
+    stored = true;
+  } else {
+    // ---------------- phase B: every thread parses its own 32-byte segment greedily ----------------
+    // A match may overshoot into the following segments of the same warp; their entry point moves and
+    // they re-parse until the warp's parse is stable (lane k is final after at most k+1 rounds).
+    const int limit = min((warp + 1) * kSub, n - kLz4LastLiterals);
+    const uint32_t M = Ms | S.segHM[tid];              // hash candidates exist only where no short-offset one does
+    C0 |= S.segHC0[tid];
+    C1 |= S.segHC1[tid];
+    uint32_t Sel = 0;
+    unsigned long long lens = 0;       // lengths of the long matches of this segment, 11 bits each, in order
+    // First guess of where the parse enters this segment: if the previous segment ends inside a run with period d
+    // (its last five bytes continue one), the match that covers them runs on to the end of the ones of E_d here. A
+    // segment in the middle of a long run then has nothing to parse (and nothing to measure: every lane of a run
+    // scanning to its end was 5 % of the kernel), and half of the repair parses of the cascade disappear. A wrong
+    // guess is corrected like any other moved entry point.
+    int entry = 0, exit_abs = seg_lo + 32;
+    if (lane > 0) {
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const uint32_t prevE = S.E[d][tid - 1], curE = S.E[d][tid];
+        if ((prevE >> 27) == 31u) entry = max(entry, curE == 0xffffffffu ? 32 : __ffs(~curE) - 1);
+      }
+    }
+    bool need = true;
+    while (true) {                     // cascade rounds
+      int pos = entry, nlong = 0, pj = 0, plen = 0;
+      const bool parsing = need;       // lanes whose entry did not move keep the parse of an earlier round
+      bool done = !need, pend = false;
+      if (need) { Sel = 0; lens = 0; }
+      while (true) {
+        if (!done && !pend) {
+          // thread-serial parse: bit operations only; a long match gets at most 16 more bytes here
+          while (true) {
+            if (pos >= 32) { done = true; break; }
+            const uint32_t mm = M & (0xffffffffu << pos);
+            if (!mm) { done = true; break; }
+            const int j = __ffs(mm) - 1;
+            const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
+            int len = 5 + code;
+            if (code == 3 && ((Ms >> j) & 1u)) {
+              // short-offset match: count the ones that follow in E_d, 32 positions per step
+              const int i = seg_lo + j, maxlen = limit - i;
+              const uint32_t* Ed = S.E[((D0 >> j) & 1u) | (((D1 >> j) & 1u) << 1)];
+              len = 8;
+              while (len < maxlen) {
+                const int p = i + len, avail = 32 - (p & 31);
+                const uint32_t z = ~(Ed[p >> 5] >> (p & 31));     // zeros where the match goes on
+                const int ones = z ? __ffs(z) - 1 : 32;
+                if (ones < avail) { len += ones; break; }
+                len += avail;
+              }
+              if (len > maxlen) len = maxlen;
+              lens |= (unsigned long long)len << (11 * nlong);
+              nlong++;
+            } else if (code == 3) {
+              const int i = seg_lo + j, c = (int)S.cand[i], maxlen = limit - i;
+              len = 8;
+              bool open = true;
+#pragma unroll 1
+              for (int it = 0; it < 4; ++it) {
+                if (len >= maxlen) { open = false; break; }
+                const uint32_t x = load4(S.data, i + len) ^ load4(S.data, c + len);
+                if (x) { len += (__ffs(x) - 1) >> 3; open = false; break; }
+                len += 4;
+              }
+              if (len >= maxlen) { len = maxlen; open = false; }
+              if (open) { pend = true; pj = j; plen = len; break; }   // still matching: the warp finishes it
+              lens |= (unsigned long long)len << (11 * nlong);
+              nlong++;
+            }
+            Sel |= 1u << j;
+            pos = j + len;
+          }
+        }
+        uint32_t pm = __ballot_sync(0xffffffffu, pend);
+        if (!pm) break;                // no lane is waiting => every lane is done
+        while (pm) {
+          const int l = __ffs(pm) - 1;
+          pm &= pm - 1;
+          const int i = __shfl_sync(0xffffffffu, seg_lo + pj, l);
+          const int c = (int)S.cand[i], maxlen = limit - i;
+          int len = __shfl_sync(0xffffffffu, plen, l);
+          while (len < maxlen) {       // 128 bytes per step
+            const int k = len + lane * 4;
+            const uint32_t x = load4(S.data, i + k) ^ load4(S.data, c + k);
+            const uint32_t bm = __ballot_sync(0xffffffffu, x != 0);
+            if (bm) {
+              const int f = __ffs(bm) - 1;
+              const uint32_t d = __shfl_sync(0xffffffffu, x, f);
+              len += f * 4 + ((__ffs(d) - 1) >> 3);
+              break;
+            }
+            len += 128;
+          }
+          if (len > maxlen) len = maxlen;
+          if (lane == l) {
+            lens |= (unsigned long long)len << (11 * nlong);
+            nlong++;
+            Sel |= 1u << pj;
+            pos = pj + len;
+            pend = false;
+          }
+          // later lanes whose pending match starts inside [i, i+len) parsed a stale speculation: drop them all at
+          // once (their entry point moves in the cascade step, so they are parsed again)
+          const bool stale = pend && lane > l && seg_lo + pj < i + len;
+          if (stale) { pend = false; done = true; pos = 0; Sel = 0; lens = 0; }
+          pm &= ~__ballot_sync(0xffffffffu, stale);
+        }
+      }
+      if (parsing) exit_abs = seg_lo + (pos > 32 ? pos : 32);
+      int incl = exit_abs;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl = max(incl, t);
+      }
+      int prev = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) prev = seg_lo;
+      const int ne = min(max(prev - seg_lo, 0), 32);
+      need = ne != entry;
+      entry = ne;
+      if (!__any_sync(0xffffffffu, need)) break;
+    }
+
+    // ---------------- phase C: sizes, literal carries, output offsets ----------------
+    const int seg_end = max(0, min(32, n - seg_lo));   // valid positions of this segment
+    if (entry > seg_end) entry = seg_end;
+    int nm = 0, rest = 0, F = 0, p = entry;
+    {
+      uint32_t m = Sel;
+      unsigned long long q = lens;
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
+        int len = 5 + code;
+        if (code == 3) { len = (int)(q & 0x7FF); q >>= 11; }
+        const int lit = j - p;
+        if (nm == 0) { F = lit; rest += 3 + ext_bytes(len - 4); }
+        else rest += 3 + ext_bytes(lit) + lit + ext_bytes(len - 4);
+        nm++;
+        p = j + len;
+      }
+    }
+    const int T = p < seg_end ? seg_end - p : 0;   // trailing literals, owned by a later sequence
+    const int has = nm > 0;
+    // carry scan: f_l(x) = has ? T : x + T ; combine(a,b) = (b.has ? b.T : a.T + b.T, a.has | b.has)
+    int sT = T, sH = has;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int tT = __shfl_up_sync(0xffffffffu, sT, d), tH = __shfl_up_sync(0xffffffffu, sH, d);
+      if (lane >= d) { sT = sH ? sT : tT + sT; sH |= tH; }
+    }
+    int eT = __shfl_up_sync(0xffffffffu, sT, 1), eH = __shfl_up_sync(0xffffffffu, sH, 1);   // exclusive
+    if (lane == 0) { eT = 0; eH = 0; }
+    // next segment (after this one) that owns a match
+    int nx = has ? tid : kInf;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_down_sync(0xffffffffu, nx, d);
+      if (lane + d < 32) nx = min(nx, t);
+    }
+    int nxt = __shfl_down_sync(0xffffffffu, nx, 1);
+    if (lane == 31) nxt = kInf;
+    if (lane == 31) { S.w_T[warp] = sT; S.w_has[warp] = sH; }
+    if (lane == 0) S.w_first[warp] = nx;
+    __syncthreads();
+    if (tid == 0) {
+      int x = 0;
+      for (int w = 0; w < kWarps; ++w) { S.w_carry_in[w] = x; x = S.w_has[w] ? S.w_T[w] : x + S.w_T[w]; }
+      S.final_lit = x;
+      int nn = kInf;
+      for (int w = kWarps - 1; w >= 0; --w) { S.w_next[w] = nn; nn = min(nn, S.w_first[w]); }
+    }
+    __syncthreads();
+    const int C = eH ? eT : S.w_carry_in[warp] + eT;   // literals carried into this segment's first sequence
+    if (nxt == kInf) nxt = S.w_next[warp];
+    const int size = has ? ext_bytes(C + F) + C + F + rest : 0;
+    int incl = size;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) S.w_size[warp] = incl;
+    // offsets of the selected matches, fetched before `out` starts to overwrite `cand`
+    uint32_t offs[4] = {0, 0, 0, 0};
+    {
+      uint32_t m = Sel;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (m) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          const int i = seg_lo + j;
+          const uint32_t off = ((Ms >> j) & 1u) ? 1u + ((D0 >> j) & 1u) + 2u * ((D1 >> j) & 1u) : (uint32_t)(i - (int)S.cand[i]);
+          offs[k >> 1] |= off << (16 * (k & 1));
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int off = 0;
+      for (int w = 0; w < kWarps; ++w) { S.w_off[w] = off; off += S.w_size[w]; }
+      S.final_off = off;
+      S.total = off + 1 + ext_bytes(S.final_lit) + S.final_lit;
+    }
+    __syncthreads();
+    csize = S.total;
+    if (csize >= n) {
+      stored = true;
+    } else {
+      // ---------------- phase D: emission ----------------
+      const int final_litbase = S.final_off + 1 + ext_bytes(S.final_lit) - (n - S.final_lit);
+      if (has) {
+        int o = S.w_off[warp] + incl - size;
+        uint32_t m = Sel;
+        unsigned long long q = lens;
+        int pp = entry;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
+            int len = 5 + code;
+            if (code == 3) { len = (int)(q & 0x7FF); q >>= 11; }
+            const int own = j - pp;                    // literals of this sequence inside this segment
+            const int lit = k == 0 ? C + own : own;
+            const int el = ext_bytes(lit);
+            const int ml = len - 4;
+            out8[o] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (ml < 15 ? ml : 15));
+            if (lit >= 15) put_ext(out8 + o + 1, lit);
+            int d = o + 1 + el + (lit - own);          // where this segment's own literals go
+            if (k == 0) S.seg_litbase[tid] = o + 1 + el - (seg_lo + entry - C);
+            for (int t = 0; t < own; ++t) out8[d + t] = data8[seg_lo + pp + t];
+            d += own;
+            const uint32_t off = (offs[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+            out8[d] = (uint8_t)(off & 0xff);
+            out8[d + 1] = (uint8_t)(off >> 8);
+            if (ml >= 15) put_ext(out8 + d + 2, ml);
+            o = d + 2 + ext_bytes(ml);
+            pp = j + len;
+          }
+        }
+      }
+      __syncthreads();
+      // trailing literals belong to the next sequence (or to the block's final literal run)
+      if (T > 0) {
+        const int lb = nxt == kInf ? final_litbase : S.seg_litbase[nxt];
+        for (int t = 0; t < T; ++t) out8[lb + seg_lo + p + t] = data8[seg_lo + p + t];
+      }
+      if (tid == 0) {
+        const int L = S.final_lit;
+        uint8_t* fp = out8 + S.final_off;
+        fp[0] = (uint8_t)((L < 15 ? L : 15) << 4);
+        if (L >= 15) put_ext(fp + 1, L);
+      }
+    }
+  }
+  stored_out = stored;
+  return csize;
+}
+
 __global__ void __launch_bounds__(kThreads, 3)
 lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* __restrict__ dst, uint32_t nblocks,
-                  uint8_t* __restrict__ staging, uint32_t* __restrict__ stats) {
+                  uint8_t* __restrict__ staging, uint32_t* __restrict__ stats, uint32_t first, uint32_t set_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EncSmem& S = *reinterpret_cast<EncSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  const uint32_t b = blockIdx.x;
+  const uint32_t b = first + blockIdx.y * set_stride + blockIdx.x;   // (whole stream: first = 0, one set)
   if (b >= nblocks) return;
   const uint64_t boff = (uint64_t)b * kB;
   const int n = (int)((raw_bytes - boff) < (uint64_t)kB ? (raw_bytes - boff) : (uint64_t)kB);
@@ -195,377 +618,7 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
     __syncthreads();
     csize = S.total;
   } else {
-    // ---------------- phase A0: byte-equality bit masks for the offsets 1..4 ----------------
-    // In bit-plane data runs and 2/4-byte periods carry the long matches. A thread compares its 32-byte segment with
-    // itself shifted by d bytes (__vcmpeq4 on 8 words) and keeps one bit per position; a match of length L at i with
-    // offset d is then simply L consecutive ones in E_d starting at bit i — found, measured and extended with shifts,
-    // ANDs and ffs on registers, never touching the bytes again.
-    const int seg_lo = tid * 32;
-    {
-      uint32_t W[9];
-      W[0] = tid > 0 ? S.data[8 * tid - 1] : 0u;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) W[k + 1] = S.data[8 * tid + k];
-      const int lim = n - kLz4LastLiterals - seg_lo;     // match bytes never touch the last 5 bytes of the block
-      const uint32_t tailmask = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : (1u << lim) - 1u);
-#pragma unroll
-      for (int d = 1; d <= 4; ++d) {
-        uint32_t e = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t prev = d == 4 ? W[k] : __funnelshift_r(W[k], W[k + 1], 32 - 8 * d);   // bytes 4k-d .. 4k-d+3
-          const uint32_t eq = __vcmpeq4(W[k + 1], prev);
-          e |= (((eq & 0x08040201u) * 0x01010101u) >> 24) << (4 * k);
-        }
-        if (tid == 0) e &= ~((1u << d) - 1u);            // no source in front of the block
-        S.E[d - 1][tid] = e & tailmask;
-      }
-      if (tid < 4) S.E[tid][kSegs] = 0;
-    }
-    __syncthreads();
-
-    // ---------------- phase A1: short-offset candidates of this thread's segment (registers only) ----------------
-    uint32_t Ms = 0, D0 = 0, D1 = 0, C0 = 0, C1 = 0;     // candidate mask, offset-1 planes, length code planes
-    {
-      uint32_t L6 = 0, L7 = 0, L8 = 0;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int d = q == 0 ? 1 : (q == 1 ? 2 : (q == 2 ? 4 : 3));   // priority order
-        // matches never cross the warp's 1 KiB sub-block: the last segment sees no successor
-        const unsigned long long e =
-            (unsigned long long)S.E[d - 1][tid] | ((unsigned long long)(lane == 31 ? 0u : S.E[d - 1][tid + 1]) << 32);
-        const unsigned long long r5 = e & (e >> 1) & (e >> 2) & (e >> 3) & (e >> 4);
-        const unsigned long long r6 = r5 & (e >> 5), r7 = r6 & (e >> 6), r8 = r7 & (e >> 7);
-        const uint32_t sel = (uint32_t)r5 & ~Ms;         // at least 5 bytes and no better-ranked offset yet
-        Ms |= sel;
-        L6 |= sel & (uint32_t)r6;
-        L7 |= sel & (uint32_t)r7;
-        L8 |= sel & (uint32_t)r8;
-        if ((d - 1) & 1) D0 |= sel;
-        if ((d - 1) & 2) D1 |= sel;
-      }
-      const int lim = n - kLz4MFLimit + 1 - seg_lo;      // a match starts at most 12 bytes before the block end
-      const uint32_t valid = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : (1u << lim) - 1u);
-      Ms &= valid;
-      C0 = (L6 ^ L7 ^ L8) & Ms;                          // code = number of the planes L6,L7,L8 that are set: 5,6,7,>=8 bytes
-      C1 = L7 & Ms;
-      S.segHM[tid] = ~Ms & valid;                        // positions that still want a hash candidate
-      S.segHC0[tid] = 0;                                 // (a segment nobody looks up in keeps HM = wants = 0 and these zeros)
-      S.segHC1[tid] = 0;
-    }
-    __syncthreads();
-
-    // ---------------- phase A2: hash candidates for the positions without a short-offset match ----------------
-    // 32 rounds of 512 positions against a 4096-entry table of earlier positions. This warp covers segment 16 r + warp in
-    // round r; `myrounds` has the rounds in which that segment looks anything up (a quarter of them on bit planes), in the
-    // others the warp only meets the round's barrier. Only the positions that look up are inserted.
-    const uint32_t myrounds = __ballot_sync(0xffffffffu, S.segHM[lane * kWarps + warp] != 0u);
-    int nfound = Ms != 0;
-    for (int r = 0; r < kB / kThreads; ++r) {
-      if ((myrounds >> r) & 1u) {
-        const int seg = r * kWarps + warp;
-        const uint32_t ns = S.segHM[seg];
-        const int i = r * kThreads + tid;
-        bool found = false;
-        int code = 0;
-        if ((ns >> lane) & 1u) {
-          const uint32_t v = load4(S.data, i);
-          const uint32_t h = (v * 2654435761u) >> (32 - kHashLog);
-          // the table is read and written without a barrier in between: an entry may already belong to this round
-          // (any earlier position with the same 4 bytes is a valid source; c < i and the compare make it safe)
-          const uint32_t c = S.htab[h];
-          if (c < (uint32_t)i && load4(S.data, (int)c) == v) {
-            const int maxlen = min((i & ~(kSub - 1)) + kSub, n - kLz4LastLiterals) - i;
-            const uint32_t x = load4(S.data, i + 4) ^ load4(S.data, (int)c + 4);
-            int len = 4 + (x ? ((__ffs(x) - 1) >> 3) : 4);
-            if (len > maxlen) len = maxlen;
-            // 4-byte matches save one byte and cost a sequence on both ends of the codec: dropping them keeps the ratio
-            // within ~1 % on bit planes, improves it on background-removed stacks and matches liblz4 on noisy 8-bit
-            // codes (tools/lz4_model.c), while halving the number of sequences
-            if (len >= 5) {
-              found = true;
-              code = len - 5 < 3 ? len - 5 : 3;   // 0,1,2: exact length 5,6,7; 3: at least 8, extended in phase B
-              S.cand[i] = (uint16_t)c;
-            }
-          }
-          S.htab[h] = (uint16_t)i;
-        }
-        const uint32_t HM = __ballot_sync(0xffffffffu, found);
-        const uint32_t HC0 = __ballot_sync(0xffffffffu, found && (code & 1));
-        const uint32_t HC1 = __ballot_sync(0xffffffffu, found && (code & 2));
-        if (lane == 0) {
-          S.segHM[seg] = HM;
-          S.segHC0[seg] = HC0;
-          S.segHC1[seg] = HC1;
-        }
-        nfound |= HM != 0;
-      }
-      __syncthreads();   // one barrier per round keeps the warps within a round of each other
-    }
-    const int any_found = __syncthreads_or(nfound);
-
-    if (!any_found) {
-      stored = true;
-    } else {
-      // ---------------- phase B: every thread parses its own 32-byte segment greedily ----------------
-      // A match may overshoot into the following segments of the same warp; their entry point moves and
-      // they re-parse until the warp's parse is stable (lane k is final after at most k+1 rounds).
-      const int limit = min((warp + 1) * kSub, n - kLz4LastLiterals);
-      const uint32_t M = Ms | S.segHM[tid];              // hash candidates exist only where no short-offset one does
-      C0 |= S.segHC0[tid];
-      C1 |= S.segHC1[tid];
-      uint32_t Sel = 0;
-      unsigned long long lens = 0;       // lengths of the long matches of this segment, 11 bits each, in order
-      // First guess of where the parse enters this segment: if the previous segment ends inside a run with period d
-      // (its last five bytes continue one), the match that covers them runs on to the end of the ones of E_d here. A
-      // segment in the middle of a long run then has nothing to parse (and nothing to measure: every lane of a run
-      // scanning to its end was 5 % of the kernel), and half of the repair parses of the cascade disappear. A wrong
-      // guess is corrected like any other moved entry point.
-      int entry = 0, exit_abs = seg_lo + 32;
-      if (lane > 0) {
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-          const uint32_t prevE = S.E[d][tid - 1], curE = S.E[d][tid];
-          if ((prevE >> 27) == 31u) entry = max(entry, curE == 0xffffffffu ? 32 : __ffs(~curE) - 1);
-        }
-      }
-      bool need = true;
-      while (true) {                     // cascade rounds
-        int pos = entry, nlong = 0, pj = 0, plen = 0;
-        const bool parsing = need;       // lanes whose entry did not move keep the parse of an earlier round
-        bool done = !need, pend = false;
-        if (need) { Sel = 0; lens = 0; }
-        while (true) {
-          if (!done && !pend) {
-            // thread-serial parse: bit operations only; a long match gets at most 16 more bytes here
-            while (true) {
-              if (pos >= 32) { done = true; break; }
-              const uint32_t mm = M & (0xffffffffu << pos);
-              if (!mm) { done = true; break; }
-              const int j = __ffs(mm) - 1;
-              const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
-              int len = 5 + code;
-              if (code == 3 && ((Ms >> j) & 1u)) {
-                // short-offset match: count the ones that follow in E_d, 32 positions per step
-                const int i = seg_lo + j, maxlen = limit - i;
-                const uint32_t* Ed = S.E[((D0 >> j) & 1u) | (((D1 >> j) & 1u) << 1)];
-                len = 8;
-                while (len < maxlen) {
-                  const int p = i + len, avail = 32 - (p & 31);
-                  const uint32_t z = ~(Ed[p >> 5] >> (p & 31));     // zeros where the match goes on
-                  const int ones = z ? __ffs(z) - 1 : 32;
-                  if (ones < avail) { len += ones; break; }
-                  len += avail;
-                }
-                if (len > maxlen) len = maxlen;
-                lens |= (unsigned long long)len << (11 * nlong);
-                nlong++;
-              } else if (code == 3) {
-                const int i = seg_lo + j, c = (int)S.cand[i], maxlen = limit - i;
-                len = 8;
-                bool open = true;
-#pragma unroll 1
-                for (int it = 0; it < 4; ++it) {
-                  if (len >= maxlen) { open = false; break; }
-                  const uint32_t x = load4(S.data, i + len) ^ load4(S.data, c + len);
-                  if (x) { len += (__ffs(x) - 1) >> 3; open = false; break; }
-                  len += 4;
-                }
-                if (len >= maxlen) { len = maxlen; open = false; }
-                if (open) { pend = true; pj = j; plen = len; break; }   // still matching: the warp finishes it
-                lens |= (unsigned long long)len << (11 * nlong);
-                nlong++;
-              }
-              Sel |= 1u << j;
-              pos = j + len;
-            }
-          }
-          uint32_t pm = __ballot_sync(0xffffffffu, pend);
-          if (!pm) break;                // no lane is waiting => every lane is done
-          while (pm) {
-            const int l = __ffs(pm) - 1;
-            pm &= pm - 1;
-            const int i = __shfl_sync(0xffffffffu, seg_lo + pj, l);
-            const int c = (int)S.cand[i], maxlen = limit - i;
-            int len = __shfl_sync(0xffffffffu, plen, l);
-            while (len < maxlen) {       // 128 bytes per step
-              const int k = len + lane * 4;
-              const uint32_t x = load4(S.data, i + k) ^ load4(S.data, c + k);
-              const uint32_t bm = __ballot_sync(0xffffffffu, x != 0);
-              if (bm) {
-                const int f = __ffs(bm) - 1;
-                const uint32_t d = __shfl_sync(0xffffffffu, x, f);
-                len += f * 4 + ((__ffs(d) - 1) >> 3);
-                break;
-              }
-              len += 128;
-            }
-            if (len > maxlen) len = maxlen;
-            if (lane == l) {
-              lens |= (unsigned long long)len << (11 * nlong);
-              nlong++;
-              Sel |= 1u << pj;
-              pos = pj + len;
-              pend = false;
-            }
-            // later lanes whose pending match starts inside [i, i+len) parsed a stale speculation: drop them all at
-            // once (their entry point moves in the cascade step, so they are parsed again)
-            const bool stale = pend && lane > l && seg_lo + pj < i + len;
-            if (stale) { pend = false; done = true; pos = 0; Sel = 0; lens = 0; }
-            pm &= ~__ballot_sync(0xffffffffu, stale);
-          }
-        }
-        if (parsing) exit_abs = seg_lo + (pos > 32 ? pos : 32);
-        int incl = exit_abs;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl = max(incl, t);
-        }
-        int prev = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) prev = seg_lo;
-        const int ne = min(max(prev - seg_lo, 0), 32);
-        need = ne != entry;
-        entry = ne;
-        if (!__any_sync(0xffffffffu, need)) break;
-      }
-
-      // ---------------- phase C: sizes, literal carries, output offsets ----------------
-      const int seg_end = max(0, min(32, n - seg_lo));   // valid positions of this segment
-      if (entry > seg_end) entry = seg_end;
-      int nm = 0, rest = 0, F = 0, p = entry;
-      {
-        uint32_t m = Sel;
-        unsigned long long q = lens;
-        while (m) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
-          int len = 5 + code;
-          if (code == 3) { len = (int)(q & 0x7FF); q >>= 11; }
-          const int lit = j - p;
-          if (nm == 0) { F = lit; rest += 3 + ext_bytes(len - 4); }
-          else rest += 3 + ext_bytes(lit) + lit + ext_bytes(len - 4);
-          nm++;
-          p = j + len;
-        }
-      }
-      const int T = p < seg_end ? seg_end - p : 0;   // trailing literals, owned by a later sequence
-      const int has = nm > 0;
-      // carry scan: f_l(x) = has ? T : x + T ; combine(a,b) = (b.has ? b.T : a.T + b.T, a.has | b.has)
-      int sT = T, sH = has;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int tT = __shfl_up_sync(0xffffffffu, sT, d), tH = __shfl_up_sync(0xffffffffu, sH, d);
-        if (lane >= d) { sT = sH ? sT : tT + sT; sH |= tH; }
-      }
-      int eT = __shfl_up_sync(0xffffffffu, sT, 1), eH = __shfl_up_sync(0xffffffffu, sH, 1);   // exclusive
-      if (lane == 0) { eT = 0; eH = 0; }
-      // next segment (after this one) that owns a match
-      int nx = has ? tid : kInf;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_down_sync(0xffffffffu, nx, d);
-        if (lane + d < 32) nx = min(nx, t);
-      }
-      int nxt = __shfl_down_sync(0xffffffffu, nx, 1);
-      if (lane == 31) nxt = kInf;
-      if (lane == 31) { S.w_T[warp] = sT; S.w_has[warp] = sH; }
-      if (lane == 0) S.w_first[warp] = nx;
-      __syncthreads();
-      if (tid == 0) {
-        int x = 0;
-        for (int w = 0; w < kWarps; ++w) { S.w_carry_in[w] = x; x = S.w_has[w] ? S.w_T[w] : x + S.w_T[w]; }
-        S.final_lit = x;
-        int nn = kInf;
-        for (int w = kWarps - 1; w >= 0; --w) { S.w_next[w] = nn; nn = min(nn, S.w_first[w]); }
-      }
-      __syncthreads();
-      const int C = eH ? eT : S.w_carry_in[warp] + eT;   // literals carried into this segment's first sequence
-      if (nxt == kInf) nxt = S.w_next[warp];
-      const int size = has ? ext_bytes(C + F) + C + F + rest : 0;
-      int incl = size;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-      }
-      if (lane == 31) S.w_size[warp] = incl;
-      // offsets of the selected matches, fetched before `out` starts to overwrite `cand`
-      uint32_t offs[4] = {0, 0, 0, 0};
-      {
-        uint32_t m = Sel;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (m) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            const int i = seg_lo + j;
-            const uint32_t off = ((Ms >> j) & 1u) ? 1u + ((D0 >> j) & 1u) + 2u * ((D1 >> j) & 1u) : (uint32_t)(i - (int)S.cand[i]);
-            offs[k >> 1] |= off << (16 * (k & 1));
-          }
-        }
-      }
-      __syncthreads();
-      if (tid == 0) {
-        int off = 0;
-        for (int w = 0; w < kWarps; ++w) { S.w_off[w] = off; off += S.w_size[w]; }
-        S.final_off = off;
-        S.total = off + 1 + ext_bytes(S.final_lit) + S.final_lit;
-      }
-      __syncthreads();
-      csize = S.total;
-      if (csize >= n) {
-        stored = true;
-      } else {
-        // ---------------- phase D: emission ----------------
-        const int final_litbase = S.final_off + 1 + ext_bytes(S.final_lit) - (n - S.final_lit);
-        if (has) {
-          int o = S.w_off[warp] + incl - size;
-          uint32_t m = Sel;
-          unsigned long long q = lens;
-          int pp = entry;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if (m) {
-              const int j = __ffs(m) - 1;
-              m &= m - 1;
-              const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
-              int len = 5 + code;
-              if (code == 3) { len = (int)(q & 0x7FF); q >>= 11; }
-              const int own = j - pp;                    // literals of this sequence inside this segment
-              const int lit = k == 0 ? C + own : own;
-              const int el = ext_bytes(lit);
-              const int ml = len - 4;
-              out8[o] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (ml < 15 ? ml : 15));
-              if (lit >= 15) put_ext(out8 + o + 1, lit);
-              int d = o + 1 + el + (lit - own);          // where this segment's own literals go
-              if (k == 0) S.seg_litbase[tid] = o + 1 + el - (seg_lo + entry - C);
-              for (int t = 0; t < own; ++t) out8[d + t] = data8[seg_lo + pp + t];
-              d += own;
-              const uint32_t off = (offs[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-              out8[d] = (uint8_t)(off & 0xff);
-              out8[d + 1] = (uint8_t)(off >> 8);
-              if (ml >= 15) put_ext(out8 + d + 2, ml);
-              o = d + 2 + ext_bytes(ml);
-              pp = j + len;
-            }
-          }
-        }
-        __syncthreads();
-        // trailing literals belong to the next sequence (or to the block's final literal run)
-        if (T > 0) {
-          const int lb = nxt == kInf ? final_litbase : S.seg_litbase[nxt];
-          for (int t = 0; t < T; ++t) out8[lb + seg_lo + p + t] = data8[seg_lo + p + t];
-        }
-        if (tid == 0) {
-          const int L = S.final_lit;
-          uint8_t* fp = out8 + S.final_off;
-          fp[0] = (uint8_t)((L < 15 ? L : 15) << 4);
-          if (L >= 15) put_ext(fp + 1, L);
-        }
-      }
-    }
+    csize = encode_general(S, n, stored);
     if (stored) { csize = n; kind = 2; }
   }
   __syncthreads();
@@ -759,31 +812,69 @@ size_t k_lz4_encode_workspace_bytes(uint64_t raw_bytes) {
 }
 
 // workspace layout: [0,8) payload bytes (u64) | [16,28) block-kind counters | [256, 256+8*nblocks) offsets | staging
-int k_lz4_encode(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, cudaStream_t st) {
+namespace {
+struct EncWs {
+  uint32_t nblocks;
+  unsigned long long *payload, *offsets, *tile_sums;
+  uint8_t* staging;
+  uint32_t* stats;
+};
+int enc_ws(uint64_t raw_bytes, void* workspace, EncWs& W) {
   const uint64_t nb64 = lz4_nblocks(raw_bytes);
   if (nb64 > 0xFFFFFFF0ull) return -2;
-  const uint32_t nblocks = (uint32_t)nb64;
+  W.nblocks = (uint32_t)nb64;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  SQYB_CUDA_OK(cudaMemsetAsync(ws, 0, 64, st));
-  unsigned long long* payload = reinterpret_cast<unsigned long long*>(ws);
-  unsigned long long* offsets = reinterpret_cast<unsigned long long*>(ws + 256);
-  uint8_t* staging = ws + ((256 + 8ull * nblocks + 8ull * (nblocks / kEncTile + 2) + 255) & ~255ull);
-  lz4_write_prefix_kernel<<<1, 32, 0, st>>>(dst, raw_bytes, nblocks, payload);
+  W.payload = reinterpret_cast<unsigned long long*>(ws);
+  W.stats = reinterpret_cast<uint32_t*>(ws + 16);
+  W.offsets = reinterpret_cast<unsigned long long*>(ws + 256);
+  W.tile_sums = W.offsets + W.nblocks;
+  W.staging = ws + ((256 + 8ull * W.nblocks + 8ull * (W.nblocks / kEncTile + 2) + 255) & ~255ull);
+  return 0;
+}
+}  // namespace
+
+int k_lz4_encode_begin(uint64_t raw_bytes, uint8_t* dst, void* workspace, cudaStream_t st) {
+  EncWs W;
+  if (int e = enc_ws(raw_bytes, workspace, W)) return e;
+  SQYB_CUDA_OK(cudaMemsetAsync(workspace, 0, 64, st));
+  lz4_write_prefix_kernel<<<1, 32, 0, st>>>(dst, raw_bytes, W.nblocks, W.payload);
   SQYB_COUNT_LAUNCH(1);
-  if (nblocks) {
-    SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
-    lz4_encode_kernel<<<nblocks, kThreads, sizeof(EncSmem), st>>>(src, raw_bytes, dst, nblocks, staging,
-                                                                    reinterpret_cast<uint32_t*>(ws + 16));
-    const uint32_t ntiles = (nblocks + kEncTile - 1) / kEncTile;
-    const uint32_t tile_grid = ntiles < (uint32_t)kNumSMs * 8 ? ntiles : (uint32_t)kNumSMs * 8;
-    unsigned long long* tile_sums = offsets + nblocks;
-    lz4_tile_sums_kernel<<<tile_grid, 256, 0, st>>>(dst, nblocks, tile_sums);
-    lz4_block_offsets_kernel<<<tile_grid, 256, 0, st>>>(dst, nblocks, tile_sums, offsets, payload);
-    const uint32_t scatter_blocks = (nblocks + 7) / 8 < (uint32_t)kNumSMs * 8 ? (nblocks + 7) / 8 : (uint32_t)kNumSMs * 8;
-    lz4_scatter_kernel<<<scatter_blocks, 256, 0, st>>>(src, raw_bytes, staging, dst, nblocks, offsets);
-    SQYB_COUNT_LAUNCH(4);
-  }
   return (int)cudaGetLastError();
+}
+
+int k_lz4_encode_blocks(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, uint32_t first, uint32_t count,
+                        uint32_t nsets, uint32_t set_stride, cudaStream_t st) {
+  EncWs W;
+  if (int e = enc_ws(raw_bytes, workspace, W)) return e;
+  if (!count || !nsets) return 0;
+  if (nsets > 65535u || (uint64_t)first + (uint64_t)(nsets - 1) * set_stride + count > W.nblocks) return -2;
+  SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
+  lz4_encode_kernel<<<dim3(count, nsets), kThreads, sizeof(EncSmem), st>>>(src, raw_bytes, dst, W.nblocks, W.staging, W.stats, first,
+                                                                            set_stride);
+  SQYB_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+int k_lz4_encode_end(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, cudaStream_t st) {
+  EncWs W;
+  if (int e = enc_ws(raw_bytes, workspace, W)) return e;
+  if (!W.nblocks) return 0;
+  const uint32_t ntiles = (W.nblocks + kEncTile - 1) / kEncTile;
+  const uint32_t tile_grid = ntiles < (uint32_t)kNumSMs * 8 ? ntiles : (uint32_t)kNumSMs * 8;
+  lz4_tile_sums_kernel<<<tile_grid, 256, 0, st>>>(dst, W.nblocks, W.tile_sums);
+  lz4_block_offsets_kernel<<<tile_grid, 256, 0, st>>>(dst, W.nblocks, W.tile_sums, W.offsets, W.payload);
+  const uint32_t scatter_blocks = (W.nblocks + 7) / 8 < (uint32_t)kNumSMs * 8 ? (W.nblocks + 7) / 8 : (uint32_t)kNumSMs * 8;
+  lz4_scatter_kernel<<<scatter_blocks, 256, 0, st>>>(src, raw_bytes, W.staging, dst, W.nblocks, W.offsets);
+  SQYB_COUNT_LAUNCH(3);
+  return (int)cudaGetLastError();
+}
+
+int k_lz4_encode(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, cudaStream_t st) {
+  EncWs W;
+  if (int e = enc_ws(raw_bytes, workspace, W)) return e;
+  if (int e = k_lz4_encode_begin(raw_bytes, dst, workspace, st)) return e;
+  if (int e = k_lz4_encode_blocks(src, raw_bytes, dst, workspace, 0, W.nblocks, 1, 0, st)) return e;
+  return k_lz4_encode_end(src, raw_bytes, dst, workspace, st);
 }
 
 }  // namespace sqyb

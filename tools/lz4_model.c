@@ -12,7 +12,9 @@ static int ext_bytes(int v) { return v < 15 ? 0 : 1 + (v - 15) / 255; }
 static uint32_t ld4(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 
 /* candidates: cand[i] = position or -1. round-based table (positions of earlier rounds) + short offsets */
-static int g_cut = 1 << 30;
+static int g_cut = 1 << 30, g_win = 3, g_minlen = 8, g_early = 0, g_div = 16;
+static int g_last_cnt = 0, g_last_short = 0;
+static long g_early_stored = 0, g_early_lost = 0;
 static long g_lookups = 0, g_lookup_segs = 0;
 static int seg_has_short(const uint8_t* d, int n, int seg) {
   static const int ds[4] = {1, 2, 4, 3};
@@ -30,6 +32,21 @@ static void find_candidates(const uint8_t* d, int n, int round, int hashlog, int
   int* tab = malloc(sizeof(int) * tsize);
   static int noshort[1 << 20];
   for (int i = 0; i < tsize; ++i) tab[i] = -1;
+  /* 4096: g_win > 0: a position does not look up (nor insert) when a short-offset candidate of >= g_minlen bytes starts
+   * within the next g_win positions: the hash match would save at most g_win literals and cost a 3-byte sequence */
+  static unsigned char slen[(1 << 20) + 16];
+  if (mode & 4096) {
+    static const int ds[4] = {1, 2, 4, 3};
+    for (int i = 0; i < n + 8; ++i) slen[i] = 0;
+    for (int i = 0; i + 12 <= n; ++i)
+      for (int q = 0; q < 4; ++q) {
+        int dd = ds[q], l = 0;
+        if (i < dd) continue;
+        int cut_hi = ((i / g_cut) + 1) * g_cut, lim = n - 5 < cut_hi ? n - 5 : cut_hi;
+        while (l < 64 && i + l < lim && d[i + l] == d[i + l - dd]) l++;
+        if (l >= 5) { slen[i] = l; break; }
+      }
+  }
   for (int r0 = 0; r0 < n; r0 += round) {
     int r1 = r0 + round < n ? r0 + round : n;
     for (int i = r0; i < r1; ++i) {
@@ -69,7 +86,9 @@ static void find_candidates(const uint8_t* d, int n, int round, int hashlog, int
           while (l < 5 && i + l < n - 5 && d[i + l] == d[i + l - dd]) l++;
           if (l >= 5) found = i - dd;
         }
-        noshort[i] = found < 0 && !((mode & 512) && i > 0 && d[i] == d[i - 1]) && !((mode & 1024) && (i & 3) && !seg_has_short(d, n, i / 32)) && !((mode & 2048) && ((i / 32) & 3) && !seg_has_short(d, n, i / 32)); /* 2048: run-free segments look up only in every 4th segment */ /* 512: look up / insert only where a run breaks */
+        int sup = 0;
+        if (mode & 4096) for (int k = 1; k <= g_win; ++k) if (slen[i + k] >= g_minlen) sup = 1;
+        noshort[i] = found < 0 && !sup && !((mode & 512) && i > 0 && d[i] == d[i - 1]) && !((mode & 1024) && (i & 3) && !seg_has_short(d, n, i / 32)) && !((mode & 2048) && ((i / 32) & 3) && !seg_has_short(d, n, i / 32)); /* 2048: run-free segments look up only in every 4th segment */ /* 512: look up / insert only where a run breaks */
         if (found < 0 && noshort[i] && c >= 0 && ld4(d + c) == v && !(mode & 128) && !((mode & 256) && c / g_cut != i / g_cut)) found = c; /* 256: same sub-block only */ /* 128: short offsets only */
       }
       cand[i] = found;
@@ -93,6 +112,21 @@ static long encode_block_size(const uint8_t* d, int n, int round, int cut, int h
   find_candidates(d, n, round, hashlog, mode, cand);
   long out = 0;
   int anchor = 0, pos = 0;
+  int early = 0;
+  if (g_early && n > g_early) { /* early-store policy: few candidates in the first g_early bytes => the block is stored unparsed */
+    int cnt = 0;
+    for (int i = 0; i < g_early; ++i) { /* the GPU's candidates agree in at least 5 bytes */
+      int c = cand[i];
+      if (c >= 0 && i + 5 <= n - 5 && d[i + 4] == d[c + 4] && (i + 5 <= ((i / cut) + 1) * cut)) cnt++;
+    }
+    g_last_short = 0;
+    for (int i = 0; i < n; ++i) {
+      int c = cand[i];
+      if (c >= 0 && i - c <= 4 && i + 5 <= n - 5 && d[i + 4] == d[c + 4] && (i + 5 <= ((i / cut) + 1) * cut)) g_last_short++;
+    }
+    g_last_cnt = cnt;
+    early = cnt < g_early / g_div;
+  }
   long nseq = 0;
   while (pos < n) {
     int c = cand[pos];
@@ -116,6 +150,8 @@ static long encode_block_size(const uint8_t* d, int n, int round, int cut, int h
   int lit = n - anchor;
   out += 1 + ext_bytes(lit) + lit;
   free(cand);
+  if (getenv("MODEL_DUMP")) fprintf(stdout, "BLK %d %d %ld\n", g_last_cnt, g_last_short, out >= n ? (long)n : out);
+  if (early) { g_early_stored++; if (out < n) g_early_lost += n - out; return n; }
   if (nseq_out) *nseq_out += nseq;
   return out >= n ? n : out;
 }
@@ -130,6 +166,10 @@ int main(int argc, char** argv) {
   if (fread(buf, 1, total, f) != (size_t)total) return 2;
   memset(buf + total, 0, 64);
   int block = atoi(argv[2]), round = atoi(argv[3]), cut = atoi(argv[4]), hashlog = atoi(argv[5]), mode = atoi(argv[6]);
+  if (argc > 7) g_win = atoi(argv[7]);
+  if (argc > 8) g_minlen = atoi(argv[8]);
+  if (argc > 9) g_early = atoi(argv[9]);
+  if (argc > 10) g_div = atoi(argv[10]);
   long out = 0, nseq = 0;
   for (long o = 0; o < total; o += block) {
     int n = o + block <= total ? block : (int)(total - o);
@@ -140,6 +180,7 @@ int main(int argc, char** argv) {
   }
   printf("block=%d round=%d cut=%d hashlog=%d mode=%d: %ld -> %ld ratio %.3f seqs %ld (%.1f B/seq)\n", block, round, cut, hashlog, mode,
          total, out, (double)total / out, nseq, nseq ? (double)total / nseq : 0.0);
+  if (g_early) fprintf(stderr, "early-stored blocks %ld, bytes lost %ld\n", g_early_stored, g_early_lost);
   fprintf(stderr, "lookups %ld (%.1f%% of bytes), segments with lookups %ld (%.1f%% of segments)\n", g_lookups, 100.0 * g_lookups / total, g_lookup_segs, 100.0 * g_lookup_segs / (total / 32.0));
   return 0;
 }
