@@ -232,6 +232,40 @@ def test_lz4_random_blocks_are_stored(sq, cuda):
     assert payload.numel() == sq.lz4_bound(a.size)
 
 
+def test_lz4_noise_blocks_are_stored_early(sq, cuda, port, ref):
+    """blocks with fewer than one match candidate per 32 sampled bytes (camera-noise bit planes, 8-bit quantiser codes of a
+    noisy stack) are stored after the hash rounds of their first 4 KiB (lz4_encode.cu: kEarlyRounds / kEarlyMin). The
+    stated price: such blocks shrink by < 3 % under the reference's liblz4, so the payload stays within 3 % of the
+    reference's; compressible blocks never take that exit."""
+    vol = numpy_volume((16, 512, 512), "scmos", index=8)
+    enc, dec = port.quantiser_luts(port.histogram(vol.reshape(-1)))
+    codes = port.lut_apply(vol.reshape(-1), enc)                     # noisy 8-bit codes: liblz4 gets ~1.02
+    payload = sq.lz4_encode_device(dev(cuda, codes))
+    st = sq.last_lz4_stats()
+    assert st["stored_blocks"] >= 0.9 * (codes.size // 16384), st
+    theirs = ref.lz4_encode(codes, nthreads=8).size    # (lz4_scheme<char>, the quantiser's tail)
+    assert payload.numel() <= 1.03 * theirs, (payload.numel(), theirs)
+    out = cuda.zeros(codes.size, dtype=cuda.uint8, device="cuda")
+    assert sq.lz4_decode_device(payload, out) == codes.size
+    assert np.array_equal(out.cpu().numpy(), codes)
+    rc, back = ref.lz4_decode_bytes(payload.cpu().numpy(), codes.size)
+    assert rc == 0 and np.array_equal(back, codes)
+    # bit planes of the same stack: the noise planes (low bits) are stored, everything else is parsed; a block that is noise
+    # in its first 4 KiB only but full of runs elsewhere is parsed too (short-offset candidates count over the whole block)
+    planes = port.bitswap_encode(1, vol.reshape(-1)).view(np.uint8)
+    sq.lz4_encode_device(dev(cuda, planes))
+    st = sq.last_lz4_stats()
+    nb = planes.size // 16384
+    assert 0.15 * nb <= st["stored_blocks"] <= 0.35 * nb and st["constant_blocks"] >= 0.4 * nb, st
+    rng = np.random.default_rng(3)
+    mixed = np.concatenate([rng.integers(0, 256, size=4096, dtype=np.uint8), np.zeros(12288, np.uint8)] * 6)
+    p2 = sq.lz4_encode_device(dev(cuda, mixed))
+    assert sq.last_lz4_stats()["stored_blocks"] == 0 and p2.numel() < 0.3 * mixed.size
+    out2 = cuda.zeros(mixed.size, dtype=cuda.uint8, device="cuda")
+    sq.lz4_decode_device(p2, out2)
+    assert np.array_equal(out2.cpu().numpy(), mixed)
+
+
 @pytest.mark.parametrize("key,src", [("lz4_serial", "lz4_vol"), ("lz4_parallel", "lz4_vol"), ("lz4_linked", "lz4_linked_in")])
 def test_lz4_decodes_reference_payloads(sq, cuda, port, golden, key, src):
     """reference-produced frames (liblz4 1.9.4 through lz4_scheme::encode): block-linked single frame (CLI default,
