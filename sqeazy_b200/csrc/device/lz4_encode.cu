@@ -120,12 +120,7 @@ __device__ __forceinline__ void store_bytes(uint8_t* __restrict__ g, const uint3
 // The general path of a block (phases A0..D on the bytes in S.data), kept out of line: the closed-form path of all-equal
 // blocks — 56 % of a background-removed stack, bound by bytes in flight — then keeps the short prologue and the register
 // allocation of a kernel that does nothing else. Returns the encoded size; `stored` when the block does not shrink.
-#ifndef SQYB_INLINE_GENERAL
-__device__ __noinline__
-#else
-__device__ __forceinline__
-#endif
-int encode_general(EncSmem& S, const int n, bool& stored_out) {
+__device__ __noinline__ int encode_general(EncSmem& S, const int n, bool& stored_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint8_t* data8 = reinterpret_cast<uint8_t*>(S.data);
   uint8_t* out8 = reinterpret_cast<uint8_t*>(S.out);
@@ -192,16 +187,10 @@ int encode_general(EncSmem& S, const int n, bool& stored_out) {
     S.segHC0[tid] = 0;                                 // (a segment nobody looks up in keeps HM = wants = 0 and these zeros)
     S.segHC1[tid] = 0;
   }
-#ifdef SQYB_NO_EARLY
-  int ncand = 0;
-  __syncthreads();
-  const int rich = 1;
-#else
   int ncand = __reduce_add_sync(0xffffffffu, __popc(Ms));   // this warp's candidates so far (warp-uniform)
   // (the barrier between A1 and A2 carries the one bit the early-store test needs first: a warp that is already rich in
   //  short-offset candidates — every compressible bit-plane block — settles it for the CTA at no cost)
   const int rich = __syncthreads_or(ncand >= kEarlyMin);
-#endif
 
   // ---------------- phase A2: hash candidates for the positions without a short-offset match ----------------
   // 32 rounds of 512 positions against a 4096-entry table of earlier positions. This warp covers segment 16 r + warp in
@@ -253,7 +242,7 @@ int encode_general(EncSmem& S, const int n, bool& stored_out) {
         S.segHC1[seg] = HC1;
       }
       nfound |= HM != 0;
-      ncand += __popc(HM);
+      if (!rich) ncand += __popc(HM);
     }
     __syncthreads();   // one barrier per round keeps the warps within a round of each other
   };
