@@ -49,6 +49,12 @@ int sqyx_encode_batch_device_UI16(int n, const char* pipeline, const void* const
 int sqyx_bitswap_encode_UI16(int w, const void* d_src, void* d_dst, long n, int threshold, void* stream);
 int sqyx_bitswap_decode_UI16(int w, const void* d_src, void* d_dst, long n, void* stream);
 
+/* bitshuffle head filter: the blocked bit transpose of the bitshuffle library that
+ * encoders/bitshuffle_scheme_impl.hpp:91-160 calls (bshuf_bitshuffle / bshuf_bitunshuffle, element size 2).
+ * block_size in elements, 0 = the library's default (4096 for uint16); must be a multiple of 8. */
+int sqyx_bitshuffle_encode_UI16(const void* d_src, void* d_dst, long n, long block_size, void* stream);
+int sqyx_bitshuffle_decode_UI16(const void* d_src, void* d_dst, long n, long block_size, void* stream);
+
 /* out = in > t ? in - t : 0. reference: encoders/remove_background_scheme_impl.hpp:73-95 */
 int sqyx_remove_background_UI16(const void* d_src, void* d_dst, long n, int threshold, void* stream);
 

@@ -66,6 +66,15 @@ class Port:
         assert self.lib.orc_bitswap_decode(c_int(w), _p(a), _p(out), c_uint64(a.size)) == 0
         return out
 
+    def bitshuffle(self, a: np.ndarray, block_size: int = 0, decode: bool = False) -> np.ndarray:
+        """bshuf_bitshuffle / bshuf_bitunshuffle of the third-party bitshuffle library, restated (parity unpinned, see the C file)"""
+        a = np.ascontiguousarray(a).ravel()
+        out = np.empty_like(a)
+        rc = self.lib.orc_bitshuffle(c_int(1 if decode else 0), _p(a), _p(out), c_uint64(a.size), c_uint32(a.itemsize), c_uint32(block_size))
+        if rc != 0:
+            raise ValueError(f"bitshuffle: error {rc}")
+        return out
+
     def remove_background(self, a: np.ndarray, threshold: int) -> np.ndarray:
         a = np.ascontiguousarray(a, dtype=np.uint16)
         out = np.empty_like(a)
@@ -388,7 +397,7 @@ def minors(args: str):
     return out
 
 
-HEAD_U16 = {"bitswap1", "remove_background", "rmestbkrd"}          # sqeazy_pipelines.hpp:31-45 (hot-path subset)
+HEAD_U16 = {"bitswap1", "bitshuffle", "remove_background", "rmestbkrd"}   # sqeazy_pipelines.hpp:31-45 (hot-path subset)
 SINK_U16 = {"pass_through", "quantiser", "lz4"}                    # :47-56
 TAIL_CHAR = {"lz4"}                                                # :58-74 (hot-path subset)
 

@@ -453,3 +453,81 @@ uint64_t orc_base64_encode(const uint8_t* p, uint64_t n, char* out) {
   }
   return o;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * bitshuffle — encoders/bitshuffle_scheme_impl.hpp:91-160 calls bshuf_bitshuffle_nthreads / bshuf_bitunshuffle of the
+ * THIRD-PARTY bitshuffle library (github.com/kiyo-masui/bitshuffle; the reference downloads its sources at cmake time,
+ * none of them is under /root/reference and no version is pinned). PARITY UNPINNED for this stage: the reference's own
+ * tests hold round trips only (tests/test_bitshuffle_scheme_impl.cpp:21-190), and the library cannot be compiled here.
+ * What follows restates the library's published scalar algorithm (src/bitshuffle_core.c) step by step:
+ *   bshuf_blocked_wrap_fun   : whole blocks of `block_size` elements (0 -> bshuf_default_block_size: 8192 bytes / element
+ *                              size, rounded down to a multiple of BSHUF_BLOCKED_MULT = 8, at least 128), one block of the
+ *                              rest rounded down to a multiple of 8, the last size % 8 elements copied
+ *   bshuf_trans_bit_elem     : per block  A bshuf_trans_byte_elem_scal (byte j of every element -> byte row j)
+ *                                         B bshuf_trans_bit_byte_scal  (8 bytes -> one byte in each of 8 bit rows, TRANS_BIT_8X8,
+ *                                                                       byte 8i+k of the input at bit k)
+ *                                         C bshuf_trans_bitrow_eight   (8 x elem_size matrix of rows -> elem_size x 8)
+ * tests/test_oracle.py checks it against an independent numpy formulation (np.unpackbits, bitorder="little").
+ * ------------------------------------------------------------------------------------------ */
+static uint32_t orc_bshuf_default_block_size(uint32_t elem_size) {
+  uint32_t b = 8192u / elem_size;
+  b = (b / 8u) * 8u;
+  return b < 128u ? 128u : b;
+}
+
+static void orc_bshuf_trans_bit_elem(const uint8_t* in, uint8_t* out, uint8_t* tmp, size_t size, size_t elem_size) {
+  const size_t nbyte = size * elem_size, nrow = nbyte / 8;
+  /* A: out[j * size + i] = in[i * elem_size + j] */
+  for (size_t i = 0; i < size; ++i)
+    for (size_t j = 0; j < elem_size; ++j) out[j * size + i] = in[i * elem_size + j];
+  /* B: tmp[k * nrow + i] bit b = bit k of out[8 i + b] */
+  for (size_t i = 0; i < nrow; ++i)
+    for (size_t k = 0; k < 8; ++k) {
+      uint8_t v = 0;
+      for (size_t b = 0; b < 8; ++b) v |= (uint8_t)(((out[8 * i + b] >> k) & 1u) << b);
+      tmp[k * nrow + i] = v;
+    }
+  /* C: bshuf_trans_elem(tmp, out, 8, elem_size, size / 8): element (k, j) of an 8 x elem_size matrix of (size/8)-byte
+   * items goes to (j, k) */
+  const size_t item = size / 8;
+  for (size_t k = 0; k < 8; ++k)
+    for (size_t j = 0; j < elem_size; ++j) memcpy(out + (j * 8 + k) * item, tmp + (k * elem_size + j) * item, item);
+}
+
+static void orc_bshuf_untrans_bit_elem(const uint8_t* in, uint8_t* out, uint8_t* tmp, size_t size, size_t elem_size) {
+  const size_t nbyte = size * elem_size, nrow = nbyte / 8, item = size / 8;
+  for (size_t k = 0; k < 8; ++k)
+    for (size_t j = 0; j < elem_size; ++j) memcpy(tmp + (k * elem_size + j) * item, in + (j * 8 + k) * item, item);
+  uint8_t* mid = (uint8_t*)malloc(nbyte ? nbyte : 1);
+  memset(mid, 0, nbyte);
+  for (size_t i = 0; i < nrow; ++i)
+    for (size_t k = 0; k < 8; ++k) {
+      const uint8_t v = tmp[k * nrow + i];
+      for (size_t b = 0; b < 8; ++b) mid[8 * i + b] |= (uint8_t)(((v >> b) & 1u) << k);
+    }
+  for (size_t i = 0; i < size; ++i)
+    for (size_t j = 0; j < elem_size; ++j) out[i * elem_size + j] = mid[j * size + i];
+  free(mid);
+}
+
+/* returns 0, or -81 (the library's error for a block size that is no multiple of 8) */
+int orc_bitshuffle(int decode, const uint8_t* in, uint8_t* out, uint64_t size, uint32_t elem_size, uint32_t block_size) {
+  if (block_size == 0) block_size = orc_bshuf_default_block_size(elem_size);
+  if (block_size % 8u) return -81;
+  uint8_t* tmp = (uint8_t*)malloc((size_t)block_size * elem_size + 8);
+  uint64_t pos = 0;
+  for (uint64_t b = 0; b < size / block_size; ++b, pos += block_size) {
+    if (decode) orc_bshuf_untrans_bit_elem(in + pos * elem_size, out + pos * elem_size, tmp, block_size, elem_size);
+    else orc_bshuf_trans_bit_elem(in + pos * elem_size, out + pos * elem_size, tmp, block_size, elem_size);
+  }
+  uint64_t last = size % block_size;
+  last -= last % 8u;
+  if (last) {
+    if (decode) orc_bshuf_untrans_bit_elem(in + pos * elem_size, out + pos * elem_size, tmp, last, elem_size);
+    else orc_bshuf_trans_bit_elem(in + pos * elem_size, out + pos * elem_size, tmp, last, elem_size);
+    pos += last;
+  }
+  memcpy(out + pos * elem_size, in + pos * elem_size, (size_t)((size - pos) * elem_size));
+  free(tmp);
+  return 0;
+}

@@ -241,6 +241,12 @@ int encode_device_impl(Arena& A, const Pipeline& pl_in, const void* d_src_any, c
       } else {
         CKK(k_remove_background(cur, out, N, t, st));
       }
+    } else if (s.kind == StageKind::Bitshuffle) {
+      if (next_buf(&out)) return 1;
+      if (k_bitshuffle16_encode(cur, out, N, s.block_size, st)) {
+        std::fprintf(stderr, "[sqeazy_b200] bitshuffle failed (block_size=%u must be a multiple of 8)\n", s.block_size);
+        return 1;
+      }
     } else {  // Bitswap
       if (next_buf(&out)) return 1;
       if (u8) CKK(k_bitswap8_encode(s.w, b8(cur), m8(out), N, 0, st));
@@ -412,9 +418,11 @@ int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const ui
   if (N == 0) return 0;
 
   // data-moving head stages in decode order (reverse); the background filters decode as identity
-  std::vector<int> swaps;
-  for (size_t i = pl.head.size(); i-- > 0;)
+  std::vector<int> swaps;                 // bitswap: bits per plane; bitshuffle: -1 - block_size
+  for (size_t i = pl.head.size(); i-- > 0;) {
     if (pl.head[i].kind == StageKind::Bitswap) swaps.push_back(pl.head[i].w);
+    if (pl.head[i].kind == StageKind::Bitshuffle) swaps.push_back(-1 - (int)pl.head[i].block_size);
+  }
 
   uint16_t* bufs[2] = {nullptr, nullptr};
   auto scratch = [&](int which, uint16_t** out) -> int {
@@ -494,6 +502,11 @@ int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const ui
     else {
       // pick the scratch buffer that does not hold `cur`
       if (scratch(cur == bufs[0] ? 1 : 0, &out)) return 1;
+    }
+    if (swaps[k] < 0) {
+      if (u8 || k_bitshuffle16_decode(cur, out, N, (uint32_t)(-1 - swaps[k]), st)) return 100 + 1;
+      cur = out;
+      continue;
     }
     if (remaining == 0 && host && !u8 && raw_bytes >= kStreamMinBytes && N % 128 == 0 && !g_timing.load() &&
         ((((uintptr_t)cur) | ((uintptr_t)out)) & 31) == 0) {
@@ -784,6 +797,19 @@ int sqyx_remove_background_UI8(const void* d_src, void* d_dst, long n, int thres
   if (n < 0) return 1;
   return k_remove_background8(static_cast<const uint8_t*>(d_src), static_cast<uint8_t*>(d_dst), (uint64_t)n, threshold,
                               static_cast<cudaStream_t>(stream)) ? 1 : 0;
+}
+
+int sqyx_bitshuffle_encode_UI16(const void* d_src, void* d_dst, long n, long block_size, void* stream) {
+  if (n < 0 || block_size < 0 || block_size > (1l << 30)) return 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (k_bitshuffle16_encode(static_cast<const uint16_t*>(d_src), static_cast<uint16_t*>(d_dst), (uint64_t)n, (uint32_t)block_size, st)) return 1;
+  return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 1;
+}
+int sqyx_bitshuffle_decode_UI16(const void* d_src, void* d_dst, long n, long block_size, void* stream) {
+  if (n < 0 || block_size < 0 || block_size > (1l << 30)) return 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (k_bitshuffle16_decode(static_cast<const uint16_t*>(d_src), static_cast<uint16_t*>(d_dst), (uint64_t)n, (uint32_t)block_size, st)) return 1;
+  return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 1;
 }
 
 int sqyx_bitswap_encode_UI16(int w, const void* d_src, void* d_dst, long n, int threshold, void* stream) {

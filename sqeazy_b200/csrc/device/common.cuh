@@ -21,6 +21,11 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");

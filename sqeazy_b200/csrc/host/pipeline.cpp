@@ -16,6 +16,7 @@ namespace sqyb {
 std::string Stage::name() const {
   switch (kind) {
     case StageKind::Bitswap: return "bitswap" + std::to_string(w);
+    case StageKind::Bitshuffle: return "bitshuffle";
     case StageKind::RemoveBackground: return "remove_background";
     case StageKind::RmEstBkrd: return "rmestbkrd";
     case StageKind::Quantiser: return "quantiser";
@@ -30,6 +31,9 @@ std::string Stage::config() const {
   switch (kind) {
     case StageKind::Bitswap:  // bitswap_scheme_impl.hpp:83-90
       msg << "num_bits_per_plane=" << w;
+      break;
+    case StageKind::Bitshuffle:  // bitshuffle_scheme_impl.hpp:78-84
+      msg << "block_size=" << block_size;
       break;
     case StageKind::RemoveBackground:  // remove_background_scheme_impl.hpp:62-67
       msg << "threshold=" << threshold;
@@ -77,7 +81,7 @@ std::string Pipeline::canonical() const {
 // registry (sqeazy_pipelines.hpp:31-77, hot-path stages only) + aliases
 // ------------------------------------------------------------------------------------------------
 static bool is_head_name(const std::string& n) {
-  return n == "bitswap1" || n == "bitswap2" || n == "bitswap4" || n == "bitswap8" || n == "remove_background" ||
+  return n == "bitswap1" || n == "bitswap2" || n == "bitswap4" || n == "bitswap8" || n == "bitshuffle" || n == "remove_background" ||
          n == "rmbkrd" || n == "rmestbkrd";
 }
 static bool is_sink_name(const std::string& n) { return n == "lz4" || n == "quantiser" || n == "pass_through"; }
@@ -101,6 +105,19 @@ static bool parse_float_like(const std::string& s, float& out) {
 
 static bool make_stage(const std::string& name, const std::string& args, Stage& st, int elem) {
   const std::map<std::string, std::string> kv = minors(args);
+  if (name == "bitshuffle") {
+    if (elem != 2) return false;                     // (uint16 kernels only in this build)
+    st.kind = StageKind::Bitshuffle;
+    st.block_size = 0;
+    auto f = kv.find("block_size");
+    if (f != kv.end()) {
+      char* e = nullptr;
+      const long v = std::strtol(f->second.c_str(), &e, 10);
+      if (!e || e == f->second.c_str() || v < 0 || v > (1l << 30)) return false;   // std::stoi would throw in the reference
+      st.block_size = (uint32_t)v;
+    }
+    return true;                                     // a block size that is no multiple of 8 fails at encode time, like bshuf's -81
+  }
   if (name.rfind("bitswap", 0) == 0) {
     st.kind = StageKind::Bitswap;
     st.w = std::atoi(name.c_str() + 7);

@@ -14,11 +14,12 @@
 
 namespace sqyb {
 
-enum class StageKind { Bitswap, RemoveBackground, RmEstBkrd, Quantiser, Lz4, PassThrough };
+enum class StageKind { Bitswap, Bitshuffle, RemoveBackground, RmEstBkrd, Quantiser, Lz4, PassThrough };
 
 struct Stage {
   StageKind kind;
   int w = 1;                                     // bitswap: bits per plane
+  uint32_t block_size = 0;                       // bitshuffle: elements per block, 0 = the library's default (bitshuffle_scheme_impl.hpp:45-58)
   int threshold = 0;                             // remove_background
   std::map<std::string, std::string> kv;         // quantiser config map (key order = std::map order, like the reference)
   bool has_decode_lut = false;

@@ -34,6 +34,7 @@ def test_version_triple(sq):
     ("remove_background(threshold=110)->bitswap1->lz4", True), ("pass_through", True),
     ("lz4(accel=1,blocksize_kb=256,framestep_kb=256,n_chunks_of_input=0)", True),
     ("bitswap1(num_bits_per_plane=1)->lz4", True), ("lz4->lz4", False), ("diff->lz4", False), ("bitswap1 ->lz4", False),
+    ("bitshuffle->lz4", True), ("rmestbkrd->bitshuffle->lz4", True), ("bitshuffle(block_size=512)->lz4", True), ("bitshuffle", True),
 ])
 def test_pipeline_possible(sq, p, ok):
     """tests/test_pipeline_interface.cpp:28-61 ; names outside the accelerated stages are refused (documented)"""
@@ -121,6 +122,7 @@ def test_hdf5_entry_points_fail_cleanly(sq):
     ("remove_background(threshold=7)->bitswap1->lz4", True), ("rmbkrd(threshold=7)->lz4", True),
     # stages without uint8 kernels here: refused (documented), like every other unaccelerated stage name
     ("rmestbkrd->lz4", False), ("quantiser->lz4", False), ("bitswap8->lz4", False), ("", False), ("lz4->lz4", False),
+    ("bitshuffle->lz4", False),
 ])
 def test_pipeline_possible_uint8(sq, p, ok):
     """dypeline<uint8_t>::can_be_built_from, src/sqeazy.cpp:243-268"""
