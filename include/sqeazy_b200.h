@@ -54,6 +54,9 @@ int sqyx_bitswap_decode_UI16(int w, const void* d_src, void* d_dst, long n, void
  * block_size in elements, 0 = the library's default (4096 for uint16); must be a multiple of 8. */
 int sqyx_bitshuffle_encode_UI16(const void* d_src, void* d_dst, long n, long block_size, void* stream);
 int sqyx_bitshuffle_decode_UI16(const void* d_src, void* d_dst, long n, long block_size, void* stream);
+/* the same for uint8 stacks (element size 1: 8 bit rows per block, default block 8192 elements) */
+int sqyx_bitshuffle_encode_UI8(const void* d_src, void* d_dst, long n, long block_size, void* stream);
+int sqyx_bitshuffle_decode_UI8(const void* d_src, void* d_dst, long n, long block_size, void* stream);
 
 /* out = in > t ? in - t : 0. reference: encoders/remove_background_scheme_impl.hpp:73-95 */
 int sqyx_remove_background_UI16(const void* d_src, void* d_dst, long n, int threshold, void* stream);

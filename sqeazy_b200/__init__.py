@@ -36,7 +36,7 @@ SQYX_SYMBOLS = [
     "sqyx_release_scratch", "sqyx_set_lz4_lane_max", "sqyx_set_device", "sqyx_enable_stage_timing", "sqyx_stage_ms", "sqyx_histogram_support",
     "sqyx_rmest_frame_portion", "sqyx_encode_device_UI8", "sqyx_decode_device_UI8", "sqyx_bitswap_encode_UI8",
     "sqyx_bitswap_decode_UI8", "sqyx_remove_background_UI8", "sqyx_decode_batch_device_UI16", "sqyx_encode_batch_device_UI16",
-    "sqyx_bitshuffle_encode_UI16", "sqyx_bitshuffle_decode_UI16",
+    "sqyx_bitshuffle_encode_UI16", "sqyx_bitshuffle_decode_UI16", "sqyx_bitshuffle_encode_UI8", "sqyx_bitshuffle_decode_UI8",
 ]
 
 _lib = None
@@ -303,14 +303,17 @@ def bitswap_decode_device(w: int, src, dst, stream=None):
 
 
 def bitshuffle_encode_device(src, dst, block_size: int = 0, stream=None):
-    rc = lib().sqyx_bitshuffle_encode_UI16(_dp(src), _dp(dst), c_long(src.numel()), c_long(block_size), _stream_handle(stream))
+    """uint16 or uint8 elements by the tensor's element size"""
+    fn = lib().sqyx_bitshuffle_encode_UI16 if src.element_size() == 2 else lib().sqyx_bitshuffle_encode_UI8
+    rc = fn(_dp(src), _dp(dst), c_long(src.numel()), c_long(block_size), _stream_handle(stream))
     if rc != 0:
         raise SqeazyError("sqyx_bitshuffle_encode_UI16 failed")
     return dst
 
 
 def bitshuffle_decode_device(src, dst, block_size: int = 0, stream=None):
-    rc = lib().sqyx_bitshuffle_decode_UI16(_dp(src), _dp(dst), c_long(src.numel()), c_long(block_size), _stream_handle(stream))
+    fn = lib().sqyx_bitshuffle_decode_UI16 if src.element_size() == 2 else lib().sqyx_bitshuffle_decode_UI8
+    rc = fn(_dp(src), _dp(dst), c_long(src.numel()), c_long(block_size), _stream_handle(stream))
     if rc != 0:
         raise SqeazyError("sqyx_bitshuffle_decode_UI16 failed")
     return dst

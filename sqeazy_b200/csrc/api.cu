@@ -243,7 +243,7 @@ int encode_device_impl(Arena& A, const Pipeline& pl_in, const void* d_src_any, c
       }
     } else if (s.kind == StageKind::Bitshuffle) {
       if (next_buf(&out)) return 1;
-      if (k_bitshuffle16_encode(cur, out, N, s.block_size, st)) {
+      if (u8 ? k_bitshuffle8_encode(b8(cur), m8(out), N, s.block_size, st) : k_bitshuffle16_encode(cur, out, N, s.block_size, st)) {
         std::fprintf(stderr, "[sqeazy_b200] bitshuffle failed (block_size=%u must be a multiple of 8)\n", s.block_size);
         return 1;
       }
@@ -504,7 +504,10 @@ int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const ui
       if (scratch(cur == bufs[0] ? 1 : 0, &out)) return 1;
     }
     if (swaps[k] < 0) {
-      if (u8 || k_bitshuffle16_decode(cur, out, N, (uint32_t)(-1 - swaps[k]), st)) return 100 + 1;
+      const uint32_t bsz = (uint32_t)(-1 - swaps[k]);
+      if (u8 ? k_bitshuffle8_decode(reinterpret_cast<const uint8_t*>(cur), reinterpret_cast<uint8_t*>(out), N, bsz, st)
+             : k_bitshuffle16_decode(cur, out, N, bsz, st))
+        return 100 + 1;
       cur = out;
       continue;
     }
@@ -809,6 +812,19 @@ int sqyx_bitshuffle_decode_UI16(const void* d_src, void* d_dst, long n, long blo
   if (n < 0 || block_size < 0 || block_size > (1l << 30)) return 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (k_bitshuffle16_decode(static_cast<const uint16_t*>(d_src), static_cast<uint16_t*>(d_dst), (uint64_t)n, (uint32_t)block_size, st)) return 1;
+  return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 1;
+}
+
+int sqyx_bitshuffle_encode_UI8(const void* d_src, void* d_dst, long n, long block_size, void* stream) {
+  if (n < 0 || block_size < 0 || block_size > (1l << 30)) return 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (k_bitshuffle8_encode(static_cast<const uint8_t*>(d_src), static_cast<uint8_t*>(d_dst), (uint64_t)n, (uint32_t)block_size, st)) return 1;
+  return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 1;
+}
+int sqyx_bitshuffle_decode_UI8(const void* d_src, void* d_dst, long n, long block_size, void* stream) {
+  if (n < 0 || block_size < 0 || block_size > (1l << 30)) return 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (k_bitshuffle8_decode(static_cast<const uint8_t*>(d_src), static_cast<uint8_t*>(d_dst), (uint64_t)n, (uint32_t)block_size, st)) return 1;
   return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 1;
 }
 

@@ -31,4 +31,17 @@ __host__ __device__ __forceinline__ void transpose16x16_pairs(uint32_t* w) {
   delta_swap_stage<1>(w);
 }
 
+// 8x8 bit-matrix transpose of the 8 bytes of x (byte j = row j, least significant bit = column 0): afterwards bit j of byte r
+// is what bit r of byte j was (the TRANS_BIT_8X8 step of the bitshuffle library on little-endian words). An involution.
+__host__ __device__ __forceinline__ uint64_t transpose8x8(uint64_t x) {
+  uint64_t t;
+  t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;
+  x ^= t ^ (t << 7);
+  t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull;
+  x ^= t ^ (t << 14);
+  t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull;
+  x ^= t ^ (t << 28);
+  return x;
+}
+
 }  // namespace sqyb

@@ -126,6 +126,93 @@ __global__ void copy_tail16(const uint16_t* __restrict__ in, uint16_t* __restric
   if (threadIdx.x < count) out[first + threadIdx.x] = in[first + threadIdx.x];
 }
 
+// ---- uint8 elements (the *_UI8 entry points): 8 bit rows per block, default blocks of 8192 elements ----
+// A thread takes 32 bytes (one 256-bit load) = four groups of 8; the 8x8 bit transpose of a group (64-bit delta swaps) leaves
+// in byte r the bits r of its 8 elements, i.e. the group's byte of row r; the four groups' bytes make the 32-bit word the
+// thread stores into row r.
+__global__ void __launch_bounds__(256) bitshuffle8_encode_fast(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                                uint64_t n32, uint32_t bs) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint32_t row_bytes = bs / 8, per_block = bs / 32;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n32; t += stride) {
+    uint32_t L[8];
+    ld256(in + t * 32, L);
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint64_t x = transpose8x8((uint64_t)L[2 * g] | ((uint64_t)L[2 * g + 1] << 32));
+      lo[g] = (uint32_t)x;          // rows 0..3 of group g
+      hi[g] = (uint32_t)(x >> 32);  // rows 4..7
+    }
+    const uint64_t blk = t / per_block;
+    const uint32_t c = (uint32_t)(t - blk * per_block);
+    uint8_t* o = out + blk * (uint64_t)bs + 4u * c;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint32_t* q = r < 4 ? lo : hi;
+      const int b = r & 3;          // byte b of the four group words
+      const uint32_t s01 = __byte_perm(q[0], q[1], 0x0040 + b * 0x0011);   // (q0.b, q1.b, -, -)
+      const uint32_t s23 = __byte_perm(q[2], q[3], 0x0040 + b * 0x0011);
+      st_stream(reinterpret_cast<uint32_t*>(o + (uint64_t)r * row_bytes), __byte_perm(s01, s23, 0x5410));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bitshuffle8_decode_fast(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                                uint64_t n32, uint32_t bs) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint32_t row_bytes = bs / 8, per_block = bs / 32;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n32; t += stride) {
+    const uint64_t blk = t / per_block;
+    const uint32_t c = (uint32_t)(t - blk * per_block);
+    const uint8_t* s = in + blk * (uint64_t)bs + 4u * c;
+    uint32_t w[8], L[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) w[r] = ld_stream(reinterpret_cast<const uint32_t*>(s + (uint64_t)r * row_bytes));
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      // byte g of the eight row words = the transposed group g
+      const uint32_t sel = 0x0040 + g * 0x0011;
+      const uint32_t lo = __byte_perm(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel), 0x5410);
+      const uint32_t hi = __byte_perm(__byte_perm(w[4], w[5], sel), __byte_perm(w[6], w[7], sel), 0x5410);
+      const uint64_t x = transpose8x8((uint64_t)lo | ((uint64_t)hi << 32));
+      L[2 * g] = (uint32_t)x;
+      L[2 * g + 1] = (uint32_t)(x >> 32);
+    }
+    st256(out + t * 32, L);
+  }
+}
+
+// any geometry / alignment: a thread per group of 8 elements
+__global__ void __launch_bounds__(256) bitshuffle8_generic(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t first,
+                                                            uint64_t count, uint32_t bs, int decode) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, groups = count / 8;
+  const uint32_t row_bytes = bs / 8;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    const uint64_t blk = g / row_bytes;
+    const uint32_t c = (uint32_t)(g - blk * row_bytes);
+    const uint64_t rows = first + blk * (uint64_t)bs + c, elems = first + g * 8;
+    uint64_t x = 0;
+    if (decode) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) x |= (uint64_t)in[rows + (uint64_t)r * row_bytes] << (8 * r);
+      x = transpose8x8(x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out[elems + i] = (uint8_t)(x >> (8 * i));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x |= (uint64_t)in[elems + i] << (8 * i);
+      x = transpose8x8(x);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) out[rows + (uint64_t)r * row_bytes] = (uint8_t)(x >> (8 * r));
+    }
+  }
+}
+
+__global__ void copy_tail8(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t first, uint32_t count) {
+  if (threadIdx.x < count) out[first + threadIdx.x] = in[first + threadIdx.x];
+}
+
 int grid_for(uint64_t work, int threads) {
   uint64_t blocks = (work + threads - 1) / threads;
   const uint64_t cap = (uint64_t)kNumSMs * 32;
@@ -185,6 +272,39 @@ int k_bitshuffle16_encode(const uint16_t* in, uint16_t* out, uint64_t n, uint32_
 }
 int k_bitshuffle16_decode(const uint16_t* in, uint16_t* out, uint64_t n, uint32_t block_size, cudaStream_t st) {
   return run_bitshuffle16(false, in, out, n, block_size, st);
+}
+
+static int run_bitshuffle8(bool encode, const uint8_t* in, uint8_t* out, uint64_t n, uint32_t block_size, cudaStream_t st) {
+  const uint32_t bs = bitshuffle_block_elems(block_size, 1);
+  if (bs % 8u) return -81;
+  if (n == 0) return 0;
+  const uint64_t full = (n / bs) * bs, last = ((n - full) / 8) * 8, left = n - full - last;
+  const bool aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 31) == 0;
+  if (full) {
+    if (aligned && bs % 32u == 0) {
+      if (encode) bitshuffle8_encode_fast<<<grid_for(full / 32, 256), 256, 0, st>>>(in, out, full / 32, bs);
+      else bitshuffle8_decode_fast<<<grid_for(full / 32, 256), 256, 0, st>>>(in, out, full / 32, bs);
+    } else {
+      bitshuffle8_generic<<<grid_for(full / 8, 256), 256, 0, st>>>(in, out, 0, full, bs, encode ? 0 : 1);
+    }
+    SQYB_COUNT_LAUNCH(1);
+  }
+  if (last) {
+    bitshuffle8_generic<<<grid_for(last / 8, 256), 256, 0, st>>>(in, out, full, last, (uint32_t)last, encode ? 0 : 1);
+    SQYB_COUNT_LAUNCH(1);
+  }
+  if (left) {
+    copy_tail8<<<1, 32, 0, st>>>(in, out, full + last, (uint32_t)left);
+    SQYB_COUNT_LAUNCH(1);
+  }
+  return (int)cudaGetLastError();
+}
+
+int k_bitshuffle8_encode(const uint8_t* in, uint8_t* out, uint64_t n, uint32_t block_size, cudaStream_t st) {
+  return run_bitshuffle8(true, in, out, n, block_size, st);
+}
+int k_bitshuffle8_decode(const uint8_t* in, uint8_t* out, uint64_t n, uint32_t block_size, cudaStream_t st) {
+  return run_bitshuffle8(false, in, out, n, block_size, st);
 }
 
 }  // namespace sqyb

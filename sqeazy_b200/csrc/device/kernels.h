@@ -27,6 +27,8 @@ int k_bitswap_decode_range(int w, const uint16_t* in, uint16_t* out, uint64_t n,
 // block_size in elements, 0 = the library's default (4096); -81 (the library's own code) when it is not a multiple of 8
 int k_bitshuffle16_encode(const uint16_t* in, uint16_t* out, uint64_t n, uint32_t block_size, cudaStream_t st);
 int k_bitshuffle16_decode(const uint16_t* in, uint16_t* out, uint64_t n, uint32_t block_size, cudaStream_t st);
+int k_bitshuffle8_encode(const uint8_t* in, uint8_t* out, uint64_t n, uint32_t block_size, cudaStream_t st);   // uint8: default 8192
+int k_bitshuffle8_decode(const uint8_t* in, uint8_t* out, uint64_t n, uint32_t block_size, cudaStream_t st);
 uint32_t bitshuffle_block_elems(uint32_t block_size, int elem_size);
 
 // bitswap8.cu (uint8 volumes)

@@ -106,7 +106,6 @@ static bool parse_float_like(const std::string& s, float& out) {
 static bool make_stage(const std::string& name, const std::string& args, Stage& st, int elem) {
   const std::map<std::string, std::string> kv = minors(args);
   if (name == "bitshuffle") {
-    if (elem != 2) return false;                     // (uint16 kernels only in this build)
     st.kind = StageKind::Bitshuffle;
     st.block_size = 0;
     auto f = kv.find("block_size");

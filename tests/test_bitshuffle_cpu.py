@@ -96,3 +96,25 @@ def test_fast_kernel_thread_program_matches_oracle(port, sim, bs):
     back = np.zeros(n, np.uint16)
     sim.sim_bitshuffle16_decode_fast(want.ctypes.data_as(ctypes.c_void_p), back.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(n // 32), ctypes.c_uint32(bs))
     assert np.array_equal(back, a)
+
+
+@pytest.mark.parametrize("bs", [32, 64, 1024, 8192])
+def test_fast_uint8_kernel_thread_program_matches_oracle(port, sim, bs):
+    n = bs * 3
+    a = np.random.default_rng(bs + 1).integers(0, 256, size=n, dtype=np.uint8)
+    want = port.bitshuffle(a, bs)
+    got = np.zeros(n, np.uint8)
+    sim.sim_bitshuffle8_encode_fast(a.ctypes.data_as(ctypes.c_void_p), got.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(n // 32), ctypes.c_uint32(bs))
+    assert np.array_equal(got, want)
+    back = np.zeros(n, np.uint8)
+    sim.sim_bitshuffle8_decode_fast(want.ctypes.data_as(ctypes.c_void_p), back.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(n // 32), ctypes.c_uint32(bs))
+    assert np.array_equal(back, a)
+
+
+@pytest.mark.parametrize("n", [0, 7, 8, 9, 8191, 8192, 8200, 32003, 100003])
+@pytest.mark.parametrize("bs", [0, 8, 24, 1000, 8192])
+def test_oracle_matches_numpy_formulation_uint8(port, n, bs):
+    a = np.random.default_rng(n + bs + 5).integers(0, 256, size=n, dtype=np.uint8)
+    enc = port.bitshuffle(a, bs)
+    assert np.array_equal(enc, numpy_bitshuffle(a, bs))
+    assert np.array_equal(port.bitshuffle(enc, bs, decode=True), a)

@@ -101,3 +101,39 @@ def test_bitshuffle_device_pipeline_and_ratio(sq, cuda):
         sizes[p] = blob.numel()
     # rows of 512 bytes per 4096-voxel block instead of whole-stack planes: the runs are shorter, the ratio a little lower
     assert sizes["bitshuffle->lz4"] < 0.6 * vol.nbytes and sizes["bitshuffle->lz4"] < 1.25 * sizes["bitswap1->lz4"]
+
+
+@pytest.mark.parametrize("bs", [0, 8, 24, 64, 1000, 8192])
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 31, 32, 8191, 8192, 8193, 8200, 32003, (1 << 22) + 5])
+def test_bitshuffle_uint8_stage_parity(sq, cuda, port, n, bs):
+    a = np.random.default_rng(n * 7 + bs).integers(0, 256, size=n, dtype=np.uint8)
+    d_in = dev(cuda, a) if n else cuda.empty(0, dtype=cuda.uint8, device="cuda")
+    d_out = cuda.full((n + 16,), 0xEE, dtype=cuda.uint8, device="cuda")
+    sq.bitshuffle_encode_device(d_in, d_out[:n], bs)
+    got = d_out.cpu().numpy()
+    assert np.array_equal(got[:n], port.bitshuffle(a, bs))
+    assert np.all(got[n:] == 0xEE)
+    back = cuda.empty(n, dtype=cuda.uint8, device="cuda")
+    sq.bitshuffle_decode_device(d_out[:n], back, bs)
+    assert np.array_equal(back.cpu().numpy(), a)
+    if n > 64:                                             # unaligned views: the thread-per-group kernel
+        out2 = cuda.zeros(n, dtype=cuda.uint8, device="cuda")
+        sq.bitshuffle_encode_device(d_in[3:], out2[1: n - 2], bs)
+        assert np.array_equal(out2.cpu().numpy()[1: n - 2], port.bitshuffle(a[3:], bs))
+
+
+@pytest.mark.parametrize("pipeline", ["bitshuffle->lz4", "bitshuffle", "remove_background(threshold=19)->bitshuffle(block_size=256)->lz4"])
+def test_bitshuffle_uint8_pipelines(sq, cuda, port, ref, pipeline):
+    rng = np.random.default_rng(6)
+    vol = np.clip(np.rint(20 + 2 * rng.standard_normal((9, 130, 257))), 0, 255).astype(np.uint8)
+    blob = sq.encode_u8(pipeline, vol)
+    hdr = orc.unpack_header(blob.tobytes())
+    assert hdr["raw_type"] in ("uint8", "unsigned char", "h") or "8" in str(hdr["raw_type"])
+    want = port.remove_background8(vol.reshape(-1), 19).reshape(vol.shape) if "remove_background" in pipeline else vol
+    assert np.array_equal(sq.decode_u8(blob).reshape(vol.shape), want)
+    payload = blob[hdr["size"]:]
+    if pipeline.endswith("lz4"):
+        rc, payload = ref.lz4_decode_bytes(payload, vol.nbytes)
+        assert rc == 0
+    bs = 256 if "block_size=256" in pipeline else 0
+    assert np.array_equal(port.bitshuffle(np.frombuffer(payload.tobytes(), dtype=np.uint8), bs, decode=True).reshape(vol.shape), want)

@@ -122,7 +122,7 @@ def test_hdf5_entry_points_fail_cleanly(sq):
     ("remove_background(threshold=7)->bitswap1->lz4", True), ("rmbkrd(threshold=7)->lz4", True),
     # stages without uint8 kernels here: refused (documented), like every other unaccelerated stage name
     ("rmestbkrd->lz4", False), ("quantiser->lz4", False), ("bitswap8->lz4", False), ("", False), ("lz4->lz4", False),
-    ("bitshuffle->lz4", False),
+    ("bitshuffle->lz4", True), ("bitshuffle(block_size=64)", True),
 ])
 def test_pipeline_possible_uint8(sq, p, ok):
     """dypeline<uint8_t>::can_be_built_from, src/sqeazy.cpp:243-268"""
