@@ -36,7 +36,7 @@ SQYX_SYMBOLS = [
     "sqyx_release_scratch", "sqyx_set_lz4_lane_max", "sqyx_set_device", "sqyx_enable_stage_timing", "sqyx_stage_ms", "sqyx_histogram_support",
     "sqyx_rmest_frame_portion", "sqyx_encode_device_UI8", "sqyx_decode_device_UI8", "sqyx_bitswap_encode_UI8",
     "sqyx_bitswap_decode_UI8", "sqyx_remove_background_UI8", "sqyx_decode_batch_device_UI16", "sqyx_encode_batch_device_UI16",
-    "sqyx_bitshuffle_encode_UI16", "sqyx_bitshuffle_decode_UI16", "sqyx_bitshuffle_encode_UI8", "sqyx_bitshuffle_decode_UI8",
+    "sqyx_bitshuffle_encode_UI16", "sqyx_bitshuffle_decode_UI16", "sqyx_bitshuffle_encode_UI8", "sqyx_bitshuffle_decode_UI8", "sqyx_set_lz4_defer_min",
 ]
 
 _lib = None
@@ -471,6 +471,13 @@ def set_lz4_lane_max(nbytes: int) -> int:
     f = lib().sqyx_set_lz4_lane_max
     f.restype = c_long
     return int(f(c_long(int(nbytes))))
+
+
+def set_lz4_defer_min(nblocks: int) -> int:
+    """linked blocks from which a stream takes the deferred-reference decoder (default 8, 0 = never); returns the previous value"""
+    f = lib().sqyx_set_lz4_defer_min
+    f.restype = c_long
+    return f(c_long(nblocks))
 
 
 def host_l2_bytes() -> int:

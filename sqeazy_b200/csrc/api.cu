@@ -53,7 +53,7 @@ constexpr int kVersionMajor = 0, kVersionMinor = 7, kVersionPatch = 2;
   } while (0)
 
 // ---- cached device scratch, one arena per device, guarded by one lock (calls are serialised) ----
-enum Slot { kSlotA = 0, kSlotB, kSlotIn, kSlotOut, kSlotWs, kSlotSmall, kNumSlots };
+enum Slot { kSlotA = 0, kSlotB, kSlotIn, kSlotOut, kSlotWs, kSlotSmall, kSlotOrigins, kNumSlots };
 
 struct Arena {
   void* ptr[kNumSlots] = {nullptr};
@@ -390,11 +390,22 @@ int lz4_decode_checked(Arena& A, const uint8_t* src, uint64_t nbytes, uint8_t* d
   for (int attempt = 0; attempt < 2; ++attempt) {
     {
       ScopedStageTimer tm(kTLz4Dec, st);
-      CKK(k_lz4_decode(src, nbytes, dst, dst_bytes, ws, attempt, st));
+      CKK(k_lz4_decode(src, nbytes, dst, dst_bytes, ws, attempt, 1, st));
     }
-    uint32_t err = 0;
+    uint32_t err = 0, deferred = 0;
     uint64_t total = 0;
-    if (k_lz4_decode_status(ws, &err, &total, st)) return 1;
+    if (k_lz4_decode_status(ws, &err, &total, &deferred, st)) return 1;
+    if (err == 0 && deferred) {
+      // block-linked frames (reference serial mode / sqy CLI default): deferred cross-block references, lz4_decode.cu
+      void* origins = nullptr;
+      if (A.get(kSlotOrigins, k_lz4_decode_linked_workspace_bytes(dst_bytes), &origins)) return 1;
+      {
+        ScopedStageTimer tm(kTLz4Dec, st);
+        CKK(k_lz4_decode_linked(src, nbytes, dst, dst_bytes, ws, origins, st));
+      }
+      uint32_t none = 0;
+      if (k_lz4_decode_status(ws, &err, &total, &none, st)) return 1;
+    }
     if (err == 0) {
       if (decoded) *decoded = total;
       return 0;
@@ -608,6 +619,7 @@ int sqyx_last_lz4_stats(long* out4) {
 }
 
 long sqyx_set_lz4_lane_max(long bytes) { return k_lz4_set_lane_max(bytes); }
+long sqyx_set_lz4_defer_min(long nblocks) { return k_lz4_set_defer_min(nblocks); }
 
 int sqyx_release_scratch(void) {
   std::lock_guard<std::mutex> lk(g_mu);

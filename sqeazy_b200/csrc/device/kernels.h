@@ -58,10 +58,18 @@ int k_lz4_encode_end(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void*
 
 // lz4_decode.cu
 size_t k_lz4_decode_workspace_bytes(uint64_t dst_bytes);
+// allow_deferred: streams with many block-LINKED blocks (the reference's serial mode) only get their block table here; their
+// blocks are decoded by k_lz4_decode_linked (deferred cross-block references) once the caller has seen deferred_blocks > 0
+// in the status and provided the origin buffer.
 int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, int measure_all,
-                 cudaStream_t st);
+                 int allow_deferred, cudaStream_t st);
+size_t k_lz4_decode_linked_workspace_bytes(uint64_t dst_bytes);
+int k_lz4_decode_linked(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, void* origins,
+                        cudaStream_t st);
 // decoded-size limit of the lane-serial block decoder (0 = warp-per-block decoder only); returns the previous value
 long k_lz4_set_lane_max(long bytes);
-int k_lz4_decode_status(void* workspace, uint32_t* error, uint64_t* total_decoded, cudaStream_t st);
+// linked blocks from which a stream takes the deferred-reference path (default 8, 0 = never); returns the previous value
+long k_lz4_set_defer_min(long nblocks);
+int k_lz4_decode_status(void* workspace, uint32_t* error, uint64_t* total_decoded, uint32_t* deferred_blocks, cudaStream_t st);
 
 }  // namespace sqyb

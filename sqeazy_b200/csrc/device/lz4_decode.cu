@@ -32,6 +32,8 @@ namespace sqyb {
 namespace {
 
 constexpr uint32_t kNoLink = 0xFFFFFFFFu;
+constexpr uint32_t kLinkHead = 0xFFFFFFFEu;   // first block of a block-linked frame: nothing in front of it, but successors link to it
+constexpr uint32_t kDeferMin = 8;             // default: streams with at least this many linked blocks take the deferred-reference path
 
 enum DecErr : uint32_t {
   kErrNone = 0,
@@ -56,6 +58,9 @@ struct DecCtl {          // lives at the start of the workspace
   uint32_t fast, fast_nblk, fast_bb, fast_pad;
   unsigned long long fast_idx, fast_first, fast_raw;
   unsigned long long total_decoded;
+  uint32_t nlinked;      // blocks that belong to block-linked frames
+  uint32_t deferred;     // 1: those blocks are left to lz4_decode_deferred_kernel + the two resolve passes (k_lz4_decode_linked)
+  uint32_t ticket_deferred, pad1;
 };
 
 struct DecTables {
@@ -110,13 +115,13 @@ constexpr uint32_t kTile = 4096;        // blocks per CTA tile of the fast table
 
 __global__ void __launch_bounds__(kDirThreads) lz4_directory_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
                                                                     DecCtl* ctl, DecTables T, uint32_t capacity,
-                                                                    int measure_all) {
+                                                                    int measure_all, int defer_min) {
   __shared__ unsigned long long warp_sums[32];
   __shared__ unsigned long long sh_pos;
-  __shared__ uint32_t sh_nb, sh_err, sh_mode, sh_need;
+  __shared__ uint32_t sh_nb, sh_err, sh_mode, sh_need, sh_linked;
   __shared__ unsigned long long sh_args[4];
   const int tid = threadIdx.x;
-  if (tid == 0) { sh_pos = 0; sh_nb = 0; sh_err = 0; sh_need = 0; }
+  if (tid == 0) { sh_pos = 0; sh_nb = 0; sh_err = 0; sh_need = 0; sh_linked = 0; }
   __syncthreads();
   while (true) {
     // ---- thread 0 classifies what starts at pos ----
@@ -193,7 +198,8 @@ __global__ void __launch_bounds__(kDirThreads) lz4_directory_kernel(const uint8_
                 // non-final blocks of liblz4 frames are full; measure_all drops that assumption
                 T.dsize[nb] = (word & kLz4StoredFlag) ? sz : (measure_all ? 0u : maxblock);
                 if (measure_all && !(word & kLz4StoredFlag)) sh_need++;
-                T.link[nb] = (!indep && nb > first_of_frame) ? nb - 1 : kNoLink;
+                T.link[nb] = indep ? kNoLink : (nb > first_of_frame ? nb - 1 : kLinkHead);
+                if (!indep) sh_linked++;
                 nb++;
                 p += 4ull + sz + (bchk ? 4 : 0);
               }
@@ -259,6 +265,8 @@ __global__ void __launch_bounds__(kDirThreads) lz4_directory_kernel(const uint8_
     ctl->nblocks = sh_nb;
     ctl->error = sh_err;
     ctl->need_sizes = sh_need;
+    ctl->nlinked = sh_linked;
+    ctl->deferred = (defer_min > 0 && sh_linked >= (uint32_t)defer_min) ? 1u : 0u;
   }
 }
 
@@ -989,7 +997,9 @@ __global__ void __launch_bounds__(kWinWarps * 32, 5) lz4_decode_kernel(const uin
     const uint32_t csize = word & 0x7FFFFFFFu;
     const uint32_t dsize = T.dsize[b];
     const unsigned long long doff = T.dst_off[b];
-    const uint32_t link = T.link[b];
+    uint32_t link = T.link[b];
+    if (link != kNoLink && ctl->deferred) continue;   // block-linked frames: lz4_decode_deferred_kernel + resolve passes
+    if (link == kLinkHead) link = kNoLink;
     const uint8_t* s = src + T.src_off[b];
     uint8_t* d = dst + doff;
     bool waited = false;
@@ -1047,6 +1057,154 @@ __global__ void __launch_bounds__(kWinWarps * 32, 5) lz4_decode_kernel(const uin
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Block-linked frames (the reference's serial mode = the sqy CLI default, encoders/lz4_utils.hpp:99-173): a block may
+// copy from the 64 KiB in front of it, i.e. from the tail of its predecessor, which exists only when the predecessor
+// is finished: decoded as they come, the blocks run one after the other (0.15 GB/s for 8192 blocks of 256 KiB).
+// Deferred cross-block references break that chain in three passes:
+//   1. lz4_decode_deferred_kernel : every block is decoded at once, a warp per block, straight in global memory. A byte
+//      that comes from in front of the block is not copied but REMEMBERED: origin[i] = its distance in front of the
+//      block start (1..65535, the LZ4 offset range; 0 = the byte in dst[i] is real). Copies inside the block carry the
+//      origin along, so after this pass every byte of every block is either real or names one byte of the 64 KiB window
+//      in front of its block.
+//   2. lz4_resolve_chain_kernel   : the only serial part — one CTA walks the blocks in order and resolves the last
+//      65535 bytes of each (what the next block's origins can point at) from the already resolved bytes in front of it:
+//      64 KiB of gathers per block instead of a whole block decode.
+//   3. lz4_resolve_rest_kernel    : all remaining remembered bytes of all blocks, in parallel.
+// A source pattern is always read in front of the match (k mod offset), so lanes never depend on each other inside a match.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lz4_decode_deferred_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                  uint16_t* __restrict__ origin, DecCtl* ctl, DecTables T) {
+  if (ctl->error || !ctl->deferred) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t nblocks = ctl->nblocks;
+  while (true) {
+    uint32_t b = 0;
+    if (lane == 0) b = atomicAdd(&ctl->ticket_deferred, 1u);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= nblocks) return;
+    const uint32_t link = T.link[b];
+    if (link == kNoLink) continue;
+    const uint32_t word = T.word[b];
+    const uint32_t csize = word & 0x7FFFFFFFu, dsize = T.dsize[b];
+    const unsigned long long doff = T.dst_off[b];
+    const uint8_t* s = src + T.src_off[b];
+    uint8_t* d = dst + doff;
+    uint16_t* o = origin + doff;
+    // bytes that exist in front of this block inside its frame's reach
+    const unsigned long long before = link == kLinkHead ? 0ull : (doff < 65535ull ? doff : 65535ull);
+    uint32_t err = 0;
+    if (word & kLz4StoredFlag) {
+      if (csize != dsize) err = kErrSizeMismatch;
+      else
+        for (uint32_t k = lane; k < csize; k += 32) { d[k] = __ldg(s + k); o[k] = 0; }
+    } else {
+      uint32_t ip = 0, op = 0;
+      while (ip < csize && !err) {
+        const uint32_t token = __ldg(s + ip);
+        ip++;
+        uint32_t lit = token >> 4;
+        if (lit == 15u) {
+          uint32_t x;
+          do {
+            if (ip >= csize) { err = kErrBadBlock; break; }
+            x = __ldg(s + ip);
+            ip++;
+            lit += x;
+          } while (x == 255u);
+        }
+        if (err) break;
+        if ((unsigned long long)ip + lit > csize || (unsigned long long)op + lit > dsize) { err = kErrBadBlock; break; }
+        for (uint32_t k = lane; k < lit; k += 32) { d[op + k] = __ldg(s + ip + k); o[op + k] = 0; }
+        ip += lit;
+        op += lit;
+        if (ip >= csize) break;            // the last sequence has literals only
+        if (ip + 2u > csize) { err = kErrBadBlock; break; }
+        const uint32_t offset = __ldg(s + ip) | (__ldg(s + ip + 1) << 8);
+        ip += 2;
+        uint32_t mlen = token & 15u;
+        if (mlen == 15u) {
+          uint32_t x;
+          do {
+            if (ip >= csize) { err = kErrBadBlock; break; }
+            x = __ldg(s + ip);
+            ip++;
+            mlen += x;
+          } while (x == 255u);
+        }
+        if (err) break;
+        mlen += 4u;
+        if (offset == 0u || (unsigned long long)op + mlen > dsize) { err = kErrBadBlock; break; }
+        if (offset > op && (unsigned long long)(offset - op) > before) { err = kErrBadBlock; break; }
+        __syncwarp();                      // the literals (and everything before them) are visible to every lane
+        const long long base = (long long)op - (long long)offset;   // start of the pattern, may lie in front of the block
+        const bool wraps = offset < mlen, pow2 = (offset & (offset - 1u)) == 0u;
+        for (uint32_t k = lane; k < mlen; k += 32) {
+          uint32_t j = k;
+          if (wraps) j = pow2 ? (k & (offset - 1u)) : (k % offset);
+          const long long sp = base + (long long)j;
+          uint8_t v = 0;
+          uint16_t g;
+          if (sp < 0) {
+            g = (uint16_t)(-sp);           // a byte of the window in front of the block: remember which one
+          } else {
+            v = __ldcg(d + sp);
+            g = __ldcg(o + sp);
+          }
+          d[op + k] = v;
+          o[op + k] = g;
+        }
+        op += mlen;
+        __syncwarp();
+      }
+      if (!err && (ip != csize || op != dsize)) err = kErrSizeMismatch;
+    }
+    if (err && lane == 0) atomicMax(&ctl->error, err);
+  }
+}
+
+__global__ void __launch_bounds__(1024) lz4_resolve_chain_kernel(uint8_t* __restrict__ dst, uint16_t* __restrict__ origin,
+                                                                 const DecCtl* ctl, DecTables T) {
+  if (ctl->error || !ctl->deferred) return;
+  const uint32_t nblocks = ctl->nblocks;
+  for (uint32_t b = 0; b < nblocks; ++b) {
+    const uint32_t link = T.link[b];
+    if (link == kNoLink || link == kLinkHead) continue;      // (the same for every thread) heads hold real bytes only
+    const unsigned long long doff = T.dst_off[b];
+    const uint32_t dsize = T.dsize[b];
+    const uint32_t tail = dsize < 65535u ? dsize : 65535u;
+    const unsigned long long t0 = doff + dsize - tail;
+    // an origin names a byte at most 65535 in front of the block: it lies in the tail of an earlier block, resolved by now
+#pragma unroll 8
+    for (uint32_t i = threadIdx.x; i < tail; i += 1024) {
+      const uint32_t g = __ldcg(origin + t0 + i);
+      if (g) {
+        dst[t0 + i] = __ldcg(dst + doff - g);
+        origin[t0 + i] = 0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) lz4_resolve_rest_kernel(uint8_t* __restrict__ dst, const uint16_t* __restrict__ origin,
+                                                               const DecCtl* ctl, DecTables T) {
+  if (ctl->error || !ctl->deferred) return;
+  const uint32_t nblocks = ctl->nblocks;
+  for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const uint32_t link = T.link[b];
+    if (link == kNoLink || link == kLinkHead) continue;
+    const unsigned long long doff = T.dst_off[b];
+    const uint32_t dsize = T.dsize[b];
+    const uint32_t body = dsize < 65535u ? 0u : dsize - 65535u;   // everything in front of the tail
+    for (uint32_t i = threadIdx.x; i < body; i += blockDim.x) {
+      const uint32_t g = __ldcg(origin + doff + i);
+      if (g) dst[doff + i] = __ldcg(dst + doff - g);
+    }
+  }
+}
+
 }  // namespace
 
 // Independent blocks that decode to at most this many bytes go to the lane-serial decoder. Default 0 = off: measured on
@@ -1070,6 +1228,15 @@ long k_lz4_set_lane_max(long bytes) {
   return prev;
 }
 
+// number of block-linked blocks from which a stream takes the deferred-reference path (0 = never: every linked block waits
+// for its predecessor, the behaviour before that path existed). sqyx_set_lz4_defer_min() lets tests and benches run both.
+static std::atomic<long> g_defer_min{(long)kDeferMin};
+long k_lz4_set_defer_min(long nblocks) {
+  const long prev = g_defer_min.load(std::memory_order_relaxed);
+  if (nblocks >= 0) g_defer_min.store(nblocks, std::memory_order_relaxed);
+  return prev;
+}
+
 size_t k_lz4_decode_capacity(uint64_t dst_bytes) { return (size_t)(dst_bytes / kLz4BlockBytes + 1024); }
 
 size_t k_lz4_decode_workspace_bytes(uint64_t dst_bytes) {
@@ -1078,8 +1245,42 @@ size_t k_lz4_decode_workspace_bytes(uint64_t dst_bytes) {
 }
 
 // Enqueues the whole decode; the status lands in workspace (see k_lz4_decode_status).
+static DecTables dec_tables(void* workspace, uint64_t dst_bytes, unsigned long long** tile_sums_out) {
+  const size_t cap = k_lz4_decode_capacity(dst_bytes);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  DecTables T;
+  uint8_t* p = ws + 256;
+  T.src_off = reinterpret_cast<unsigned long long*>(p); p += 8 * cap;
+  T.dst_off = reinterpret_cast<unsigned long long*>(p); p += 8 * cap;
+  T.word = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
+  T.dsize = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
+  T.link = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
+  T.done = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
+  T.kind = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
+  T.work = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
+  if (tile_sums_out) *tile_sums_out = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(p) + 7) & ~(uintptr_t)7);
+  return T;
+}
+
+size_t k_lz4_decode_linked_workspace_bytes(uint64_t dst_bytes) { return 2 * (size_t)dst_bytes + 256; }
+
+// second step for streams of block-linked frames (k_lz4_decode_status reported them as deferred): `workspace` still
+// holds the block table of the k_lz4_decode call, `origins` has room for one uint16 per output byte
+int k_lz4_decode_linked(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, void* origins,
+                        cudaStream_t st) {
+  (void)src_bytes;
+  DecCtl* ctl = reinterpret_cast<DecCtl*>(workspace);
+  const DecTables T = dec_tables(workspace, dst_bytes, nullptr);
+  uint16_t* org = static_cast<uint16_t*>(origins);
+  lz4_decode_deferred_kernel<<<kNumSMs * 8, 256, 0, st>>>(src, dst, org, ctl, T);
+  lz4_resolve_chain_kernel<<<1, 1024, 0, st>>>(dst, org, ctl, T);
+  lz4_resolve_rest_kernel<<<kNumSMs * 8, 256, 0, st>>>(dst, org, ctl, T);
+  SQYB_COUNT_LAUNCH(3);
+  return (int)cudaGetLastError();
+}
+
 int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, int measure_all,
-                 cudaStream_t st) {
+                 int allow_deferred, cudaStream_t st) {
   const size_t cap = k_lz4_decode_capacity(dst_bytes);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   DecCtl* ctl = reinterpret_cast<DecCtl*>(ws);
@@ -1096,7 +1297,8 @@ int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t 
   unsigned long long* tile_sums = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(p) + 7) & ~(uintptr_t)7);
   const uint32_t tiles = (uint32_t)(cap / kTile + 1), tile_grid = tiles < 1024u ? tiles : 1024u;
   SQYB_CUDA_OK(cudaMemsetAsync(ctl, 0, sizeof(DecCtl), st));
-  lz4_directory_kernel<<<1, kDirThreads, 0, st>>>(src, src_bytes, ctl, T, (uint32_t)cap, measure_all);
+  lz4_directory_kernel<<<1, kDirThreads, 0, st>>>(src, src_bytes, ctl, T, (uint32_t)cap, measure_all,
+                                                  allow_deferred ? (int)g_defer_min.load(std::memory_order_relaxed) : 0);
   lz4_tile_sums_kernel<<<tile_grid, 256, 0, st>>>(src, ctl, tile_sums);
   lz4_expand_kernel<<<tile_grid, 256, 0, st>>>(src, ctl, T, tile_sums, dst_bytes);
   lz4_sizes_kernel<<<kNumSMs * 4, kDecThreads, 0, st>>>(src, ctl, T);
@@ -1116,12 +1318,13 @@ int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t 
 }
 
 // copies {error, total_decoded} back (synchronises the stream)
-int k_lz4_decode_status(void* workspace, uint32_t* error, uint64_t* total_decoded, cudaStream_t st) {
+int k_lz4_decode_status(void* workspace, uint32_t* error, uint64_t* total_decoded, uint32_t* deferred_blocks, cudaStream_t st) {
   DecCtl h;
   SQYB_CUDA_OK(cudaMemcpyAsync(&h, workspace, sizeof(DecCtl), cudaMemcpyDeviceToHost, st));
   SQYB_CUDA_OK(cudaStreamSynchronize(st));
   *error = h.error;
   *total_decoded = h.total_decoded;
+  if (deferred_blocks) *deferred_blocks = h.deferred ? h.nlinked : 0u;
   return 0;
 }
 
