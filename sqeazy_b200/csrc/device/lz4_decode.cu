@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kDirThreads) lz4_directory_kernel(const uint8_
                 T.dsize[nb] = (word & kLz4StoredFlag) ? sz : (measure_all ? 0u : maxblock);
                 if (measure_all && !(word & kLz4StoredFlag)) sh_need++;
                 T.link[nb] = indep ? kNoLink : (nb > first_of_frame ? nb - 1 : kLinkHead);
-                if (!indep) sh_linked++;
+                if (!indep && nb > first_of_frame) sh_linked++;
                 nb++;
                 p += 4ull + sz + (bchk ? 4 : 0);
               }
@@ -207,6 +207,8 @@ __global__ void __launch_bounds__(kDirThreads) lz4_directory_kernel(const uint8_
                 if (cchk) p += 4;
                 // the last block of a frame may be short: its size has to be measured
                 if (!measure_all && nb > first_of_frame && !(T.word[nb - 1] & kLz4StoredFlag)) { T.dsize[nb - 1] = 0; sh_need++; }
+                // a "linked" frame of a single block (the reference's multi-threaded mode: one frame per chunk) links nothing
+                if (!indep && nb == first_of_frame + 1) T.link[first_of_frame] = kNoLink;
                 sh_nb = nb;
                 sh_pos = p;
                 sh_mode = 2;
@@ -1164,27 +1166,102 @@ __global__ void __launch_bounds__(256) lz4_decode_deferred_kernel(const uint8_t*
   }
 }
 
-__global__ void __launch_bounds__(1024) lz4_resolve_chain_kernel(uint8_t* __restrict__ dst, uint16_t* __restrict__ origin,
-                                                                 const DecCtl* ctl, DecTables T) {
+constexpr uint32_t kChainThreads = 512;
+constexpr uint32_t kChainTail = 65536;      // bytes resolved per regular block (one more than an origin can reach: keeps the vectors aligned)
+constexpr size_t kChainSmem = 2 * (size_t)kChainTail;
+
+__global__ void __launch_bounds__(kChainThreads) lz4_resolve_chain_kernel(uint8_t* __restrict__ dst, uint16_t* __restrict__ origin,
+                                                                          const DecCtl* ctl, DecTables T) {
+  extern __shared__ __align__(16) unsigned char chain_smem[];
   if (ctl->error || !ctl->deferred) return;
   const uint32_t nblocks = ctl->nblocks;
+  const uint32_t tid = threadIdx.x;
+  // The window in front of the current block = the resolved tail of its predecessor lives in shared memory (two 64 KiB
+  // buffers, swapped every block), so the gathers of the chain cost shared-memory latency instead of an L2 round trip each.
+  uint32_t cur = 0;                          // byte offset of the buffer this block writes (0 or 65536); the other one is `prev`
+  bool have_prev = false;                    // `prev` holds the 65536 bytes in front of the block
+  // the table row of the next block is fetched while this one is resolved
+  uint32_t link = nblocks ? T.link[0] : kNoLink, dsize = nblocks ? T.dsize[0] : 0u;
+  unsigned long long doff = nblocks ? T.dst_off[0] : 0ull;
   for (uint32_t b = 0; b < nblocks; ++b) {
-    const uint32_t link = T.link[b];
-    if (link == kNoLink || link == kLinkHead) continue;      // (the same for every thread) heads hold real bytes only
-    const unsigned long long doff = T.dst_off[b];
-    const uint32_t dsize = T.dsize[b];
-    const uint32_t tail = dsize < 65535u ? dsize : 65535u;
-    const unsigned long long t0 = doff + dsize - tail;
-    // an origin names a byte at most 65535 in front of the block: it lies in the tail of an earlier block, resolved by now
-#pragma unroll 8
-    for (uint32_t i = threadIdx.x; i < tail; i += 1024) {
-      const uint32_t g = __ldcg(origin + t0 + i);
-      if (g) {
-        dst[t0 + i] = __ldcg(dst + doff - g);
-        origin[t0 + i] = 0;
+    const uint32_t nb = b + 1 < nblocks ? b + 1 : b;
+    const uint32_t link_n = T.link[nb], dsize_n = T.dsize[nb];
+    const unsigned long long doff_n = T.dst_off[nb];
+    if (link == kNoLink || link == kLinkHead) {              // (the same for every thread) heads hold real bytes only
+      have_prev = false;
+    } else {
+      const unsigned long long t0r = doff + dsize - kChainTail;
+      const bool regular = dsize >= kChainTail && doff >= kChainTail && ((((uintptr_t)(dst + t0r)) | ((uintptr_t)(dst + doff))) & 15) == 0 &&
+                           (((uintptr_t)(origin + t0r)) & 15) == 0;
+      if (regular) {
+        uint8_t* prev = chain_smem + (cur ^ kChainTail);
+        if (!have_prev) {                    // first regular block behind a head / an irregular block: fetch the window once
+          const uint4* w = reinterpret_cast<const uint4*>(dst + doff - kChainTail);
+          for (uint32_t v = tid; v < kChainTail / 16; v += kChainThreads) reinterpret_cast<uint4*>(prev)[v] = __ldcg(w + v);
+          __syncthreads();
+        }
+        // 8 consecutive bytes per step: their origins are one 16-byte vector, their real bytes one 8-byte vector
+        constexpr int kVec = kChainTail / 8 / kChainThreads;   // 16 vectors per thread, all loads in flight at once
+        uint4 g[kVec];
+        uint2 v[kVec];
+        const uint4* go = reinterpret_cast<const uint4*>(origin + t0r);
+        const uint2* gv = reinterpret_cast<const uint2*>(dst + t0r);
+#pragma unroll
+        for (int q = 0; q < kVec; ++q) {
+          g[q] = __ldcg(go + tid + q * kChainThreads);
+          v[q] = __ldcg(gv + tid + q * kChainThreads);
+        }
+        uint8_t* mine = chain_smem + cur;
+#pragma unroll
+        for (int q = 0; q < kVec; ++q) {
+          const uint32_t gw[4] = {g[q].x, g[q].y, g[q].z, g[q].w};
+          uint32_t lo = v[q].x, hi = v[q].y;
+          if (gw[0] | gw[1] | gw[2] | gw[3]) {
+            uint32_t out[2] = {0u, 0u};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t ge = (gw[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+              const uint32_t real = ((e < 4 ? lo : hi) >> (8 * (e & 3))) & 0xffu;
+              const uint32_t byte = ge ? (uint32_t)prev[kChainTail - ge] : real;
+              out[e >> 2] |= byte << (8 * (e & 3));
+            }
+            lo = out[0];
+            hi = out[1];
+            reinterpret_cast<uint2*>(dst + t0r)[tid + q * kChainThreads] = make_uint2(lo, hi);
+          }
+          reinterpret_cast<uint2*>(mine)[tid + q * kChainThreads] = make_uint2(lo, hi);
+        }
+        __syncthreads();
+        cur ^= kChainTail;
+        have_prev = true;
+      } else {
+        // short or unaligned block (the last one of a frame): gathers through L2
+        const uint32_t tail = dsize < 65535u ? dsize : 65535u;
+        const unsigned long long t0 = doff + dsize - tail;
+        constexpr int kBatch = 16;
+        for (uint32_t base = tid; base < tail; base += kChainThreads * kBatch) {
+          uint32_t gg[kBatch];
+          uint8_t vv[kBatch];
+#pragma unroll
+          for (int q = 0; q < kBatch; ++q) {
+            const uint32_t i = base + kChainThreads * q;
+            gg[q] = i < tail ? (uint32_t)__ldcg(origin + t0 + i) : 0u;
+          }
+#pragma unroll
+          for (int q = 0; q < kBatch; ++q) vv[q] = gg[q] ? __ldcg(dst + doff - gg[q]) : (uint8_t)0;
+#pragma unroll
+          for (int q = 0; q < kBatch; ++q) {
+            const uint32_t i = base + kChainThreads * q;
+            if (gg[q]) dst[t0 + i] = vv[q];
+          }
+        }
+        __syncthreads();
+        have_prev = false;
       }
     }
-    __syncthreads();
+    link = link_n;
+    dsize = dsize_n;
+    doff = doff_n;
   }
 }
 
@@ -1273,7 +1350,8 @@ int k_lz4_decode_linked(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, ui
   const DecTables T = dec_tables(workspace, dst_bytes, nullptr);
   uint16_t* org = static_cast<uint16_t*>(origins);
   lz4_decode_deferred_kernel<<<kNumSMs * 8, 256, 0, st>>>(src, dst, org, ctl, T);
-  lz4_resolve_chain_kernel<<<1, 1024, 0, st>>>(dst, org, ctl, T);
+  SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_resolve_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem));
+  lz4_resolve_chain_kernel<<<1, kChainThreads, kChainSmem, st>>>(dst, org, ctl, T);
   lz4_resolve_rest_kernel<<<kNumSMs * 8, 256, 0, st>>>(dst, org, ctl, T);
   SQYB_COUNT_LAUNCH(3);
   return (int)cudaGetLastError();
