@@ -1103,6 +1103,16 @@ __global__ void __launch_bounds__(256) lz4_decode_deferred_kernel(const uint8_t*
         for (uint32_t k = lane; k < csize; k += 32) { d[k] = __ldg(s + k); o[k] = 0; }
     } else {
       uint32_t ip = 0, op = 0;
+      // The last 32 output symbols (byte | origin << 8) stay in registers, lane l holding position op - 32 + l: a match with
+      // an offset of at most 32 — runs and short periods, most of what bit planes consist of — takes its pattern from
+      // there with one shuffle per 32 bytes and never waits for an L2 round trip. In front of the block: origins 32..1.
+      uint32_t tail = (uint32_t)(32 - lane) << 8;
+      auto push = [&](uint32_t L, uint32_t last) {   // L symbols were written at op; `last` = the last one this lane wrote
+        // every one of the final 32 positions is the LAST write of its lane, (L + lane) mod 32; older ones slide down
+        const uint32_t a = __shfl_sync(0xffffffffu, last, (L + lane) & 31);
+        const uint32_t b = __shfl_sync(0xffffffffu, tail, (L + lane) & 31);
+        tail = ((uint64_t)L + lane >= 32u) ? a : b;
+      };
       while (ip < csize && !err) {
         const uint32_t token = __ldg(s + ip);
         ip++;
@@ -1118,9 +1128,17 @@ __global__ void __launch_bounds__(256) lz4_decode_deferred_kernel(const uint8_t*
         }
         if (err) break;
         if ((unsigned long long)ip + lit > csize || (unsigned long long)op + lit > dsize) { err = kErrBadBlock; break; }
-        for (uint32_t k = lane; k < lit; k += 32) { d[op + k] = __ldg(s + ip + k); o[op + k] = 0; }
-        ip += lit;
-        op += lit;
+        if (lit) {
+          uint32_t last = 0;
+          for (uint32_t k = lane; k < lit; k += 32) {
+            last = __ldg(s + ip + k);
+            d[op + k] = (uint8_t)last;
+            o[op + k] = 0;
+          }
+          push(lit, last);
+          ip += lit;
+          op += lit;
+        }
         if (ip >= csize) break;            // the last sequence has literals only
         if (ip + 2u > csize) { err = kErrBadBlock; break; }
         const uint32_t offset = __ldg(s + ip) | (__ldg(s + ip + 1) << 8);
@@ -1139,27 +1157,46 @@ __global__ void __launch_bounds__(256) lz4_decode_deferred_kernel(const uint8_t*
         mlen += 4u;
         if (offset == 0u || (unsigned long long)op + mlen > dsize) { err = kErrBadBlock; break; }
         if (offset > op && (unsigned long long)(offset - op) > before) { err = kErrBadBlock; break; }
-        __syncwarp();                      // the literals (and everything before them) are visible to every lane
-        const long long base = (long long)op - (long long)offset;   // start of the pattern, may lie in front of the block
-        const bool wraps = offset < mlen, pow2 = (offset & (offset - 1u)) == 0u;
-        for (uint32_t k = lane; k < mlen; k += 32) {
-          uint32_t j = k;
-          if (wraps) j = pow2 ? (k & (offset - 1u)) : (k % offset);
-          const long long sp = base + (long long)j;
-          uint8_t v = 0;
-          uint16_t g;
-          if (sp < 0) {
-            g = (uint16_t)(-sp);           // a byte of the window in front of the block: remember which one
-          } else {
-            v = __ldcg(d + sp);
-            g = __ldcg(o + sp);
+        uint32_t last = 0;
+        if (offset <= 32u) {
+          // pattern = the last `offset` symbols = tail lanes 32-offset .. 31; output k takes pattern[k mod offset]
+          uint32_t j = (uint32_t)lane % offset;
+          const uint32_t step = 32u % offset;
+          for (uint32_t kb = 0; kb < mlen; kb += 32) {   // (same trip count on every lane: the shuffle needs them all)
+            const uint32_t sym = __shfl_sync(0xffffffffu, tail, (32u - offset + j) & 31u);
+            const uint32_t k = kb + lane;
+            if (k < mlen) {
+              d[op + k] = (uint8_t)sym;
+              o[op + k] = (uint16_t)(sym >> 8);
+              last = sym;
+            }
+            j += step;
+            if (j >= offset) j -= offset;
           }
-          d[op + k] = v;
-          o[op + k] = g;
+        } else {
+          __syncwarp();                    // everything written so far is visible to every lane
+          const long long base = (long long)op - (long long)offset;   // start of the pattern, may lie in front of the block
+          const bool wraps = offset < mlen, pow2 = (offset & (offset - 1u)) == 0u;
+          for (uint32_t k = lane; k < mlen; k += 32) {
+            uint32_t j = k;
+            if (wraps) j = pow2 ? (k & (offset - 1u)) : (k % offset);
+            const long long sp = base + (long long)j;
+            uint32_t v = 0, g;
+            if (sp < 0) {
+              g = (uint32_t)(-sp);         // a byte of the window in front of the block: remember which one
+            } else {
+              v = __ldcg(d + sp);
+              g = __ldcg(o + sp);
+            }
+            d[op + k] = (uint8_t)v;
+            o[op + k] = (uint16_t)g;
+            last = v | (g << 8);
+          }
         }
+        push(mlen, last);
         op += mlen;
-        __syncwarp();
       }
+      __syncwarp();
       if (!err && (ip != csize || op != dsize)) err = kErrSizeMismatch;
     }
     if (err && lane == 0) atomicMax(&ctl->error, err);
