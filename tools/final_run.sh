@@ -9,3 +9,6 @@ bash tools/profile_bench.sh cfg2 > gpurun_out/f1/profile.log 2>&1; tail -n 2 gpu
 timeout 600 python tools/bench_pageable.py > gpurun_out/f1/pageable.log 2>&1; tail -n 5 gpurun_out/f1/pageable.log
 timeout 600 python tools/bench_cfg5_batch.py 32 > gpurun_out/f1/cfg5_batch.log 2>&1; tail -n 1 gpurun_out/f1/cfg5_batch.log
 timeout 900 python tools/bench_cfg4_batch.py 256x2048x2048 8 > gpurun_out/f1/cfg4_batch.log 2>&1; tail -n 1 gpurun_out/f1/cfg4_batch.log
+timeout 900 python tools/bench_cfg4_batch.py 128x2048x2048 8 serial > gpurun_out/f1/cfg4_batch_serial.log 2>&1; tail -n 1 gpurun_out/f1/cfg4_batch_serial.log
+timeout 900 python tools/bench_cfg4.py 256x2048x2048 > gpurun_out/f1/cfg4_single.log 2>&1; tail -n 2 gpurun_out/f1/cfg4_single.log
+timeout 600 python tools/bench_bitshuffle.py > gpurun_out/f1/bitshuffle.log 2>&1; tail -n 7 gpurun_out/f1/bitshuffle.log
