@@ -36,7 +36,6 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kSub = kB / kWarps;        // 1 KiB sub-block per warp: matches never cross it
 constexpr int kSegs = kB / 32;           // 32-byte segments, one per thread
 constexpr int kPad = 256;
-constexpr uint32_t kNone = 0xFFFFu;
 constexpr int kHashLog = 12;
 constexpr int kInf = 0x7FFFFFFF;
 constexpr int kEarlyRounds = 8;          // early-store test after the hash rounds of the first 4 KiB ...
@@ -78,43 +77,6 @@ __device__ __forceinline__ int put_ext(uint8_t* p, int v) {
   while (r >= 255) { p[k++] = 255; r -= 255; }
   p[k++] = (uint8_t)r;
   return k;
-}
-
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-constexpr unsigned long long kFlagAgg = 1ull << 62;
-constexpr unsigned long long kFlagPre = 2ull << 62;
-constexpr unsigned long long kValMask = (1ull << 62) - 1;
-
-// coalesced copy of nbytes from shared memory (word array, arbitrary byte offset 0) to an arbitrarily
-// aligned global address
-__device__ __forceinline__ void store_bytes(uint8_t* __restrict__ g, const uint32_t* __restrict__ sw, int nbytes, int tid) {
-  const uint8_t* sb = reinterpret_cast<const uint8_t*>(sw);
-  int head = (int)((16 - ((uintptr_t)g & 15)) & 15);
-  if (head > nbytes) head = nbytes;
-  if (tid < head) g[tid] = sb[tid];
-  const int body = (nbytes - head) >> 4;
-  uint4* g4 = reinterpret_cast<uint4*>(g + head);
-  for (int v = tid; v < body; v += kThreads) {
-    const int so = head + (v << 4);
-    const int w = so >> 2, sh = (so & 3) * 8;
-    const uint32_t x0 = sw[w], x1 = sw[w + 1], x2 = sw[w + 2], x3 = sw[w + 3], x4 = sw[w + 4];
-    uint4 val;
-    val.x = __funnelshift_r(x0, x1, sh);
-    val.y = __funnelshift_r(x1, x2, sh);
-    val.z = __funnelshift_r(x2, x3, sh);
-    val.w = __funnelshift_r(x3, x4, sh);
-    g4[v] = val;
-  }
-  const int done = head + (body << 4);
-  if (tid < nbytes - done) g[done + tid] = sb[done + tid];
 }
 
 // The general path of a block (phases A0..D on the bytes in S.data), kept out of line: the closed-form path of all-equal
