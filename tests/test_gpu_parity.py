@@ -121,6 +121,35 @@ def test_histogram(sq, cuda, port, n, kind):
     assert np.array_equal(hist.cpu().numpy().view(np.uint32), port.histogram(a))
 
 
+HIST_KINDS = {
+    # (bins below 49152 are CTA-private shared-memory atomics, the rest global atomics: quantise.cu)
+    "camera": lambda rng, n: np.clip(rng.normal(100, 3, n), 0, 65535),
+    "one_value": lambda rng, n: np.full(n, 4242),
+    "zero_mode": lambda rng, n: np.abs(rng.normal(0, 4, n)),
+    "two_modes": lambda rng, n: np.where(rng.random(n) < 0.5, rng.normal(300, 2, n), rng.normal(9000, 2, n)),
+    "window_edges": lambda rng, n: 1000 + rng.integers(-40, 40, n),              # wider than the window on both sides
+    "private_bin_limit": lambda rng, n: 49152 + rng.integers(-20, 20, n),        # mode at the edge of the CTA-private bins
+    "above_private_bins": lambda rng, n: 60000 + rng.integers(-5, 5, n),         # global atomics only
+    "drifting": lambda rng, n: np.linspace(50, 3000, n) + rng.normal(0, 2, n),   # the mode of the first voxels is not the stack's
+    "wide": lambda rng, n: rng.exponential(400, n) + 100,
+}
+
+
+@pytest.mark.parametrize("kind", list(HIST_KINDS))
+def test_histogram_distributions(sq, cuda, port, kind):
+    """exact counts whatever the distribution: one value, modes at both ends of the private bins, values above them, drift"""
+    n = (1 << 24) + 11
+    rng = np.random.default_rng(len(kind))
+    a = np.clip(np.rint(HIST_KINDS[kind](rng, n)), 0, 65535).astype(np.uint16)
+    hist = cuda.zeros(65536, dtype=cuda.int32, device="cuda")
+    d = dev(cuda, a)
+    sq.histogram_device(d, hist)
+    sq.histogram_device(d[5: n - 3], hist)                                        # unaligned view, accumulating
+    cuda.cuda.synchronize()
+    want = port.histogram(a).astype(np.uint64) + port.histogram(a[5: n - 3])
+    assert np.array_equal(hist.cpu().numpy().view(np.uint32), want.astype(np.uint32))
+
+
 def test_histogram_unaligned_and_accumulating(sq, cuda, port):
     a = np.random.default_rng(0).integers(0, 3000, size=(1 << 21) + 5, dtype=np.uint16)
     d = dev(cuda, a)
