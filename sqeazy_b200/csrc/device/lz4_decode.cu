@@ -1199,7 +1199,13 @@ __global__ void __launch_bounds__(256) lz4_decode_deferred_kernel(const uint8_t*
       __syncwarp();
       if (!err && (ip != csize || op != dsize)) err = kErrSizeMismatch;
     }
-    if (err && lane == 0) atomicMax(&ctl->error, err);
+    // publish the block (the chain walk runs beside this kernel and picks the blocks up in order)
+    __syncwarp();
+    if (lane == 0) {
+      if (err) atomicMax(&ctl->error, err);
+      __threadfence();
+      atomicExch(T.done + b, 1u);
+    }
   }
 }
 
@@ -1210,7 +1216,8 @@ constexpr size_t kChainSmem = 2 * (size_t)kChainTail;
 __global__ void __launch_bounds__(kChainThreads) lz4_resolve_chain_kernel(uint8_t* __restrict__ dst, uint16_t* __restrict__ origin,
                                                                           const DecCtl* ctl, DecTables T) {
   extern __shared__ __align__(16) unsigned char chain_smem[];
-  if (ctl->error || !ctl->deferred) return;
+  __shared__ uint32_t sh_abort;
+  if (!ctl->deferred) return;
   const uint32_t nblocks = ctl->nblocks;
   const uint32_t tid = threadIdx.x;
   // The window in front of the current block = the resolved tail of its predecessor lives in shared memory (two 64 KiB
@@ -1224,6 +1231,21 @@ __global__ void __launch_bounds__(kChainThreads) lz4_resolve_chain_kernel(uint8_
     const uint32_t nb = b + 1 < nblocks ? b + 1 : b;
     const uint32_t link_n = T.link[nb], dsize_n = T.dsize[nb];
     const unsigned long long doff_n = T.dst_off[nb];
+    if (link != kNoLink) {
+      // This kernel runs BESIDE pass 1 (second stream): wait until the block has been decoded. Pass 1 publishes every
+      // block it takes, also a broken one, and the blocks in front of this one were waited for in earlier iterations.
+      if (tid == 0) {
+        uint32_t abort = 0;
+        while (atomicAdd(T.done + b, 0u) == 0u) {
+          if (atomicAdd(const_cast<uint32_t*>(&ctl->error), 0u) != 0u) { abort = 1; break; }
+          __nanosleep(200);
+        }
+        __threadfence();
+        sh_abort = abort;
+      }
+      __syncthreads();
+      if (sh_abort) return;
+    }
     if (link == kNoLink || link == kLinkHead) {              // (the same for every thread) heads hold real bytes only
       have_prev = false;
     } else {
@@ -1386,12 +1408,34 @@ int k_lz4_decode_linked(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, ui
   DecCtl* ctl = reinterpret_cast<DecCtl*>(workspace);
   const DecTables T = dec_tables(workspace, dst_bytes, nullptr);
   uint16_t* org = static_cast<uint16_t*>(origins);
-  lz4_decode_deferred_kernel<<<kNumSMs * 8, 256, 0, st>>>(src, dst, org, ctl, T);
-  SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_resolve_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem));
-  lz4_resolve_chain_kernel<<<1, kChainThreads, kChainSmem, st>>>(dst, org, ctl, T);
-  lz4_resolve_rest_kernel<<<kNumSMs * 8, 256, 0, st>>>(dst, org, ctl, T);
-  SQYB_COUNT_LAUNCH(3);
-  return (int)cudaGetLastError();
+  // The chain walk starts together with pass 1 on a stream of its own and follows it block by block (T.done): the blocks
+  // come in plane order, the all-zero planes in front are decoded within a millisecond, and only the tail of the walk is
+  // left when the last noisy block of pass 1 is through.
+  cudaStream_t aux = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  SQYB_CUDA_OK(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+  cudaError_t e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lz4_resolve_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem);
+  if (e == cudaSuccess) e = cudaEventRecord(fork, st);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(aux, fork, 0);
+  if (e == cudaSuccess) {
+    // pass 1 is launched first: where kernels of different streams are serialised (profilers), the walk then simply finds
+    // every block published; side by side, it gets an SM as soon as the first CTAs of pass 1 (the all-zero planes) retire
+    lz4_decode_deferred_kernel<<<kNumSMs * 8, 256, 0, st>>>(src, dst, org, ctl, T);
+    lz4_resolve_chain_kernel<<<1, kChainThreads, kChainSmem, aux>>>(dst, org, ctl, T);
+    e = cudaEventRecord(join, aux);
+  }
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, join, 0);
+  if (e == cudaSuccess) {
+    lz4_resolve_rest_kernel<<<kNumSMs * 8, 256, 0, st>>>(dst, org, ctl, T);
+    SQYB_COUNT_LAUNCH(3);
+    e = cudaGetLastError();
+  }
+  if (fork) cudaEventDestroy(fork);     // (released when the work that uses them has finished)
+  if (join) cudaEventDestroy(join);
+  cudaStreamDestroy(aux);
+  return (int)e;
 }
 
 int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, int measure_all,

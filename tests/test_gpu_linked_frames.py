@@ -101,3 +101,16 @@ def test_corrupt_linked_stream_fails_cleanly(sq, cuda, ref, route):
         except sq.SqeazyError:
             pass
         assert bool((out[a.size:] == 0x11).all())      # whatever happened, nothing was written behind the buffer
+
+
+def test_linked_frames_into_unaligned_buffers(sq, cuda, ref, route):
+    """destination at odd addresses: the chain walk takes its element-wise route (no 16-byte vectors), same bytes"""
+    rng = np.random.default_rng(9)
+    a = _mixed_content(rng, 2_000_003)
+    payload = dev(cuda, ref.lz4_encode(a, nthreads=1))
+    for off in (1, 3, 8):
+        out = cuda.full((a.size + 64,), 0x33, dtype=cuda.uint8, device="cuda")
+        assert sq.lz4_decode_device(payload, out[off: off + a.size]) == a.size
+        h = out.cpu().numpy()
+        assert np.array_equal(h[off: off + a.size], a)
+        assert np.all(h[:off] == 0x33) and np.all(h[off + a.size:] == 0x33)
