@@ -38,11 +38,13 @@ int SQY_Version_Triple(int* version);
 
 /* reference: sqeazy.h:143-166, sqeazy.cpp:108-142
  * pipeline: NUL-terminated, e.g. "rmestbkrd->bitswap1->lz4"; src: shape-product uint16 voxels (C order);
- * dst: at least SQY_Pipeline_Max_Compressed_Length_UI16 bytes; *dstlength (out only) = blob bytes. */
+ * dst: at least SQY_Pipeline_Max_Compressed_Length_UI16 bytes; *dstlength (out only) = blob bytes.
+ * nthreads: host threads, <= 0 or more than the machine has = all cores (sqeazy_algorithms.hpp:14-22). Here they stage
+ * pageable src/dst buffers for the PCIe hop (page-locked buffers need none); the kernels have no thread knob. */
 int SQY_PipelineEncode_UI16(const char* pipeline, const char* src, long* shape, unsigned shape_size, char* dst,
                             long* dstlength, int nthreads);
 
-/* reference: sqeazy.cpp:72-106 (dypeline<uint8_t>) — uint8 voxels; stages with uint8 kernels: bitswap1|2|4,
+/* reference: sqeazy.cpp:72-106 (dypeline<uint8_t>) — uint8 voxels; stages with uint8 kernels: bitswap1|2|4, bitshuffle,
  * remove_background(threshold=N) -> lz4 | pass_through [-> lz4]; any other stage name returns 1 */
 int SQY_PipelineEncode_UI8(const char* pipeline, const char* src, long* shape, unsigned shape_size, char* dst,
                            long* dstlength, int nthreads);

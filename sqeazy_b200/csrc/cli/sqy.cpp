@@ -41,7 +41,7 @@ struct OptSpec { const char* longname; char shortname; bool takes_value; const c
 const OptSpec kGeneral[] = {
     {"help", 'h', false, "produce help message"},
     {"verbose", 'v', false, "enable verbose output"},
-    {"nthreads", 'n', true, "number of threads to use (accepted for compatibility: the GPU build has no thread knob)"},
+    {"nthreads", 'n', true, "number of host threads to use (they stage the stack for the PCIe hop; <= 0: all cores)"},
 };
 const OptSpec kCompress[] = {
     {"pipeline", 'p', true, "compression pipeline to be used (default bitswap1->lz4)"},
