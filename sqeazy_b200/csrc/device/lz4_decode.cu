@@ -174,46 +174,63 @@ __global__ void __launch_bounds__(kDirThreads) lz4_directory_kernel(const uint8_
             }
           }
         } else if (magic == kLz4FrameMagic) {
-          // ---- foreign frame: serial walk of the block headers ----
-          if (pos + 7 > src_bytes) sh_err = kErrTruncated;
-          else {
-            const uint32_t flg = src[pos + 4], bd = src[pos + 5];
+          // ---- foreign frames: serial walk of the block headers. Consecutive foreign frames (the reference's multi-threaded
+          // mode writes one per 256 KiB chunk: 8192 for a 2 GiB stack) are walked without leaving this thread — a round of
+          // CTA barriers per frame cost more than the walk itself.
+          unsigned long long fpos = pos;
+          uint32_t nb = sh_nb;
+          uint32_t pending = kNoLink, pending_max = 0;   // single-block frame whose size is still to be settled
+          while (sh_err == 0) {
+            if (fpos + 7 > src_bytes) { sh_err = kErrTruncated; break; }
+            // another frame follows the pending single-block frame: a chunked writer fills every chunk but the last, so
+            // its block is taken as full instead of being measured by a token walk (a wrong guess shows up as a size
+            // mismatch and the caller retries with measure_all)
+            if (pending != kNoLink) {
+              T.dsize[pending] = pending_max;
+              sh_need--;
+              pending = kNoLink;
+            }
+            const uint32_t flg = src[fpos + 4], bd = src[fpos + 5];
             const bool indep = (flg >> 5) & 1, bchk = (flg >> 4) & 1, csz = (flg >> 3) & 1, cchk = (flg >> 2) & 1, dict = flg & 1;
             const uint32_t bsid = (bd >> 4) & 7;
-            if ((flg >> 6) != 1 || bsid < 4) sh_err = kErrBadHeader;
-            else {
-              const uint32_t maxblock = 1u << (8 + 2 * bsid);
-              unsigned long long p = pos + 7 + (csz ? 8 : 0) + (dict ? 4 : 0);
-              uint32_t nb = sh_nb;
-              const uint32_t first_of_frame = nb;
-              while (true) {
-                if (p + 4 > src_bytes) { sh_err = kErrTruncated; break; }
-                const uint32_t word = rd32(src + p);
-                if (word == 0) { p += 4; break; }
-                const uint32_t sz = word & 0x7FFFFFFFu;
-                if (sz > maxblock || p + 4 + sz > src_bytes) { sh_err = kErrBadBlock; break; }
-                if (nb >= capacity) { sh_err = kErrTooManyBlocks; break; }
-                T.src_off[nb] = p + 4;
-                T.word[nb] = word;
-                // non-final blocks of liblz4 frames are full; measure_all drops that assumption
-                T.dsize[nb] = (word & kLz4StoredFlag) ? sz : (measure_all ? 0u : maxblock);
-                if (measure_all && !(word & kLz4StoredFlag)) sh_need++;
-                T.link[nb] = indep ? kNoLink : (nb > first_of_frame ? nb - 1 : kLinkHead);
-                if (!indep && nb > first_of_frame) sh_linked++;
-                nb++;
-                p += 4ull + sz + (bchk ? 4 : 0);
-              }
-              if (sh_err == 0) {
-                if (cchk) p += 4;
-                // the last block of a frame may be short: its size has to be measured
-                if (!measure_all && nb > first_of_frame && !(T.word[nb - 1] & kLz4StoredFlag)) { T.dsize[nb - 1] = 0; sh_need++; }
-                // a "linked" frame of a single block (the reference's multi-threaded mode: one frame per chunk) links nothing
-                if (!indep && nb == first_of_frame + 1) T.link[first_of_frame] = kNoLink;
-                sh_nb = nb;
-                sh_pos = p;
-                sh_mode = 2;
-              }
+            if ((flg >> 6) != 1 || bsid < 4) { sh_err = kErrBadHeader; break; }
+            const uint32_t maxblock = 1u << (8 + 2 * bsid);
+            unsigned long long p = fpos + 7 + (csz ? 8 : 0) + (dict ? 4 : 0);
+            const uint32_t first_of_frame = nb;
+            while (true) {
+              if (p + 4 > src_bytes) { sh_err = kErrTruncated; break; }
+              const uint32_t word = rd32(src + p);
+              if (word == 0) { p += 4; break; }
+              const uint32_t sz = word & 0x7FFFFFFFu;
+              if (sz > maxblock || p + 4 + sz > src_bytes) { sh_err = kErrBadBlock; break; }
+              if (nb >= capacity) { sh_err = kErrTooManyBlocks; break; }
+              T.src_off[nb] = p + 4;
+              T.word[nb] = word;
+              // non-final blocks of liblz4 frames are full; measure_all drops that assumption
+              T.dsize[nb] = (word & kLz4StoredFlag) ? sz : (measure_all ? 0u : maxblock);
+              if (measure_all && !(word & kLz4StoredFlag)) sh_need++;
+              T.link[nb] = indep ? kNoLink : (nb > first_of_frame ? nb - 1 : kLinkHead);
+              if (!indep && nb > first_of_frame) sh_linked++;
+              nb++;
+              p += 4ull + sz + (bchk ? 4 : 0);
             }
+            if (sh_err) break;
+            if (cchk) p += 4;
+            // the last block of a frame may be short: its size has to be measured
+            if (!measure_all && nb > first_of_frame && !(T.word[nb - 1] & kLz4StoredFlag)) {
+              T.dsize[nb - 1] = 0;
+              sh_need++;
+              if (nb == first_of_frame + 1) { pending = nb - 1; pending_max = maxblock; }
+            }
+            // a "linked" frame of a single block (the reference's multi-threaded mode: one frame per chunk) links nothing
+            if (!indep && nb == first_of_frame + 1) T.link[first_of_frame] = kNoLink;
+            fpos = p;
+            if (fpos + 4 > src_bytes || rd32(src + fpos) != kLz4FrameMagic) break;   // something else follows: back to the classifier
+          }
+          if (sh_err == 0) {
+            sh_nb = nb;
+            sh_pos = fpos;
+            sh_mode = 2;
           }
         } else {
           sh_err = kErrBadMagic;
