@@ -1,7 +1,12 @@
 /* CPU model of the GPU LZ4 encoder's match finding + greedy parse, for tuning the compression ratio
  * without a GPU (development tool, not shipped, not an oracle). Computes encoded sizes only.
  * build: gcc -O2 -o /tmp/lz4_model tools/lz4_model.c
- * usage: lz4_model file block_bytes round cut hashlog mode
+ * usage: lz4_model file block_bytes round cut hashlog mode [win minlen early_bytes early_div]
+ *   mode 72 (= 64 | 8) is the shipped policy: short offsets 1,2,4,3 first, hash rounds only for positions without one, minimum match 5
+ *   mode bit 4096 + win/minlen: (rejected) no lookup when a short-offset match of >= minlen bytes starts within `win` positions
+ *   early_bytes/early_div: the early-store policy — a block with fewer than early_bytes/early_div candidates (>= 5 bytes) in
+ *   its first early_bytes bytes is stored; MODEL_DUMP=1 prints per block "BLK <candidates in the prefix> <short-offset candidates
+ *   in the whole block> <encoded size>", which is where kEarlyMin = 128 per 4 KiB (lz4_encode.cu) comes from
  */
 #include <stdint.h>
 #include <stdio.h>
