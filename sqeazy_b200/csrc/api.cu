@@ -419,6 +419,64 @@ int lz4_decode_checked(Arena& A, const uint8_t* src, uint64_t nbytes, uint8_t* d
   return 1;
 }
 
+// Host decode of `[filters ->] bitswapN -> lz4` blobs of this library, >= 512 MiB: the LZ4 blocks are decoded slab by slab (the
+// blocks of all 16/N bit planes that make up a z-slab: one block-set launch), each slab is transposed back and leaves for the
+// host while the next one is decoded; only the first slab's kernels run in front of the bus. Returns -1 when the blob is not
+// of that kind (the caller takes the general route), 0 on success, an error code otherwise.
+int decode_streamed(Arena& A, const Pipeline& pl, const uint8_t* d_payload, uint64_t payload_bytes, uint16_t* d_dst, uint64_t N,
+                    cudaStream_t st, HostSink* host) {
+  const uint64_t raw_bytes = 2 * N;
+  if (pl.elem != 2 || !pl.has_sink || pl.sink.kind != StageKind::Lz4 || pl.has_tail || g_timing.load()) return -1;
+  if (raw_bytes < kStreamMinBytes || N % kStreamGrainVoxels) return -1;
+  int w = 0, nswaps = 0;
+  for (const Stage& s : pl.head) {
+    if (s.kind == StageKind::Bitswap) { w = s.w; nswaps++; }
+    else if (s.kind == StageKind::Bitshuffle) return -1;
+  }
+  if (nswaps != 1) return -1;
+  const int P = 16 / w;
+  void *ws = nullptr, *planes_v = nullptr;
+  if (A.get(kSlotWs, k_lz4_decode_workspace_bytes(raw_bytes), &ws) || A.get(kSlotA, raw_bytes, &planes_v)) return 1;
+  uint8_t* planes = static_cast<uint8_t*>(planes_v);
+  if (((((uintptr_t)planes) | ((uintptr_t)d_dst)) & 31) != 0) return -1;
+  CKK(k_lz4_decode_tables(d_payload, payload_bytes, raw_bytes, ws, 0, 0, st));
+  uint32_t err = 0, own = 0, nblk = 0, bb = 0;
+  if (k_lz4_decode_peek(ws, &err, &own, &nblk, &bb, st)) return 1;
+  if (err || !own || bb != kLz4BlockBytes || (uint64_t)nblk * bb != raw_bytes) return -1;
+  cudaStream_t cs = nullptr;
+  if (copy_stream(&cs)) return 1;
+  // at most 32 slabs (one work counter each)
+  uint64_t slab = kStreamSlabBytes / 2;
+  while ((N + slab - 1) / slab > 32) slab *= 2;
+  const uint32_t blocks_per_plane = (uint32_t)(raw_bytes / P / kLz4BlockBytes);
+  EventList events;
+  uint32_t slot = 0;
+  for (uint64_t first = 0; first < N; first += slab, ++slot) {
+    const uint64_t count = std::min(slab, N - first);
+    CKK(k_lz4_decode_run(d_payload, payload_bytes, planes, raw_bytes, ws, (uint32_t)(2 * first / P / kLz4BlockBytes),
+                         (uint32_t)(2 * count / P / kLz4BlockBytes), (uint32_t)P, blocks_per_plane, slot, st));
+    if (k_bitswap_decode_range(w, reinterpret_cast<const uint16_t*>(planes), d_dst, N, first, count, st)) return 101;
+    cudaEvent_t e = nullptr;
+    if (events.next(&e)) return 1;
+    CK(cudaEventRecord(e, st));
+  }
+  size_t i = 0;
+  for (uint64_t first = 0; first < N; first += slab, ++i) {
+    CK(cudaStreamWaitEvent(cs, events.ev[i], 0));
+    CK((cudaError_t)staged_d2h(host->dst + 2 * first, d_dst + first, 2 * std::min(slab, N - first), host->nthreads, cs));
+  }
+  uint64_t total = 0;
+  uint32_t none = 0;
+  if (k_lz4_decode_status(ws, &err, &total, &none, st)) return 1;
+  CK(cudaStreamSynchronize(cs));
+  if (err || total != raw_bytes) {
+    std::fprintf(stderr, "[sqeazy_b200] lz4 decode failed (code %u)\n", err);
+    return 11;
+  }
+  host->done = true;
+  return 0;
+}
+
 int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const uint8_t* d_payload, uint64_t payload_bytes,
                        void* d_dst_any, uint64_t dst_cap, cudaStream_t st, HostSink* host = nullptr) {
   const uint64_t N = shape_product(hdr.shape);
@@ -427,6 +485,10 @@ int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const ui
   uint16_t* d_dst = static_cast<uint16_t*>(d_dst_any);
   if (dst_cap < raw_bytes) return 1;
   if (N == 0) return 0;
+  if (host) {
+    const int rc = decode_streamed(A, pl, d_payload, payload_bytes, d_dst, N, st, host);
+    if (rc >= 0) return rc;
+  }
 
   // data-moving head stages in decode order (reverse); the background filters decode as identity
   std::vector<int> swaps;                 // bitswap: bits per plane; bitshuffle: -1 - block_size

@@ -63,6 +63,13 @@ size_t k_lz4_decode_workspace_bytes(uint64_t dst_bytes);
 // in the status and provided the origin buffer.
 int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, int measure_all,
                  int allow_deferred, cudaStream_t st);
+// k_lz4_decode in two steps, for callers that want the blocks of one z-slab at a time (the host entry points ship a slab while
+// the next one is decoded): the block table, then any number of block-set launches over it (count == 0: the whole stream).
+int k_lz4_decode_tables(const uint8_t* src, uint64_t src_bytes, uint64_t dst_bytes, void* workspace, int measure_all, int allow_deferred,
+                        cudaStream_t st);
+int k_lz4_decode_run(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, uint32_t first,
+                     uint32_t count, uint32_t nsets, uint32_t set_stride, uint32_t slot, cudaStream_t st);
+int k_lz4_decode_peek(void* workspace, uint32_t* error, uint32_t* own_frame, uint32_t* nblocks, uint32_t* block_bytes, cudaStream_t st);
 size_t k_lz4_decode_linked_workspace_bytes(uint64_t dst_bytes);
 int k_lz4_decode_linked(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, void* origins,
                         cudaStream_t st);

@@ -61,7 +61,9 @@ struct DecCtl {          // lives at the start of the workspace
   uint32_t nlinked;      // blocks that belong to block-linked frames
   uint32_t deferred;     // 1: those blocks are left to lz4_decode_deferred_kernel + the two resolve passes (k_lz4_decode_linked)
   uint32_t ticket_deferred, pad1;
+  uint32_t set_ticket[32];   // work counters of the block-set launches (k_lz4_decode_run with count != 0)
 };
+static_assert(sizeof(DecCtl) <= 256, "DecCtl lives in the first 256 bytes of the workspace");
 
 struct DecTables {
   unsigned long long* src_off;   // offset of block data in the stream
@@ -998,7 +1000,8 @@ __global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSM) lz4_decode_lanes
 // classification pass in front of this kernel cost 0.63 ms per 4 GiB.
 __global__ void __launch_bounds__(kWinWarps * 32, 5) lz4_decode_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
                                                                         uint8_t* __restrict__ dst, DecCtl* ctl, DecTables T,
-                                                                        int classified) {
+                                                                        int classified, uint32_t first, uint32_t count,
+                                                                        uint32_t nsets, uint32_t set_stride, uint32_t slot) {
   extern __shared__ __align__(16) unsigned char dsm[];
   if (ctl->error) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1006,11 +1009,20 @@ __global__ void __launch_bounds__(kWinWarps * 32, 5) lz4_decode_kernel(const uin
   uint8_t* ring8 = win + kWin;
   const uint32_t nblocks = ctl->nblocks;
   if (classified && ctl->nwarp == 0) return;
+  // count != 0: only `nsets` sets of `count` consecutive blocks, set j starting at first + j * set_stride (the blocks of all
+  // bit planes that make up one z-slab), with a work counter of their own
+  const uint32_t total = count ? count * nsets : nblocks;
+  uint32_t* ticket = count ? &ctl->set_ticket[slot & 31u] : &ctl->ticket_decode;
   while (true) {
     uint32_t b = 0;
-    if (lane == 0) b = atomicAdd(&ctl->ticket_decode, 1u);
+    if (lane == 0) b = atomicAdd(ticket, 1u);
     b = __shfl_sync(0xffffffffu, b, 0);
-    if (b >= nblocks) return;
+    if (b >= total) return;
+    if (count) {
+      const uint32_t j = b / count;
+      b = first + j * set_stride + (b - j * count);
+      if (b >= nblocks) continue;
+    }
     if (classified && T.kind[b] != kKindWarp) continue;
     const uint32_t word = T.word[b];
     const uint32_t csize = word & 0x7FFFFFFFu;
@@ -1455,8 +1467,8 @@ int k_lz4_decode_linked(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, ui
   return (int)e;
 }
 
-int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, int measure_all,
-                 int allow_deferred, cudaStream_t st) {
+int k_lz4_decode_tables(const uint8_t* src, uint64_t src_bytes, uint64_t dst_bytes, void* workspace, int measure_all,
+                        int allow_deferred, cudaStream_t st) {
   const size_t cap = k_lz4_decode_capacity(dst_bytes);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   DecCtl* ctl = reinterpret_cast<DecCtl*>(ws);
@@ -1479,7 +1491,18 @@ int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t 
   lz4_expand_kernel<<<tile_grid, 256, 0, st>>>(src, ctl, T, tile_sums, dst_bytes);
   lz4_sizes_kernel<<<kNumSMs * 4, kDecThreads, 0, st>>>(src, ctl, T);
   lz4_offsets_kernel<<<1, kDirThreads, 0, st>>>(ctl, T, dst_bytes);
-  const bool lanes = lane_max_bytes() > 0;
+  SQYB_COUNT_LAUNCH(5);
+  return (int)cudaGetLastError();
+}
+
+// the block decoders over the table k_lz4_decode_tables left in `workspace`: the whole stream (count == 0), or `nsets` sets of
+// `count` consecutive blocks, set j starting at block first + j * set_stride, with work counter `slot` (0..31, one per launch
+// in flight)
+int k_lz4_decode_run(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, uint32_t first,
+                     uint32_t count, uint32_t nsets, uint32_t set_stride, uint32_t slot, cudaStream_t st) {
+  DecCtl* ctl = reinterpret_cast<DecCtl*>(workspace);
+  const DecTables T = dec_tables(workspace, dst_bytes, nullptr);
+  const bool lanes = count == 0 && lane_max_bytes() > 0;
   if (lanes) {
     lz4_classify_kernel<<<kNumSMs * 8, 256, 0, st>>>(src, dst, ctl, T, lane_max_bytes());
     const size_t lane_smem = 32 * sizeof(uint32_t) * kLaneThreads;
@@ -1488,9 +1511,29 @@ int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t 
     SQYB_COUNT_LAUNCH(2);
   }
   const size_t win_smem = kWinWarps * kWinWarpSmem;
-  lz4_decode_kernel<<<kNumSMs * 5, kWinWarps * 32, win_smem, st>>>(src, src_bytes, dst, ctl, T, lanes ? 1 : 0);
-  SQYB_COUNT_LAUNCH(6);
+  lz4_decode_kernel<<<kNumSMs * 5, kWinWarps * 32, win_smem, st>>>(src, src_bytes, dst, ctl, T, lanes ? 1 : 0, first, count, nsets,
+                                                                    set_stride, slot);
+  SQYB_COUNT_LAUNCH(1);
   return (int)cudaGetLastError();
+}
+
+int k_lz4_decode(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, int measure_all,
+                 int allow_deferred, cudaStream_t st) {
+  if (int e = k_lz4_decode_tables(src, src_bytes, dst_bytes, workspace, measure_all, allow_deferred, st)) return e;
+  return k_lz4_decode_run(src, src_bytes, dst, dst_bytes, workspace, 0, 0, 0, 0, 0, st);
+}
+
+// what kind of stream the tables describe (synchronises the stream): one indexed frame of this library = regular geometry
+int k_lz4_decode_peek(void* workspace, uint32_t* error, uint32_t* own_frame, uint32_t* nblocks, uint32_t* block_bytes,
+                      cudaStream_t st) {
+  DecCtl h;
+  SQYB_CUDA_OK(cudaMemcpyAsync(&h, workspace, sizeof(DecCtl), cudaMemcpyDeviceToHost, st));
+  SQYB_CUDA_OK(cudaStreamSynchronize(st));
+  *error = h.error;
+  *own_frame = h.fast;
+  *nblocks = h.fast ? h.fast_nblk : h.nblocks;
+  *block_bytes = h.fast ? h.fast_bb : 0u;
+  return 0;
 }
 
 // copies {error, total_decoded} back (synchronises the stream)
