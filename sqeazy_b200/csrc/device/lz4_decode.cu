@@ -1265,8 +1265,18 @@ __global__ void __launch_bounds__(kChainThreads) lz4_resolve_chain_kernel(uint8_
       // block it takes, also a broken one, and the blocks in front of this one were waited for in earlier iterations.
       if (tid == 0) {
         uint32_t abort = 0;
+        unsigned long long t_start = 0;
         while (atomicAdd(T.done + b, 0u) == 0u) {
           if (atomicAdd(const_cast<uint32_t*>(&ctl->error), 0u) != 0u) { abort = 1; break; }
+          // never spin for ever: ten seconds without the block (pass 1 was not started, or was killed) end the walk with an error
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t_start == 0) t_start = now;
+          if (now - t_start > 10000000000ull) {
+            atomicMax(const_cast<uint32_t*>(&ctl->error), (uint32_t)kErrBadBlock);
+            abort = 1;
+            break;
+          }
           __nanosleep(200);
         }
         __threadfence();
@@ -1452,8 +1462,12 @@ int k_lz4_decode_linked(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, ui
     // pass 1 is launched first: where kernels of different streams are serialised (profilers), the walk then simply finds
     // every block published; side by side, it gets an SM as soon as the first CTAs of pass 1 (the all-zero planes) retire
     lz4_decode_deferred_kernel<<<kNumSMs * 8, 256, 0, st>>>(src, dst, org, ctl, T);
-    lz4_resolve_chain_kernel<<<1, kChainThreads, kChainSmem, aux>>>(dst, org, ctl, T);
-    e = cudaEventRecord(join, aux);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) {              // (the walk waits for pass 1: it is only started when pass 1 was)
+      lz4_resolve_chain_kernel<<<1, kChainThreads, kChainSmem, aux>>>(dst, org, ctl, T);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(join, aux);
   }
   if (e == cudaSuccess) e = cudaStreamWaitEvent(st, join, 0);
   if (e == cudaSuccess) {
