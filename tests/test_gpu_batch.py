@@ -67,6 +67,25 @@ def test_decode_batch_of_reference_blobs(sq, cuda, ref):
         assert np.array_equal(host16(o), v)
 
 
+def test_decode_batch_of_linked_blobs_on_the_deferred_route(sq, cuda, ref):
+    """stacks of 12 linked 256 KiB blocks each: every lane of the batch runs the deferred-reference decoder (pass 1 and the
+    chain walk side by side on two streams of its own) at the same time as the others"""
+    name = "bitswap1(num_bits_per_plane=1)->lz4(accel=1,blocksize_kb=256,framestep_kb=256,n_chunks_of_input=0)"
+    shape = (24, 256, 256)
+    vols, blobs = [], []
+    for i in range(9):
+        vol = numpy_volume(shape, "scmos" if i % 2 else "ref", index=70 + i)
+        payload, _ = ref.pipeline_encode_stages(0, vol, 1)
+        h = orc.pack_header(vol.shape, name, payload.size, version="0.5.2", headref="4c45a9b")
+        vols.append(vol)
+        blobs.append(cuda.from_numpy(np.concatenate([np.frombuffer(h.encode(), dtype=np.uint8), payload])).cuda())
+    for _ in range(2):
+        outs = [cuda.full(shape, -1, dtype=cuda.int16, device="cuda") for _ in blobs]
+        sq.decode_batch_device(blobs, outs)
+        for v, o in zip(vols, outs):
+            assert np.array_equal(host16(o), v)
+
+
 def test_batch_reports_the_broken_stack(sq, cuda):
     shape = (4, 64, 128)
     vols = [numpy_volume(shape, "scmos", index=60 + i) for i in range(5)]
