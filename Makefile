@@ -8,7 +8,7 @@ CSRC      := sqeazy_b200/csrc
 OBJDIR    := build/obj
 LIB       := sqeazy_b200/libsqeazy.so
 
-CU_SRCS   := $(CSRC)/api.cu $(CSRC)/staging.cu $(CSRC)/device/bitswap.cu $(CSRC)/device/bitswap8.cu $(CSRC)/device/bitshuffle.cu $(CSRC)/device/quantise.cu $(CSRC)/device/lz4_encode.cu $(CSRC)/device/lz4_decode.cu
+CU_SRCS   := $(CSRC)/api.cu $(CSRC)/staging.cu $(CSRC)/device/bitswap.cu $(CSRC)/device/bitswap8.cu $(CSRC)/device/bitshuffle.cu $(CSRC)/device/diff.cu $(CSRC)/device/quantise.cu $(CSRC)/device/lz4_encode.cu $(CSRC)/device/lz4_decode.cu
 CPP_SRCS  := $(CSRC)/host/text.cpp $(CSRC)/host/numerics.cpp $(CSRC)/host/pipeline.cpp
 CU_OBJS   := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
 CPP_OBJS  := $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP_SRCS))
@@ -38,11 +38,16 @@ $(SQY): $(CSRC)/cli/sqy.cpp $(CSRC)/cli/tiff_min.hpp include/sqeazy.h $(LIB)
 	$(CXX) -O2 -std=c++17 -Wall -o $@ $(CSRC)/cli/sqy.cpp -Lsqeazy_b200 -lsqeazy -Wl,-rpath,'$$ORIGIN/..'
 
 # ---- test-only oracle: C restatement (always) and the compiled reference stages (when /root/reference exists)
-oracle: oracle/_build/libsqyoracle.so oracle_ref
+oracle: oracle/_build/libsqyoracle.so oracle/_build/libdiff_sim.so oracle_ref
 
 oracle/_build/libsqyoracle.so: oracle/sqy_oracle.c
 	@mkdir -p oracle/_build
 	gcc -O2 -std=c11 -fPIC -shared -ffp-contract=off -Wall -o $@ $<
+
+# CPU replay of the diff3x3x1 kernels' thread program (tests/test_diff_cpu.py)
+oracle/_build/libdiff_sim.so: tests/helpers/diff_sim.cpp $(CSRC)/device/diff_thread.h
+	@mkdir -p oracle/_build
+	g++ -O2 -std=c++17 -fPIC -shared -I$(CSRC)/device -o $@ $<
 
 oracle_ref:
 	@if [ -d $(REF) ]; then $(MAKE) oracle/_ref/libsqyref.so; else echo "no /root/reference: using prebuilt oracle/_ref if present"; fi

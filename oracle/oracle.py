@@ -124,6 +124,21 @@ class Port:
         self.lib.orc_rmestbkrd(_p(vol), _p(out), c_uint64(Z), c_uint64(Y), c_uint64(X), c_uint64(l2_bytes), ctypes.byref(t))
         return out, t.value
 
+    def diff_supported(self, shape) -> bool:
+        Z, Y, X = (int(v) for v in shape)
+        return bool(self.lib.orc_diff_supported(c_uint64(Z), c_uint64(Y), c_uint64(X)))
+
+    def diff(self, vol: np.ndarray, decode: bool = False) -> np.ndarray:
+        """diff3x3x1 (encoders/diff_scheme_impl.hpp:78-199), uint16 or uint8 by the array's dtype; ValueError for a refused shape"""
+        vol = np.ascontiguousarray(vol)
+        assert vol.dtype in (np.uint16, np.uint8) and vol.ndim == 3
+        Z, Y, X = vol.shape
+        out = np.empty_like(vol)
+        rc = self.lib.orc_diff(c_int(1 if decode else 0), _p(vol), _p(out), c_uint64(Z), c_uint64(Y), c_uint64(X), c_int(vol.itemsize))
+        if rc != 0:
+            raise ValueError(f"diff3x3x1: shape {vol.shape} not supported")
+        return out
+
     def quantiser_luts(self, hist: np.ndarray):
         hist = np.ascontiguousarray(hist, dtype=np.uint32)
         enc = np.zeros(65536, dtype=np.uint8)
@@ -238,6 +253,26 @@ class Ref:
         out = np.zeros_like(vol)
         assert self.lib.ref_rmestbkrd_encode(_p(vol), _p(out), c_long(Z), c_long(Y), c_long(X), c_int(nthreads)) == 0
         return out
+
+    def diff(self, vol, decode=False, nthreads=1):
+        """diff_scheme<uint16_t> / <uint8_t> of the reference (encode with nthreads, decode always serial)"""
+        vol = np.ascontiguousarray(vol)
+        assert vol.dtype in (np.uint16, np.uint8) and vol.ndim == 3
+        Z, Y, X = vol.shape
+        out = np.zeros_like(vol)
+        if vol.dtype == np.uint16:
+            rc = (self.lib.ref_diff_decode(_p(vol), _p(out), c_long(Z), c_long(Y), c_long(X)) if decode
+                  else self.lib.ref_diff_encode(_p(vol), _p(out), c_long(Z), c_long(Y), c_long(X), c_int(nthreads)))
+        else:
+            fn = self.lib.ref_diff8_decode if decode else self.lib.ref_diff8_encode
+            rc = fn(_p(vol), _p(out), c_long(Z), c_long(Y), c_long(X))
+        assert rc == 0
+        return out
+
+    def diff_name(self) -> str:
+        buf = ctypes.create_string_buffer(64)
+        assert self.lib.ref_diff_name(buf, c_int(64)) == 0
+        return buf.value.decode()
 
     def quantiser_setup(self, a):
         a = np.ascontiguousarray(a, dtype=np.uint16)
@@ -397,7 +432,7 @@ def minors(args: str):
     return out
 
 
-HEAD_U16 = {"bitswap1", "bitshuffle", "remove_background", "rmestbkrd"}   # sqeazy_pipelines.hpp:31-45 (hot-path subset)
+HEAD_U16 = {"bitswap1", "bitshuffle", "diff3x3x1", "remove_background", "rmestbkrd"}   # sqeazy_pipelines.hpp:31-45 (hot-path subset)
 SINK_U16 = {"pass_through", "quantiser", "lz4"}                    # :47-56
 TAIL_CHAR = {"lz4"}                                                # :58-74 (hot-path subset)
 

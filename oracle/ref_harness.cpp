@@ -11,6 +11,7 @@
 //   quantiser<uint16_t,char>              encoders/quantiser_utils.hpp:44-545
 //   lz4_scheme<uint16_t>/<char>           encoders/lz4.hpp:34-347, lz4_utils.hpp:99-274
 //   compass::runtime::size::cache::level  compass.hpp:1312-1326
+//   diff_scheme<uint16_t>/<uint8_t>       encoders/diff_scheme_impl.hpp:15-213 (last_plane_neighborhood<3>, "diff3x3x1")
 // Boost is absent in this image: oracle/refshim/ provides ~40 lines of stand-ins
 // and a stub of string_parsers.hpp. The full
 // dynamic_pipeline/header (boost::property_tree) cannot be compiled here; the
@@ -29,6 +30,7 @@
 #include "encoders/remove_estimated_background_scheme_impl.hpp"
 #include "encoders/quantiser_utils.hpp"
 #include "encoders/lz4.hpp"
+#include "encoders/diff_scheme_impl.hpp"
 
 namespace sqy = sqeazy;
 
@@ -106,6 +108,38 @@ int ref_rmestbkrd_encode(const uint16_t* in, uint16_t* out, long z, long y, long
   s.set_n_threads(nthreads);
   std::vector<std::size_t> dims = {(std::size_t)z, (std::size_t)y, (std::size_t)x};
   return s.encode(in, out, dims) == out + z * y * x ? 0 : 1;
+}
+
+// ---- diff: difference to the mean of the 3x3 neighbours in the previous z plane --------------
+int ref_diff_encode(const uint16_t* in, uint16_t* out, long z, long y, long x, int nthreads) {
+  sqy::diff_scheme<uint16_t> s;
+  s.set_n_threads(nthreads);
+  std::vector<std::size_t> dims = {(std::size_t)z, (std::size_t)y, (std::size_t)x};
+  return s.encode(in, out, dims) == out + z * y * x ? 0 : 1;
+}
+int ref_diff_decode(const uint16_t* in, uint16_t* out, long z, long y, long x) {
+  sqy::diff_scheme<uint16_t> s;
+  s.set_n_threads(1);                       // the reference's decode loop races across planes with more threads
+  std::vector<std::size_t> dims = {(std::size_t)z, (std::size_t)y, (std::size_t)x};
+  return s.decode(in, out, dims);
+}
+int ref_diff8_encode(const uint8_t* in, uint8_t* out, long z, long y, long x) {
+  sqy::diff_scheme<uint8_t> s;
+  s.set_n_threads(1);
+  std::vector<std::size_t> dims = {(std::size_t)z, (std::size_t)y, (std::size_t)x};
+  return s.encode(in, out, dims) == out + z * y * x ? 0 : 1;
+}
+int ref_diff8_decode(const uint8_t* in, uint8_t* out, long z, long y, long x) {
+  sqy::diff_scheme<uint8_t> s;
+  s.set_n_threads(1);
+  std::vector<std::size_t> dims = {(std::size_t)z, (std::size_t)y, (std::size_t)x};
+  return s.decode(in, out, dims);
+}
+int ref_diff_name(char* out, int cap) {
+  const std::string n = sqy::diff_scheme<uint16_t>().name();
+  if ((int)n.size() + 1 > cap) return 1;
+  std::memcpy(out, n.c_str(), n.size() + 1);
+  return 0;
 }
 
 // ---- quantiser -----------------------------------------------------------

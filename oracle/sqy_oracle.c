@@ -531,3 +531,59 @@ int orc_bitshuffle(int decode, const uint8_t* in, uint8_t* out, uint64_t size, u
   free(tmp);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * diff3x3x1 — encoders/diff_scheme_impl.hpp:78-199 with last_plane_neighborhood<3>
+ * (neighborhood_utils.hpp:72-92), halo::compute_offsets_in_x (:186-226), naive_sum (diff_scheme_utils.hpp:75-103).
+ * Pinned against oracle/_ref (the compiled reference) in tests/test_oracle.py.
+ *
+ *   out[i] = in[i] - (sum of the 9 voxels around i in the previous z plane, ACCUMULATED IN THE VOXEL TYPE, i.e. mod 2^16
+ *            or 2^8) / 9          for i in the covered set, out[i] = in[i] elsewhere; decode adds the same term, computed
+ *            from already decoded voxels, in index order.
+ * naive_sum only uses linear offsets: the 9 voxels are i - Y*X + dy*X + dx, dy, dx in {-1,0,1}.
+ * Covered set, as the reference's loops produce it (halo is built with world = {Z,Y,X} but asked per axis in x,y,z
+ * order, so the x range comes from the Z extent and the z range from the X extent):
+ *   rows (z, y) with 1 <= z < min(X, Z), 1 <= y < Y-1; of each row the indices z*Y*X + y*X + 1 + [0, Z-2).
+ * For Z > X the runs spill into the following rows. Shapes where a run would leave its plane, where fewer than two
+ * rows qualify (the reference then sweeps to the end of the buffer and reads in front of it) or where an extent does
+ * not fit the reference's int16 coordinates are refused (return 1).
+ * elem = 2 (uint16) or 1 (uint8).
+ * ------------------------------------------------------------------------------------------ */
+int orc_diff_supported(uint64_t Z, uint64_t Y, uint64_t X) {
+  if (Z < 3 || Y < 3 || X < 2) return 0;
+  if (Z > 32767 || Y > 32767 || X > 32767) return 0;
+  if ((X - 1) * (Y - 2) <= 1) return 0;                        /* num_offsets_required <= 1: the degenerate sweep */
+  const uint64_t zend = X < Z ? X : Z;
+  if ((zend - 1) * (Y - 2) <= 1) return 0;                     /* a single offset pushed: same sweep */
+  if ((Y - 2) * X + 1 + (Z - 2) > Y * X) return 0;             /* the last run would leave the plane */
+  return 1;
+}
+
+int orc_diff(int decode, const void* in_v, void* out_v, uint64_t Z, uint64_t Y, uint64_t X, int elem) {
+  if (!orc_diff_supported(Z, Y, X) || (elem != 1 && elem != 2)) return 1;
+  const uint64_t frame = Y * X, n = Z * frame, zend = X < Z ? X : Z;
+  memcpy(out_v, in_v, n * (uint64_t)elem);
+  const uint8_t* in8 = (const uint8_t*)in_v;   uint8_t* out8 = (uint8_t*)out_v;
+  const uint16_t* in16 = (const uint16_t*)in_v; uint16_t* out16 = (uint16_t*)out_v;
+  for (uint64_t z = 1; z < zend; ++z)
+    for (uint64_t y = 1; y + 1 < Y; ++y)
+      for (uint64_t k = 0; k + 2 < Z; ++k) {
+        const uint64_t i = z * frame + y * X + 1 + k;
+        if (elem == 2) {
+          const uint16_t* nb = decode ? out16 : in16;          /* decode reads what it has already written (plane z-1) */
+          uint16_t sum = 0;
+          for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) sum = (uint16_t)(sum + nb[i - frame + (int64_t)dy * (int64_t)X + dx]);
+          const uint32_t q = (uint32_t)sum / 9u;
+          out16[i] = decode ? (uint16_t)(in16[i] + q) : (uint16_t)(in16[i] - q);
+        } else {
+          const uint8_t* nb = decode ? out8 : in8;
+          uint8_t sum = 0;
+          for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) sum = (uint8_t)(sum + nb[i - frame + (int64_t)dy * (int64_t)X + dx]);
+          const uint32_t q = (uint32_t)sum / 9u;
+          out8[i] = decode ? (uint8_t)(in8[i] + q) : (uint8_t)(in8[i] - q);
+        }
+      }
+  return 0;
+}

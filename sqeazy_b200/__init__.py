@@ -37,6 +37,7 @@ SQYX_SYMBOLS = [
     "sqyx_rmest_frame_portion", "sqyx_encode_device_UI8", "sqyx_decode_device_UI8", "sqyx_bitswap_encode_UI8",
     "sqyx_bitswap_decode_UI8", "sqyx_remove_background_UI8", "sqyx_decode_batch_device_UI16", "sqyx_encode_batch_device_UI16",
     "sqyx_bitshuffle_encode_UI16", "sqyx_bitshuffle_decode_UI16", "sqyx_bitshuffle_encode_UI8", "sqyx_bitshuffle_decode_UI8", "sqyx_set_lz4_defer_min",
+    "sqyx_diff_device", "sqyx_diff_shape_supported",
 ]
 
 _lib = None
@@ -317,6 +318,22 @@ def bitshuffle_decode_device(src, dst, block_size: int = 0, stream=None):
     if rc != 0:
         raise SqeazyError("sqyx_bitshuffle_decode_UI16 failed")
     return dst
+
+
+def diff_device(src, dst, decode: bool = False, stream=None):
+    """diff3x3x1 (encoders/diff_scheme_impl.hpp:78-199) of a rank-3 uint16 / uint8 device tensor into `dst` (another buffer)"""
+    if src.dim() != 3:
+        raise SqeazyError("diff3x3x1 needs a rank-3 stack")
+    z, y, x = (int(v) for v in src.shape)
+    rc = lib().sqyx_diff_device(c_int(1 if decode else 0), c_int(src.element_size()), _dp(src), _dp(dst), c_long(z), c_long(y),
+                                c_long(x), _stream_handle(stream))
+    if rc != 0:
+        raise SqeazyError(f"sqyx_diff_device failed ({rc}: {'shape not supported' if rc == 2 else 'error'})")
+    return dst
+
+
+def diff_shape_supported(z: int, y: int, x: int) -> bool:
+    return bool(lib().sqyx_diff_shape_supported(c_long(z), c_long(y), c_long(x)))
 
 
 def remove_background_device(src, dst, threshold: int, stream=None):

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -247,6 +248,13 @@ int encode_device_impl(Arena& A, const Pipeline& pl_in, const void* d_src_any, c
         std::fprintf(stderr, "[sqeazy_b200] bitshuffle failed (block_size=%u must be a multiple of 8)\n", s.block_size);
         return 1;
       }
+    } else if (s.kind == StageKind::Diff) {
+      if (next_buf(&out)) return 1;
+      if (shape.size() != 3 || k_diff_encode(pl.elem, cur, out, shape[0], shape[1], shape[2], st)) {
+        // diff_scheme_impl.hpp:84-87 needs rank 3; shapes on which the reference's own loops leave the plane are refused
+        std::fprintf(stderr, "[sqeazy_b200] diff3x3x1: shape not supported\n");
+        return 1;
+      }
     } else {  // Bitswap
       if (next_buf(&out)) return 1;
       if (u8) CKK(k_bitswap8_encode(s.w, b8(cur), m8(out), N, 0, st));
@@ -431,7 +439,7 @@ int decode_streamed(Arena& A, const Pipeline& pl, const uint8_t* d_payload, uint
   int w = 0, nswaps = 0;
   for (const Stage& s : pl.head) {
     if (s.kind == StageKind::Bitswap) { w = s.w; nswaps++; }
-    else if (s.kind == StageKind::Bitshuffle) return -1;
+    else if (s.kind == StageKind::Bitshuffle || s.kind == StageKind::Diff) return -1;
   }
   if (nswaps != 1) return -1;
   const int P = 16 / w;
@@ -491,9 +499,14 @@ int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const ui
   }
 
   // data-moving head stages in decode order (reverse); the background filters decode as identity
-  std::vector<int> swaps;                 // bitswap: bits per plane; bitshuffle: -1 - block_size
+  std::vector<int> swaps;                 // bitswap: bits per plane; bitshuffle: -1 - block_size; diff3x3x1: kDiffOp
+  constexpr int kDiffOp = INT_MIN;
   for (size_t i = pl.head.size(); i-- > 0;) {
     if (pl.head[i].kind == StageKind::Bitswap) swaps.push_back(pl.head[i].w);
+    if (pl.head[i].kind == StageKind::Diff) {
+      if (hdr.shape.size() != 3 || !diff_shape_supported(hdr.shape[0], hdr.shape[1], hdr.shape[2])) return 100 + 1;
+      swaps.push_back(kDiffOp);
+    }
     if (pl.head[i].kind == StageKind::Bitshuffle) swaps.push_back(-1 - (int)pl.head[i].block_size);
   }
 
@@ -575,6 +588,11 @@ int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const ui
     else {
       // pick the scratch buffer that does not hold `cur`
       if (scratch(cur == bufs[0] ? 1 : 0, &out)) return 1;
+    }
+    if (swaps[k] == kDiffOp) {
+      if (k_diff_decode(pl.elem, cur, out, hdr.shape[0], hdr.shape[1], hdr.shape[2], st)) return 100 + 1;
+      cur = out;
+      continue;
     }
     if (swaps[k] < 0) {
       const uint32_t bsz = (uint32_t)(-1 - swaps[k]);
@@ -902,6 +920,19 @@ int sqyx_bitshuffle_decode_UI8(const void* d_src, void* d_dst, long n, long bloc
   return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 1;
 }
 
+int sqyx_diff_device(int decode, int sizeof_voxel, const void* d_src, void* d_dst, long z, long y, long x, void* stream) {
+  if (z < 0 || y < 0 || x < 0 || (sizeof_voxel != 1 && sizeof_voxel != 2) || d_src == d_dst) return 1;
+  if (!diff_shape_supported((uint64_t)z, (uint64_t)y, (uint64_t)x)) return 2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (decode ? k_diff_decode(sizeof_voxel, d_src, d_dst, (uint64_t)z, (uint64_t)y, (uint64_t)x, st)
+             : k_diff_encode(sizeof_voxel, d_src, d_dst, (uint64_t)z, (uint64_t)y, (uint64_t)x, st))
+    return 1;
+  return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 1;
+}
+int sqyx_diff_shape_supported(long z, long y, long x) {
+  return z >= 0 && y >= 0 && x >= 0 && diff_shape_supported((uint64_t)z, (uint64_t)y, (uint64_t)x) ? 1 : 0;
+}
+
 int sqyx_bitswap_encode_UI16(int w, const void* d_src, void* d_dst, long n, int threshold, void* stream) {
   if (n < 0) return 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1166,24 +1197,22 @@ int host_encode_streamed(Arena& A, const Pipeline& pl, const char* src, const st
   const Stage& swap = pl.head.back();
   const int P = 16 / swap.w;
 
-  int thr = 0;
-  if (pl.head.size() == 2) {
-    thr = pl.head[0].threshold;
-    if (pl.head[0].kind == StageKind::RmEstBkrd) {
-      // the estimate samples the two z faces and six border rows: those voxels go first
-      const uint64_t Z = shape[0], Y = shape[1], X = shape[2], frame = Y * X;
-      const uint64_t portion = rmest_frame_portion(frame, host_l2_cache_bytes());
-      const uint16_t* h = reinterpret_cast<const uint16_t*>(src);
-      CK(cudaMemcpyAsync(d_in, h, 2 * portion, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(d_in + (Z - 1) * frame, h + (Z - 1) * frame, 2 * portion, cudaMemcpyHostToDevice, st));
-      const uint64_t zs[3] = {1, Z / 2, Z - 2}, ys[2] = {0, Y - 1};
-      for (uint64_t z : zs)
-        for (uint64_t y : ys) CK(cudaMemcpyAsync(d_in + z * frame + y * X, h + z * frame + y * X, 2 * X, cudaMemcpyHostToDevice, st));
-      float sup[4];
-      ScopedStageTimer tm(kTFilterSwap, st);
-      if (estimate_background(A, d_in, Z, Y, X, -1, sup, &thr, st)) return 1;
-    }
-  }
+  int thr = pl.head.size() == 2 ? pl.head[0].threshold : 0;
+  // rmestbkrd: the estimate samples the two z faces and six border rows. They are sent on their own (behind the first slab,
+  // which is already on its way: the bus never waits for the estimate) and the threshold is there before the first kernel.
+  auto estimate = [&]() -> int {
+    if (pl.head.size() != 2 || pl.head[0].kind != StageKind::RmEstBkrd) return 0;
+    const uint64_t Z = shape[0], Y = shape[1], X = shape[2], frame = Y * X;
+    const uint64_t portion = rmest_frame_portion(frame, host_l2_cache_bytes());
+    const uint16_t* h = reinterpret_cast<const uint16_t*>(src);
+    CK(cudaMemcpyAsync(d_in, h, 2 * portion, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_in + (Z - 1) * frame, h + (Z - 1) * frame, 2 * portion, cudaMemcpyHostToDevice, st));
+    const uint64_t zs[3] = {1, Z / 2, Z - 2}, ys[2] = {0, Y - 1};
+    for (uint64_t z : zs)
+      for (uint64_t y : ys) CK(cudaMemcpyAsync(d_in + z * frame + y * X, h + z * frame + y * X, 2 * X, cudaMemcpyHostToDevice, st));
+    float sup[4];
+    return estimate_background(A, d_in, Z, Y, X, -1, sup, &thr, st);
+  };
 
   CKK(k_lz4_encode_begin(raw_bytes, payload, ws, st));
   const uint64_t slab_voxels = kStreamSlabBytes / 2;          // a multiple of the grain
@@ -1195,6 +1224,7 @@ int host_encode_streamed(Arena& A, const Pipeline& pl, const char* src, const st
     cudaEvent_t arrived = nullptr;
     if (events.next(&arrived)) return 1;
     CK(cudaEventRecord(arrived, cs));
+    if (first == 0 && estimate()) return 1;
     CK(cudaStreamWaitEvent(st, arrived, 0));
     CKK(k_bitswap_encode_range(swap.w, d_in, d_planes, N, first, count, thr, st));
     // plane piece of this slab: bytes [2*first/P, 2*(first+count)/P) of every plane

@@ -1,0 +1,61 @@
+// diff3x3x1 head filter: every voxel minus the mean of the 3x3 voxels around it in the previous z plane.
+// Reference: encoders/diff_scheme_impl.hpp:78-199 with last_plane_neighborhood<3> (neighborhood_utils.hpp:72-92), the
+// row list of halo::compute_offsets_in_x (neighborhood_utils.hpp:186-226) and naive_sum (diff_scheme_utils.hpp:75-103).
+//
+// What the reference computes (restated in oracle/sqy_oracle.c: orc_diff, pinned against the compiled reference):
+//   q(i)   = ((sum of v[i - Y*X + dy*X + dx], dy, dx in {-1,0,1}) mod 2^bits) / 9        -- the sum wraps in the voxel type
+//   encode : out[i] = in[i] - q(i) on `in`            for covered i, out[i] = in[i] elsewhere
+//   decode : out[i] = in[i] + q(i) on `out`, in index order (plane z needs the decoded plane z-1)
+//   covered: rows (z, y), 1 <= z < min(X, Z), 1 <= y < Y-1, of each the Z-2 indices from x = 1 on (the reference takes
+//            the x range from the Z extent and the z range from the X extent); for Z > X the runs spill into the next row.
+// Shapes the reference itself mishandles (runs leaving the plane, the one-row sweep, extents beyond int16) are refused.
+//
+// Encode is one launch over the volume: 4 B/voxel of HBM traffic (the previous plane is re-read from L2: 9 reads per voxel
+// come as three 16-byte row loads + six halo elements per 8 voxels). Decode is a recurrence along z only: one launch per
+// coded plane (all voxels of a plane are independent), planes 0 and >= min(X, Z) are copies.
+#include "common.cuh"
+#include "diff_thread.h"
+#include "kernels.h"
+
+namespace sqyb {
+
+namespace {
+
+template <typename T, bool DECODE>
+__global__ void __launch_bounds__(256) diff_kernel(const T* in, T* out, const T* nb, uint64_t begin, uint64_t end, DiffGeom g) {
+  diff_thread<T, DECODE>(in, out, nb, begin, end, g, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+template <typename T, bool DECODE>
+int launch_range(const T* in, T* out, const T* nb, uint64_t begin, uint64_t end, const DiffGeom& g, cudaStream_t st) {
+  if (end <= begin) return 0;
+  const uint64_t threads = (end - begin + 7) / 8, blocks = (threads + 255) / 256;
+  if (blocks > 0x7fffffffull) return 1;
+  diff_kernel<T, DECODE><<<(unsigned)blocks, 256, 0, st>>>(in, out, nb, begin, end, g);
+  SQYB_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+int diff_run(bool decode, const T* in, T* out, uint64_t Z, uint64_t Y, uint64_t X, cudaStream_t st) {
+  if (!diff_shape_ok(Z, Y, X) || in == out) return 1;
+  const DiffGeom g = diff_geom(Z, Y, X);
+  return diff_for_each_launch(decode, g, [&](uint64_t begin, uint64_t end) {
+    return decode ? launch_range<T, true>(in, out, out, begin, end, g, st) : launch_range<T, false>(in, out, in, begin, end, g, st);
+  });
+}
+
+}  // namespace
+
+bool diff_shape_supported(uint64_t Z, uint64_t Y, uint64_t X) { return diff_shape_ok(Z, Y, X); }
+
+int k_diff_encode(int elem, const void* in, void* out, uint64_t Z, uint64_t Y, uint64_t X, cudaStream_t st) {
+  return elem == 1 ? diff_run<uint8_t>(false, static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), Z, Y, X, st)
+                   : diff_run<uint16_t>(false, static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), Z, Y, X, st);
+}
+int k_diff_decode(int elem, const void* in, void* out, uint64_t Z, uint64_t Y, uint64_t X, cudaStream_t st) {
+  return elem == 1 ? diff_run<uint8_t>(true, static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), Z, Y, X, st)
+                   : diff_run<uint16_t>(true, static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), Z, Y, X, st);
+}
+
+}  // namespace sqyb

@@ -17,6 +17,7 @@ std::string Stage::name() const {
   switch (kind) {
     case StageKind::Bitswap: return "bitswap" + std::to_string(w);
     case StageKind::Bitshuffle: return "bitshuffle";
+    case StageKind::Diff: return "diff3x3x1";   // diff_scheme_impl.hpp:35-45 with last_plane_neighborhood<3>
     case StageKind::RemoveBackground: return "remove_background";
     case StageKind::RmEstBkrd: return "rmestbkrd";
     case StageKind::Quantiser: return "quantiser";
@@ -40,6 +41,7 @@ std::string Stage::config() const {
       break;
     case StageKind::RmEstBkrd:
     case StageKind::PassThrough:
+    case StageKind::Diff:  // diff_scheme_impl.hpp:55-59: empty
       break;
     case StageKind::Quantiser: {  // quantiser_scheme_impl.hpp:104-120 (map order)
       size_t count = 0;
@@ -81,7 +83,7 @@ std::string Pipeline::canonical() const {
 // registry (sqeazy_pipelines.hpp:31-77, hot-path stages only) + aliases
 // ------------------------------------------------------------------------------------------------
 static bool is_head_name(const std::string& n) {
-  return n == "bitswap1" || n == "bitswap2" || n == "bitswap4" || n == "bitswap8" || n == "bitshuffle" || n == "remove_background" ||
+  return n == "bitswap1" || n == "bitswap2" || n == "bitswap4" || n == "bitswap8" || n == "bitshuffle" || n == "diff3x3x1" || n == "remove_background" ||
          n == "rmbkrd" || n == "rmestbkrd";
 }
 static bool is_sink_name(const std::string& n) { return n == "lz4" || n == "quantiser" || n == "pass_through"; }
@@ -117,6 +119,7 @@ static bool make_stage(const std::string& name, const std::string& args, Stage& 
     }
     return true;                                     // a block size that is no multiple of 8 fails at encode time, like bshuf's -81
   }
+  if (name == "diff3x3x1") { st.kind = StageKind::Diff; return true; }   // a shape it cannot take fails at encode time
   if (name.rfind("bitswap", 0) == 0) {
     st.kind = StageKind::Bitswap;
     st.w = std::atoi(name.c_str() + 7);

@@ -3,7 +3,7 @@
 //   dynamic_pipeline.hpp:137-170 (from_string), :177-226 (can_be_built_from), :476-503 (name),
 //   :866-890 (max_encoded_size); sqeazy_pipelines.hpp:31-77 (registry);
 //   stage configs: bitswap_scheme_impl.hpp:40-90, remove_background_scheme_impl.hpp:32-71,
-//   quantiser_scheme_impl.hpp:83-137, lz4.hpp:58-188.
+//   quantiser_scheme_impl.hpp:83-137, lz4.hpp:58-188, diff_scheme_impl.hpp:35-59 ("diff3x3x1", no config).
 #pragma once
 #include <cstdint>
 #include <map>
@@ -14,7 +14,7 @@
 
 namespace sqyb {
 
-enum class StageKind { Bitswap, Bitshuffle, RemoveBackground, RmEstBkrd, Quantiser, Lz4, PassThrough };
+enum class StageKind { Bitswap, Bitshuffle, Diff, RemoveBackground, RmEstBkrd, Quantiser, Lz4, PassThrough };
 
 struct Stage {
   StageKind kind;
