@@ -44,7 +44,7 @@ int SQY_Version_Triple(int* version);
 int SQY_PipelineEncode_UI16(const char* pipeline, const char* src, long* shape, unsigned shape_size, char* dst,
                             long* dstlength, int nthreads);
 
-/* reference: sqeazy.cpp:72-106 (dypeline<uint8_t>) — uint8 voxels; stages with uint8 kernels: bitswap1|2|4, bitshuffle,
+/* reference: sqeazy.cpp:72-106 (dypeline<uint8_t>) — uint8 voxels; stages with uint8 kernels: bitswap1|2|4, bitshuffle, diff3x3x1,
  * remove_background(threshold=N) -> lz4 | pass_through [-> lz4]; any other stage name returns 1 */
 int SQY_PipelineEncode_UI8(const char* pipeline, const char* src, long* shape, unsigned shape_size, char* dst,
                            long* dstlength, int nthreads);
