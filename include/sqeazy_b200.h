@@ -62,9 +62,10 @@ int sqyx_bitshuffle_decode_UI8(const void* d_src, void* d_dst, long n, long bloc
  * (neighborhood_utils.hpp:72-92, :186-226; diff_scheme_utils.hpp:75-103): voxel minus (sum of the 3x3 voxels around it in
  * the previous z plane, wrapped in the voxel type) / 9 on the rows the reference visits; decode = the inverse recurrence
  * along z. Device buffers of z*y*x voxels (C order), d_src != d_dst, sizeof_voxel 1 or 2. Returns 2 for a shape on which
- * the reference's own loops leave the plane or the buffer (sqyx_diff_shape_supported tells), 1 for any other failure. */
+ * the reference's own loops leave the plane or the buffer, or an extent exceeds the int16 / int8 coordinates the reference
+ * keeps for uint16 / uint8 stacks (32767 / 128) (sqyx_diff_shape_supported tells), 1 for any other failure. */
 int sqyx_diff_device(int decode, int sizeof_voxel, const void* d_src, void* d_dst, long z, long y, long x, void* stream);
-int sqyx_diff_shape_supported(long z, long y, long x);
+int sqyx_diff_shape_supported(int sizeof_voxel, long z, long y, long x);
 
 /* out = in > t ? in - t : 0. reference: encoders/remove_background_scheme_impl.hpp:73-95 */
 int sqyx_remove_background_UI16(const void* d_src, void* d_dst, long n, int threshold, void* stream);

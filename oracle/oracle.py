@@ -124,9 +124,9 @@ class Port:
         self.lib.orc_rmestbkrd(_p(vol), _p(out), c_uint64(Z), c_uint64(Y), c_uint64(X), c_uint64(l2_bytes), ctypes.byref(t))
         return out, t.value
 
-    def diff_supported(self, shape) -> bool:
+    def diff_supported(self, shape, elem: int = 2) -> bool:
         Z, Y, X = (int(v) for v in shape)
-        return bool(self.lib.orc_diff_supported(c_uint64(Z), c_uint64(Y), c_uint64(X)))
+        return bool(self.lib.orc_diff_supported(c_uint64(Z), c_uint64(Y), c_uint64(X), c_int(elem)))
 
     def diff(self, vol: np.ndarray, decode: bool = False) -> np.ndarray:
         """diff3x3x1 (encoders/diff_scheme_impl.hpp:78-199), uint16 or uint8 by the array's dtype; ValueError for a refused shape"""

@@ -546,12 +546,14 @@ int orc_bitshuffle(int decode, const uint8_t* in, uint8_t* out, uint64_t size, u
  *   rows (z, y) with 1 <= z < min(X, Z), 1 <= y < Y-1; of each row the indices z*Y*X + y*X + 1 + [0, Z-2).
  * For Z > X the runs spill into the following rows. Shapes where a run would leave its plane, where fewer than two
  * rows qualify (the reference then sweeps to the end of the buffer and reads in front of it) or where an extent does
- * not fit the reference's int16 coordinates are refused (return 1).
+ * not fit the coordinates naive_sum keeps in the SIGNED type of the voxel width (int16 for uint16 stacks, int8 for uint8
+ * stacks: from 129 rows on the reference reads from wrapped coordinates, in front of the buffer) are refused (return 1).
  * elem = 2 (uint16) or 1 (uint8).
  * ------------------------------------------------------------------------------------------ */
-int orc_diff_supported(uint64_t Z, uint64_t Y, uint64_t X) {
+int orc_diff_supported(uint64_t Z, uint64_t Y, uint64_t X, int elem) {
   if (Z < 3 || Y < 3 || X < 2) return 0;
-  if (Z > 32767 || Y > 32767 || X > 32767) return 0;
+  const uint64_t lim = elem == 1 ? 128 : 32767;                /* coord_t = int8 / int16 (diff_scheme_utils.hpp:81-89) */
+  if (Z > lim || Y > lim || X > lim) return 0;
   if ((X - 1) * (Y - 2) <= 1) return 0;                        /* num_offsets_required <= 1: the degenerate sweep */
   const uint64_t zend = X < Z ? X : Z;
   if ((zend - 1) * (Y - 2) <= 1) return 0;                     /* a single offset pushed: same sweep */
@@ -560,7 +562,7 @@ int orc_diff_supported(uint64_t Z, uint64_t Y, uint64_t X) {
 }
 
 int orc_diff(int decode, const void* in_v, void* out_v, uint64_t Z, uint64_t Y, uint64_t X, int elem) {
-  if (!orc_diff_supported(Z, Y, X) || (elem != 1 && elem != 2)) return 1;
+  if ((elem != 1 && elem != 2) || !orc_diff_supported(Z, Y, X, elem)) return 1;
   const uint64_t frame = Y * X, n = Z * frame, zend = X < Z ? X : Z;
   memcpy(out_v, in_v, n * (uint64_t)elem);
   const uint8_t* in8 = (const uint8_t*)in_v;   uint8_t* out8 = (uint8_t*)out_v;

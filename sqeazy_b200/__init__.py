@@ -332,8 +332,8 @@ def diff_device(src, dst, decode: bool = False, stream=None):
     return dst
 
 
-def diff_shape_supported(z: int, y: int, x: int) -> bool:
-    return bool(lib().sqyx_diff_shape_supported(c_long(z), c_long(y), c_long(x)))
+def diff_shape_supported(z: int, y: int, x: int, sizeof_voxel: int = 2) -> bool:
+    return bool(lib().sqyx_diff_shape_supported(c_int(sizeof_voxel), c_long(z), c_long(y), c_long(x)))
 
 
 def remove_background_device(src, dst, threshold: int, stream=None):

@@ -504,7 +504,7 @@ int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const ui
   for (size_t i = pl.head.size(); i-- > 0;) {
     if (pl.head[i].kind == StageKind::Bitswap) swaps.push_back(pl.head[i].w);
     if (pl.head[i].kind == StageKind::Diff) {
-      if (hdr.shape.size() != 3 || !diff_shape_supported(hdr.shape[0], hdr.shape[1], hdr.shape[2])) return 100 + 1;
+      if (hdr.shape.size() != 3 || !diff_shape_supported(hdr.shape[0], hdr.shape[1], hdr.shape[2], pl.elem)) return 100 + 1;
       swaps.push_back(kDiffOp);
     }
     if (pl.head[i].kind == StageKind::Bitshuffle) swaps.push_back(-1 - (int)pl.head[i].block_size);
@@ -922,15 +922,15 @@ int sqyx_bitshuffle_decode_UI8(const void* d_src, void* d_dst, long n, long bloc
 
 int sqyx_diff_device(int decode, int sizeof_voxel, const void* d_src, void* d_dst, long z, long y, long x, void* stream) {
   if (z < 0 || y < 0 || x < 0 || (sizeof_voxel != 1 && sizeof_voxel != 2) || d_src == d_dst) return 1;
-  if (!diff_shape_supported((uint64_t)z, (uint64_t)y, (uint64_t)x)) return 2;
+  if (!diff_shape_supported((uint64_t)z, (uint64_t)y, (uint64_t)x, sizeof_voxel)) return 2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (decode ? k_diff_decode(sizeof_voxel, d_src, d_dst, (uint64_t)z, (uint64_t)y, (uint64_t)x, st)
              : k_diff_encode(sizeof_voxel, d_src, d_dst, (uint64_t)z, (uint64_t)y, (uint64_t)x, st))
     return 1;
   return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 1;
 }
-int sqyx_diff_shape_supported(long z, long y, long x) {
-  return z >= 0 && y >= 0 && x >= 0 && diff_shape_supported((uint64_t)z, (uint64_t)y, (uint64_t)x) ? 1 : 0;
+int sqyx_diff_shape_supported(int sizeof_voxel, long z, long y, long x) {
+  return z >= 0 && y >= 0 && x >= 0 && diff_shape_supported((uint64_t)z, (uint64_t)y, (uint64_t)x, sizeof_voxel) ? 1 : 0;
 }
 
 int sqyx_bitswap_encode_UI16(int w, const void* d_src, void* d_dst, long n, int threshold, void* stream) {

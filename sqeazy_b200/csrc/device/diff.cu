@@ -8,11 +8,13 @@
 //   decode : out[i] = in[i] + q(i) on `out`, in index order (plane z needs the decoded plane z-1)
 //   covered: rows (z, y), 1 <= z < min(X, Z), 1 <= y < Y-1, of each the Z-2 indices from x = 1 on (the reference takes
 //            the x range from the Z extent and the z range from the X extent); for Z > X the runs spill into the next row.
-// Shapes the reference itself mishandles (runs leaving the plane, the one-row sweep, extents beyond int16) are refused.
+// Shapes the reference itself mishandles (runs leaving the plane, the one-row sweep, extents beyond the int16 / int8
+// coordinates it keeps for uint16 / uint8 stacks) are refused.
 //
-// Encode is one launch over the volume: 4 B/voxel of HBM traffic (the previous plane is re-read from L2: 9 reads per voxel
-// come as three 16-byte row loads + six halo elements per 8 voxels). Decode is a recurrence along z only: one launch per
-// coded plane (all voxels of a plane are independent), planes 0 and >= min(X, Z) are copies.
+// Encode is one launch over the volume: 4 B/voxel of HBM traffic, the previous plane is re-read from L2. A thread walks a
+// strip of 8 voxels x kDiffRows rows and keeps the 3-tap row sums of the previous plane it can reuse (kDiffRows + 2 row
+// loads of 16 bytes + 2 halo voxels for kDiffRows output rows). Decode is a recurrence along z only: one launch per coded
+// plane (all voxels of a plane are independent), planes 0 and >= min(X, Z) are copies.
 #include "common.cuh"
 #include "diff_thread.h"
 #include "kernels.h"
@@ -22,32 +24,34 @@ namespace sqyb {
 namespace {
 
 template <typename T, bool DECODE>
-__global__ void __launch_bounds__(256) diff_kernel(const T* in, T* out, const T* nb, uint64_t begin, uint64_t end, DiffGeom g) {
-  diff_thread<T, DECODE>(in, out, nb, begin, end, g, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+__global__ void __launch_bounds__(256) diff_kernel(const T* in, T* out, const T* nb, DiffGeom g, uint32_t z0) {
+  diff_thread<T, DECODE>(in, out, nb, g, z0 + blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 template <typename T, bool DECODE>
-int launch_range(const T* in, T* out, const T* nb, uint64_t begin, uint64_t end, const DiffGeom& g, cudaStream_t st) {
-  if (end <= begin) return 0;
-  const uint64_t threads = (end - begin + 7) / 8, blocks = (threads + 255) / 256;
-  if (blocks > 0x7fffffffull) return 1;
-  diff_kernel<T, DECODE><<<(unsigned)blocks, 256, 0, st>>>(in, out, nb, begin, end, g);
-  SQYB_COUNT_LAUNCH(1);
+int launch_planes(const T* in, T* out, const T* nb, const DiffGeom& g, uint32_t z0, uint32_t planes, cudaStream_t st) {
+  if (planes == 0) return 0;
+  const uint64_t blocks = (diff_threads_per_plane(g) + 255) / 256;     // <= 2^19
+  for (uint32_t done = 0; done < planes; done += 65535) {              // gridDim.y limit (not reached: Z <= 32767)
+    const uint32_t now = planes - done < 65535 ? planes - done : 65535;
+    diff_kernel<T, DECODE><<<dim3((unsigned)blocks, now), 256, 0, st>>>(in, out, nb, g, z0 + done);
+    SQYB_COUNT_LAUNCH(1);
+  }
   return (int)cudaGetLastError();
 }
 
 template <typename T>
 int diff_run(bool decode, const T* in, T* out, uint64_t Z, uint64_t Y, uint64_t X, cudaStream_t st) {
-  if (!diff_shape_ok(Z, Y, X) || in == out) return 1;
+  if (!diff_shape_ok(Z, Y, X, (int)sizeof(T)) || in == out) return 1;
   const DiffGeom g = diff_geom(Z, Y, X);
-  return diff_for_each_launch(decode, g, [&](uint64_t begin, uint64_t end) {
-    return decode ? launch_range<T, true>(in, out, out, begin, end, g, st) : launch_range<T, false>(in, out, in, begin, end, g, st);
+  return diff_for_each_launch(decode, g, [&](uint32_t z0, uint32_t planes) {
+    return decode ? launch_planes<T, true>(in, out, out, g, z0, planes, st) : launch_planes<T, false>(in, out, in, g, z0, planes, st);
   });
 }
 
 }  // namespace
 
-bool diff_shape_supported(uint64_t Z, uint64_t Y, uint64_t X) { return diff_shape_ok(Z, Y, X); }
+bool diff_shape_supported(uint64_t Z, uint64_t Y, uint64_t X, int elem) { return diff_shape_ok(Z, Y, X, elem); }
 
 int k_diff_encode(int elem, const void* in, void* out, uint64_t Z, uint64_t Y, uint64_t X, cudaStream_t st) {
   return elem == 1 ? diff_run<uint8_t>(false, static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), Z, Y, X, st)

@@ -1,5 +1,6 @@
-// Thread program of the diff3x3x1 kernels (diff.cu), compilable for the device and for the host: tests/helpers/diff_sim.cpp
-// replays it thread by thread against the oracle where no GPU exists (any thread order, poisoned output).
+// Thread program and launch schedule of the diff3x3x1 kernels (diff.cu), compilable for the device and for the host:
+// tests/helpers/diff_sim.cpp replays them thread by thread against the oracle where no GPU exists (any thread order,
+// poisoned output).
 #pragma once
 #include <stdint.h>
 
@@ -11,18 +12,32 @@
 
 namespace sqyb {
 
+constexpr int kDiffRows = 4;   // rows of a strip: a thread walks 8 voxels x kDiffRows rows and keeps the row sums it can reuse
+
 template <typename T> struct alignas(sizeof(T) * 8) Pack8 { T v[8]; };
 
 struct DiffGeom {
-  uint64_t Z, Y, X, frame, zend;
+  uint32_t Z, Y, X, zend;   // zend = min(X, Z): the planes the reference codes are 1 .. zend-1
+  uint64_t frame;           // Y * X
+  uint32_t ppr, strips;     // 8-voxel packs per row, strips of kDiffRows rows per plane
 };
 
-inline DiffGeom diff_geom(uint64_t Z, uint64_t Y, uint64_t X) { return DiffGeom{Z, Y, X, Y * X, X < Z ? X : Z}; }
+inline DiffGeom diff_geom(uint64_t Z, uint64_t Y, uint64_t X) {
+  DiffGeom g;
+  g.Z = (uint32_t)Z; g.Y = (uint32_t)Y; g.X = (uint32_t)X; g.zend = (uint32_t)(X < Z ? X : Z);
+  g.frame = Y * X;
+  g.ppr = (uint32_t)((X + 7) / 8);
+  g.strips = (uint32_t)((Y + kDiffRows - 1) / kDiffRows);
+  return g;
+}
 
-// shapes on which the reference's loops stay inside their plane (see diff.cu)
-inline bool diff_shape_ok(uint64_t Z, uint64_t Y, uint64_t X) {
+// shapes on which the reference's loops stay inside their plane (see diff.cu); elem = bytes per voxel
+inline bool diff_shape_ok(uint64_t Z, uint64_t Y, uint64_t X, int elem) {
   if (Z < 3 || Y < 3 || X < 2) return false;
-  if (Z > 32767 || Y > 32767 || X > 32767) return false;       // int16 coordinates in naive_sum (diff_scheme_utils.hpp:81-89)
+  // naive_sum keeps z, y, x in the signed type of the voxel width (diff_scheme_utils.hpp:81-89): int16 for uint16 stacks,
+  // int8 for uint8 stacks - beyond that the reference reads from wrapped coordinates (in front of the buffer)
+  const uint64_t lim = elem == 1 ? 128 : 32767;
+  if (Z > lim || Y > lim || X > lim) return false;
   if ((X - 1) * (Y - 2) <= 1) return false;                    // compute_offsets_in_x: a single offset = sweep to the end
   const uint64_t zend = X < Z ? X : Z;
   if ((zend - 1) * (Y - 2) <= 1) return false;
@@ -30,96 +45,114 @@ inline bool diff_shape_ok(uint64_t Z, uint64_t Y, uint64_t X) {
   return true;
 }
 
-// the launches of one encode (the whole volume at once) or decode (plane 0 as stored, one launch per coded plane in z
-// order, the planes the reference skips): f(begin, end) over element ranges, stops at the first non-zero return
+// the launches of one encode (all planes at once) or decode (plane 0 as stored, one launch per coded plane in z order,
+// the planes the reference skips): f(first plane, planes), stops at the first non-zero return
 template <typename F>
 inline int diff_for_each_launch(bool decode, const DiffGeom& g, F f) {
-  if (!decode) return f(0, g.Z * g.frame);
-  int rc = f(0, g.frame);
-  for (uint64_t z = 1; z < g.zend && !rc; ++z) rc = f(z * g.frame, (z + 1) * g.frame);
-  if (!rc && g.zend < g.Z) rc = f(g.zend * g.frame, g.Z * g.frame);
+  if (!decode) return f(0u, g.Z);
+  int rc = f(0u, 1u);
+  for (uint32_t z = 1; z < g.zend && !rc; ++z) rc = f(z, 1u);
+  if (!rc && g.zend < g.Z) rc = f(g.zend, g.Z - g.zend);
   return rc;
 }
+inline uint64_t diff_threads_per_plane(const DiffGeom& g) { return (uint64_t)g.strips * g.ppr; }
 
-SQYB_HD bool diff_covered(const DiffGeom& g, uint64_t z, uint64_t y, uint64_t x) {
-  if (z < 1 || z >= g.zend) return false;
-  const bool own = y >= 1 && y + 1 < g.Y && x >= 1 && x + 1 < g.Z;          // the run of row y
-  const bool spilled = y >= 2 && y <= g.Y - 1 && x + g.X + 1 < g.Z;          // the end of the run of row y-1
+// is voxel (y, x) of a coded plane one the reference visits: in the run of its own row, or in the end of the run of the
+// row above that spilled over (Z > X + 1)
+SQYB_HD bool diff_covered(const DiffGeom& g, uint32_t y, uint32_t x) {
+  const bool own = y >= 1 && y + 1 < g.Y && x >= 1 && x + 1 < g.Z;
+  const bool spilled = y >= 2 && x + g.X + 1 < g.Z;
   return own || spilled;
 }
 
-// Elements [begin, end) of the volume, 8 per thread. `nb` holds the neighbours: `in` itself for encode, `out` for decode
-// (decode: the launch covers one plane, every neighbour lies in the plane before it or, for the spilled end of the last
-// run, in row 0 of the same plane, which is never coded and therefore read from `in`).
+// one voxel the slow way: linear offsets exactly as naive_sum forms them. In decode a neighbour inside the plane being
+// written (row 0, reached by the spilled end of the last run) is never coded and is taken from `in`.
 template <typename T, bool DECODE>
-SQYB_HD void diff_thread(const T* in, T* out, const T* nb, uint64_t begin, uint64_t end, const DiffGeom& g, uint64_t tid) {
-  const uint64_t i0 = begin + 8 * tid;
-  if (i0 >= end) return;
-  const int cnt = end - i0 < 8 ? (int)(end - i0) : 8;
-  const uint64_t z = i0 / g.frame, r = i0 - z * g.frame, y = r / g.X, x = r - y * g.X;
-  constexpr uintptr_t kMask = sizeof(T) * 8 - 1;
-
-  const bool one_row = cnt == 8 && x + 8 <= g.X;
-  const bool io_aligned = ((((uintptr_t)(in + i0)) | ((uintptr_t)(out + i0))) & kMask) == 0;
-  if (one_row && io_aligned && (z < 1 || z >= g.zend || y < 1)) {   // nothing coded here: copy
-    *reinterpret_cast<Pack8<T>*>(out + i0) = *reinterpret_cast<const Pack8<T>*>(in + i0);
-    return;
-  }
-  if (one_row && io_aligned && y + 1 < g.Y) {
-    const Pack8<T> v = *reinterpret_cast<const Pack8<T>*>(in + i0);
-    T acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0;
-    const uint64_t base = i0 - g.frame;   // z >= 1 here
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      const uint64_t row = dy < 0 ? base - g.X : (dy > 0 ? base + g.X : base);   // y >= 1: row >= 0
-      const T* p = nb + row;
-      T e[10];
-      if ((((uintptr_t)p) & kMask) == 0) {
-        const Pack8<T> c = *reinterpret_cast<const Pack8<T>*>(p);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) e[j + 1] = c.v[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) e[j + 1] = p[j];
+SQYB_HD T diff_voxel(const T* in, const T* nb, const DiffGeom& g, uint64_t plane, bool z_coded, uint32_t y, uint32_t x) {
+  const uint64_t i = plane + (uint64_t)y * g.X + x;
+  uint32_t q = 0;
+  if (z_coded && diff_covered(g, y, x)) {
+    T sum = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const uint64_t k = (uint64_t)((int64_t)(i - g.frame) + (int64_t)dy * (int64_t)g.X + dx);
+        sum = (T)(sum + ((DECODE && k >= plane) ? in[k] : nb[k]));
       }
-      e[0] = row > 0 ? p[-1] : (T)0;      // row == 0 only for z = 1, y = 1, x = 0, which is not coded
-      // x + 8 == X in row Y-2: the element after the row below is row 0 of the plane being decoded (never coded: from `in`)
-      e[9] = (DECODE && row + 8 >= z * g.frame) ? in[row + 8] : p[8];
+    q = (uint32_t)sum / 9u;
+  }
+  return DECODE ? (T)(in[i] + q) : (T)(in[i] - q);
+}
+
+// 3-tap sums (in the voxel type) of row r of the previous plane at x0 .. x0+7; rows start 16-byte aligned here
+template <typename T, bool DECODE>
+SQYB_HD void diff_row_sums(const T* in, const T* nb, const DiffGeom& g, uint64_t plane, uint32_t r, uint32_t x0, T* h) {
+  const uint64_t row = plane - g.frame + (uint64_t)r * g.X + x0;
+  const Pack8<T> c = *reinterpret_cast<const Pack8<T>*>(nb + row);
+  const T left = row > 0 ? nb[row - 1] : (T)0;          // row == 0: z = 1, r = 0, x0 = 0 - feeds only voxels that are not coded
+  const T right = (DECODE && row + 8 >= plane) ? in[row + 8] : nb[row + 8];   // r = Y-1 at the row end: row 0 of this plane
+  h[0] = (T)(left + (T)(c.v[0] + c.v[1]));
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = (T)(acc[j] + (T)(e[j] + (T)(e[j + 1] + e[j + 2])));
-    }
-    Pack8<T> o;
+  for (int j = 1; j < 7; ++j) h[j] = (T)(c.v[j - 1] + (T)(c.v[j] + c.v[j + 1]));
+  h[7] = (T)(c.v[6] + (T)(c.v[7] + right));
+}
+
+// Thread t of plane z: 8 voxels x kDiffRows rows. `nb` holds the neighbours: `in` itself for encode, `out` for decode
+// (one plane per launch: every neighbour lies in the plane before).
+template <typename T, bool DECODE>
+SQYB_HD void diff_thread(const T* in, T* out, const T* nb, const DiffGeom& g, uint32_t z, uint32_t t) {
+  const uint32_t s = t / g.ppr, p = t - s * g.ppr;
+  if (s >= g.strips) return;
+  const uint32_t x0 = 8 * p, y0 = s * kDiffRows;
+  const uint32_t rows = g.Y - y0 < (uint32_t)kDiffRows ? g.Y - y0 : (uint32_t)kDiffRows;
+  const uint32_t cnt = g.X - x0 < 8u ? g.X - x0 : 8u;
+  const uint64_t plane = (uint64_t)z * g.frame;
+  const bool z_coded = z >= 1 && z < g.zend;
+  constexpr uintptr_t kMask = sizeof(T) * 8 - 1;
+  const bool aligned = (g.X & 7u) == 0 && (((uintptr_t)in | (uintptr_t)out | (uintptr_t)nb) & kMask) == 0;
+  const bool has_spill = g.Z > g.X + 1;
+
+  if (!aligned) {   // any row length, any buffer alignment: voxel by voxel
+    for (uint32_t k = 0; k < rows; ++k)
+      for (uint32_t j = 0; j < cnt; ++j)
+        out[plane + (uint64_t)(y0 + k) * g.X + x0 + j] = diff_voxel<T, DECODE>(in, nb, g, plane, z_coded, y0 + k, x0 + j);
+    return;
+  }
+  if (!z_coded) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t q = diff_covered(g, z, y, x + j) ? (uint32_t)acc[j] / 9u : 0u;
-      o.v[j] = DECODE ? (T)(v.v[j] + q) : (T)(v.v[j] - q);
-    }
-    *reinterpret_cast<Pack8<T>*>(out + i0) = o;
+    for (int k = 0; k < kDiffRows; ++k)
+      if ((uint32_t)k < rows) {
+        const uint64_t i = plane + (uint64_t)(y0 + k) * g.X + x0;
+        *reinterpret_cast<Pack8<T>*>(out + i) = *reinterpret_cast<const Pack8<T>*>(in + i);
+      }
     return;
   }
 
-  // general route: any alignment, packs that cross a row, the last row of a plane
-  uint64_t zz = z, yy = y, xx = x;
-  for (int j = 0; j < cnt; ++j) {
-    const uint64_t i = i0 + j;
-    uint32_t q = 0;
-    if (diff_covered(g, zz, yy, xx)) {
-      T sum = 0;
-      const uint64_t plane_begin = zz * g.frame;
-      for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-          const uint64_t k = (uint64_t)((int64_t)(i - g.frame) + (int64_t)dy * (int64_t)g.X + dx);
-          sum = (T)(sum + ((DECODE && k >= plane_begin) ? in[k] : nb[k]));
-        }
-      q = (uint32_t)sum / 9u;
+  T hm[8], hc[8], hp[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hm[j] = hc[j] = hp[j] = 0;
+  if (y0 >= 1) diff_row_sums<T, DECODE>(in, nb, g, plane, y0 - 1, x0, hm);
+  diff_row_sums<T, DECODE>(in, nb, g, plane, y0, x0, hc);
+#pragma unroll
+  for (int k = 0; k < kDiffRows; ++k) {
+    if ((uint32_t)k >= rows) break;
+    const uint32_t y = y0 + k;
+    const uint64_t i = plane + (uint64_t)y * g.X + x0;
+    if (y + 1 < g.Y) diff_row_sums<T, DECODE>(in, nb, g, plane, y + 1, x0, hp);
+    if (y + 1 == g.Y && has_spill) {          // the last row takes the end of a spilled run and looks into this plane's row 0
+      for (uint32_t j = 0; j < 8; ++j) out[i + j] = diff_voxel<T, DECODE>(in, nb, g, plane, true, y, x0 + j);
+    } else {
+      const Pack8<T> v = *reinterpret_cast<const Pack8<T>*>(in + i);
+      Pack8<T> o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const T sum = (T)(hm[j] + (T)(hc[j] + hp[j]));
+        const uint32_t q = diff_covered(g, y, x0 + j) ? (uint32_t)sum / 9u : 0u;   // rows 0 and Y-1 (no spill): never
+        o.v[j] = DECODE ? (T)(v.v[j] + q) : (T)(v.v[j] - q);
+      }
+      *reinterpret_cast<Pack8<T>*>(out + i) = o;
     }
-    out[i] = DECODE ? (T)(in[i] + q) : (T)(in[i] - q);
-    if (++xx == g.X) {
-      xx = 0;
-      if (++yy == g.Y) { yy = 0; ++zz; }
-    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { hm[j] = hc[j]; hc[j] = hp[j]; }
   }
 }
 

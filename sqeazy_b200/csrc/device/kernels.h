@@ -32,7 +32,7 @@ int k_bitshuffle8_decode(const uint8_t* in, uint8_t* out, uint64_t n, uint32_t b
 uint32_t bitshuffle_block_elems(uint32_t block_size, int elem_size);
 
 // diff.cu: diff3x3x1 (encoders/diff_scheme_impl.hpp:78-199), elem = bytes per voxel (1 or 2); in != out; 1 = shape refused
-bool diff_shape_supported(uint64_t Z, uint64_t Y, uint64_t X);
+bool diff_shape_supported(uint64_t Z, uint64_t Y, uint64_t X, int elem);
 int k_diff_encode(int elem, const void* in, void* out, uint64_t Z, uint64_t Y, uint64_t X, cudaStream_t st);
 int k_diff_decode(int elem, const void* in, void* out, uint64_t Z, uint64_t Y, uint64_t X, cudaStream_t st);
 

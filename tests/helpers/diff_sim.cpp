@@ -10,18 +10,21 @@
 template <typename T>
 static int run(int decode, const T* in, T* out, uint64_t Z, uint64_t Y, uint64_t X, int order) {
   using namespace sqyb;
-  if (!diff_shape_ok(Z, Y, X)) return 1;
+  if (!diff_shape_ok(Z, Y, X, (int)sizeof(T))) return 1;
   const DiffGeom g = diff_geom(Z, Y, X);
   std::memset(out, 0xA5, Z * Y * X * sizeof(T));
-  return diff_for_each_launch(decode != 0, g, [&](uint64_t begin, uint64_t end) {
-    const uint64_t threads = ((end - begin + 7) / 8 + 255) / 256 * 256;     // whole CTAs, like the grid
-    auto one = [&](uint64_t t) {
-      if (decode) diff_thread<T, true>(in, out, out, begin, end, g, t);
-      else diff_thread<T, false>(in, out, in, begin, end, g, t);
+  return diff_for_each_launch(decode != 0, g, [&](uint32_t z0, uint32_t planes) {
+    const uint32_t threads = (uint32_t)((diff_threads_per_plane(g) + 255) / 256 * 256);     // whole CTAs, like the grid
+    auto one = [&](uint32_t z, uint32_t t) {
+      if (decode) diff_thread<T, true>(in, out, out, g, z, t);
+      else diff_thread<T, false>(in, out, in, g, z, t);
     };
-    if (order == 0) for (uint64_t t = 0; t < threads; ++t) one(t);
-    else if (order == 1) for (uint64_t t = threads; t-- > 0;) one(t);
-    else { for (uint64_t t = 1; t < threads; t += 2) one(t); for (uint64_t t = 0; t < threads; t += 2) one(t); }
+    for (uint32_t zi = 0; zi < planes; ++zi) {
+      const uint32_t z = order == 1 ? z0 + planes - 1 - zi : z0 + zi;       // planes of one launch in any order too
+      if (order == 0) for (uint32_t t = 0; t < threads; ++t) one(z, t);
+      else if (order == 1) for (uint32_t t = threads; t-- > 0;) one(z, t);
+      else { for (uint32_t t = 1; t < threads; t += 2) one(z, t); for (uint32_t t = 0; t < threads; t += 2) one(z, t); }
+    }
     return 0;
   });
 }

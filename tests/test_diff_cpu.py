@@ -17,6 +17,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "golden_diff_v1.npz")
 SHAPES = [(8, 8, 8), (5, 7, 9), (16, 16, 16), (4, 6, 32), (9, 8, 8), (12, 9, 8), (17, 9, 8), (3, 3, 3), (3, 4, 2), (20, 5, 10), (7, 3, 40),
           (33, 64, 32), (17, 16, 8), (16, 24, 16), (33, 16, 16), (9, 5, 4), (32, 8, 64), (10, 11, 13), (6, 40, 24)]
 REFUSED = [(2, 8, 8), (1, 8, 8), (8, 2, 8), (8, 8, 1), (3, 3, 2), (18, 9, 8), (40000, 3, 3), (100, 4, 4)]
+REFUSED_U8 = [(129, 64, 64), (9, 130, 64), (9, 16, 136)]       # int8 coordinates in the reference's naive_sum
+BIG = [(24, 128, 128), (128, 20, 128), (130, 9, 72), (20, 129, 24), (6, 16, 136)]   # uint8: the first two only
+
+
+def _ok(port, shape, dtype):
+    return port.diff_supported(shape, np.dtype(dtype).itemsize)
 
 
 @pytest.fixture(scope="module")
@@ -56,8 +62,12 @@ def test_oracle_matches_golden(port, golden, case):
 
 
 @pytest.mark.parametrize("dtype", [np.uint16, np.uint8])
-@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("shape", SHAPES + BIG)
 def test_oracle_matches_reference_live(port, ref, shape, dtype):
+    if not _ok(port, shape, dtype):
+        with pytest.raises(ValueError):
+            port.diff(np.zeros(shape, dtype=dtype))
+        return
     for seed in (1, 2):
         a = _volume(shape, dtype, seed + 7 * shape[0])
         enc = ref.diff(a)
@@ -91,10 +101,23 @@ def test_refused_shapes(port, sim, shape):
     assert sim.sim_diff(0, None, None, ctypes.c_uint64(z), ctypes.c_uint64(y), ctypes.c_uint64(x), 2, 0) == 1
 
 
+@pytest.mark.parametrize("shape", REFUSED_U8)
+def test_refused_uint8_extents(port, ref, sim, shape):
+    """uint8 stacks: naive_sum keeps z, y, x in int8 (diff_scheme_utils.hpp:81-89); from 129 on the reference reads from
+    wrapped coordinates - what it returns there no longer follows its own rule on the shapes where it does not crash"""
+    z, y, x = shape
+    assert port.diff_supported(shape, 2) and not port.diff_supported(shape, 1)
+    with pytest.raises(ValueError):
+        port.diff(np.zeros(shape, dtype=np.uint8))
+    assert sim.sim_diff(0, None, None, ctypes.c_uint64(z), ctypes.c_uint64(y), ctypes.c_uint64(x), 1, 0) == 1
+
+
 @pytest.mark.parametrize("dtype", [np.uint16, np.uint8])
-@pytest.mark.parametrize("shape", SHAPES + [(24, 128, 128), (130, 9, 72)])
+@pytest.mark.parametrize("shape", SHAPES + BIG + [(7, 9, 520), (10, 23, 264)])
 def test_kernel_thread_program_replay(port, sim, shape, dtype):
     """every launch of the schedule, threads forward / backward / odd first, over poisoned output, any buffer alignment"""
+    if not _ok(port, shape, dtype):
+        pytest.skip("extent beyond the reference's int8 coordinates")
     z, y, x = shape
     n = z * y * x
     u64 = ctypes.c_uint64
@@ -128,3 +151,21 @@ def test_host_logic_names_and_bounds(sq):
     raw = 64 * 64 * 64 * 2
     assert sq.max_compressed_length("diff3x3x1->lz4", raw) >= sq.max_compressed_length("lz4", raw)
     assert sq.max_compressed_length("diff3x3x1", raw) > raw
+
+
+def test_reference_offset_kats_on_cube_of_8(port):
+    """tests/test_diff_scheme_impl.cpp:50-87 (offset_exact_last_plane) and :91-97 (9 traversed voxels), read off the coded set:
+    a constant stack codes to 0 wherever the filter is applied; the first voxel of every run is one of the reference's offsets"""
+    n = 8
+    enc = port.diff(np.full((n, n, n), 900, dtype=np.uint16)).ravel()      # 9 * 900 / 9 = 900 -> 0
+    coded = enc == 0
+    starts = np.flatnonzero(coded & ~np.roll(coded, 1))
+    assert starts.size == (n - 1) * (n - 2)
+    assert starts[0] == n * n + n + 1 and starts[1] == n * n + 2 * n + 1
+    assert starts[-1] == (n - 1) * n * n + (n - 2) * n + 1
+    runs = np.flatnonzero(coded & ~np.roll(coded, -1)) - starts + 1
+    assert np.all(runs == n - 2)                                              # non_halo_end(0) - non_halo_begin(0)
+    one = np.zeros((n, n, n), dtype=np.uint16)
+    one[3, 4, 4] = 9                                                          # seen by the 9 voxels below it, each gets 9 / 9
+    e1 = port.diff(one).astype(np.int32)
+    assert np.all(e1[4, 3:6, 3:6] == 65535) and (e1 != one).sum() == 9

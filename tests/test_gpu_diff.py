@@ -6,7 +6,7 @@ import pytest
 
 from oracle import oracle as orc
 from sqeazy_b200.synth import numpy_volume
-from test_diff_cpu import GOLDEN, REFUSED, SHAPES, _volume
+from test_diff_cpu import BIG, GOLDEN, REFUSED, REFUSED_U8, SHAPES, _volume
 from test_gpu_parity import dev, host16
 
 pytestmark = pytest.mark.gpu
@@ -17,8 +17,15 @@ def _host(t, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.uint16, np.uint8])
-@pytest.mark.parametrize("shape", SHAPES + [(24, 128, 128), (130, 9, 72), (40, 250, 264), (64, 256, 512)])
+@pytest.mark.parametrize("shape", SHAPES + BIG + [(7, 9, 520), (10, 23, 264), (40, 250, 264), (64, 256, 512)])
 def test_diff_stage_parity(sq, cuda, port, shape, dtype):
+    if not port.diff_supported(shape, np.dtype(dtype).itemsize):
+        assert shape in REFUSED_U8 + BIG + [(7, 9, 520), (10, 23, 264), (40, 250, 264), (64, 256, 512)] and dtype == np.uint8
+        assert not sq.diff_shape_supported(*shape, sizeof_voxel=1)
+        d = cuda.zeros(shape, dtype=cuda.uint8, device="cuda")
+        with pytest.raises(sq.SqeazyError):
+            sq.diff_device(d, cuda.zeros_like(d))
+        return
     tdt = cuda.int16 if dtype == np.uint16 else cuda.uint8
     poison = 0x7EEE if dtype == np.uint16 else 0xEE
     n = int(np.prod(shape))
@@ -113,7 +120,9 @@ def test_diff_pipelines(sq, cuda, port, ref, pipeline, shape):
 
 def test_diff_uint8_pipelines(sq, cuda, port, ref):
     rng = np.random.default_rng(8)
-    vol = np.clip(np.rint(20 + 2 * rng.standard_normal((9, 130, 264))), 0, 255).astype(np.uint8)
+    vol = np.clip(np.rint(20 + 2 * rng.standard_normal((9, 120, 128))), 0, 255).astype(np.uint8)
+    with pytest.raises(sq.SqeazyError):                      # 130 rows: beyond the reference's int8 coordinates
+        sq.encode_u8("diff3x3x1->lz4", np.zeros((9, 130, 64), dtype=np.uint8))
     for pipeline in ("diff3x3x1->lz4", "diff3x3x1", "diff3x3x1->bitswap1->lz4"):
         blob = sq.encode_u8(pipeline, vol)
         assert np.array_equal(sq.decode_u8(blob).reshape(vol.shape), vol)
