@@ -23,18 +23,21 @@ namespace sqyb {
 
 namespace {
 
+constexpr int kDiffThreads = 128;   // a 2048 x 2048 plane = 1024 CTAs: one wave of the 148 SMs at 7 CTAs per SM
+
 template <typename T, bool DECODE>
-__global__ void __launch_bounds__(256) diff_kernel(const T* in, T* out, const T* nb, DiffGeom g, uint32_t z0) {
+__global__ void __launch_bounds__(kDiffThreads) diff_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ nb, DiffGeom g,
+                                                            uint32_t z0) {
   diff_thread<T, DECODE>(in, out, nb, g, z0 + blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 template <typename T, bool DECODE>
 int launch_planes(const T* in, T* out, const T* nb, const DiffGeom& g, uint32_t z0, uint32_t planes, cudaStream_t st) {
   if (planes == 0) return 0;
-  const uint64_t blocks = (diff_threads_per_plane(g) + 255) / 256;     // <= 2^19
+  const uint64_t blocks = (diff_threads_per_plane(g) + kDiffThreads - 1) / kDiffThreads;     // <= 2^20
   for (uint32_t done = 0; done < planes; done += 65535) {              // gridDim.y limit (not reached: Z <= 32767)
     const uint32_t now = planes - done < 65535 ? planes - done : 65535;
-    diff_kernel<T, DECODE><<<dim3((unsigned)blocks, now), 256, 0, st>>>(in, out, nb, g, z0 + done);
+    diff_kernel<T, DECODE><<<dim3((unsigned)blocks, now), kDiffThreads, 0, st>>>(in, out, nb, g, z0 + done);
     SQYB_COUNT_LAUNCH(1);
   }
   return (int)cudaGetLastError();

@@ -9,6 +9,11 @@
 #else
 #define SQYB_HD inline
 #endif
+// `in`, `out` and `nb` of one launch never touch the same voxel through two names: encode reads `in` (= `nb`) and writes
+// `out`; decode reads the stored plane through `in`, the decoded plane before it through `nb` and writes the plane itself
+// through `out` (`nb` and `out` are the same buffer, one plane apart). Saying so lets the loads of a strip leave together
+// instead of waiting behind the stores of the row before.
+#define SQYB_RESTRICT __restrict__
 
 namespace sqyb {
 
@@ -68,7 +73,7 @@ SQYB_HD bool diff_covered(const DiffGeom& g, uint32_t y, uint32_t x) {
 // one voxel the slow way: linear offsets exactly as naive_sum forms them. In decode a neighbour inside the plane being
 // written (row 0, reached by the spilled end of the last run) is never coded and is taken from `in`.
 template <typename T, bool DECODE>
-SQYB_HD T diff_voxel(const T* in, const T* nb, const DiffGeom& g, uint64_t plane, bool z_coded, uint32_t y, uint32_t x) {
+SQYB_HD T diff_voxel(const T* SQYB_RESTRICT in, const T* SQYB_RESTRICT nb, const DiffGeom& g, uint64_t plane, bool z_coded, uint32_t y, uint32_t x) {
   const uint64_t i = plane + (uint64_t)y * g.X + x;
   uint32_t q = 0;
   if (z_coded && diff_covered(g, y, x)) {
@@ -83,23 +88,73 @@ SQYB_HD T diff_voxel(const T* in, const T* nb, const DiffGeom& g, uint64_t plane
   return DECODE ? (T)(in[i] + q) : (T)(in[i] - q);
 }
 
-// 3-tap sums (in the voxel type) of row r of the previous plane at x0 .. x0+7; rows start 16-byte aligned here
-template <typename T, bool DECODE>
-SQYB_HD void diff_row_sums(const T* in, const T* nb, const DiffGeom& g, uint64_t plane, uint32_t r, uint32_t x0, T* h) {
-  const uint64_t row = plane - g.frame + (uint64_t)r * g.X + x0;
-  const Pack8<T> c = *reinterpret_cast<const Pack8<T>*>(nb + row);
-  const T left = row > 0 ? nb[row - 1] : (T)0;          // row == 0: z = 1, r = 0, x0 = 0 - feeds only voxels that are not coded
-  const T right = (DECODE && row + 8 >= plane) ? in[row + 8] : nb[row + 8];   // r = Y-1 at the row end: row 0 of this plane
-  h[0] = (T)(left + (T)(c.v[0] + c.v[1]));
+// ---- packed lanes: 8 voxels = 4 words of 2 x uint16 or 2 words of 4 x uint8; every lane wraps on its own
+template <typename T> struct alignas(sizeof(T) * 8) DiffWords { uint32_t w[2 * sizeof(T)]; };
+
+template <typename T> struct DiffLanes;
+template <> struct DiffLanes<uint16_t> {
+  static constexpr int kBits = 16, kPerWord = 2, kWords = 4;
+  static constexpr uint32_t kLaneMask = 0xffffu;
+  static SQYB_HD uint32_t add(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __vadd2(a, b);                                    // VIADD.16x2
+#else
+    return ((a + b) & 0xffffu) | ((((a >> 16) + (b >> 16)) & 0xffffu) << 16);
+#endif
+  }
+  static SQYB_HD uint32_t sub(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __vsub2(a, b);
+#else
+    return ((a - b) & 0xffffu) | ((((a >> 16) - (b >> 16)) & 0xffffu) << 16);
+#endif
+  }
+  static SQYB_HD uint32_t div9(uint32_t a) { return ((a & 0xffffu) / 9u) | (((a >> 16) / 9u) << 16); }
+};
+template <> struct DiffLanes<uint8_t> {
+  static constexpr int kBits = 8, kPerWord = 4, kWords = 2;
+  static constexpr uint32_t kLaneMask = 0xffu;
+  static SQYB_HD uint32_t add(uint32_t a, uint32_t b) {      // carries stopped at the lane tops
+    return ((a & 0x7f7f7f7fu) + (b & 0x7f7f7f7fu)) ^ ((a ^ b) & 0x80808080u);
+  }
+  static SQYB_HD uint32_t sub(uint32_t a, uint32_t b) {      // borrows stopped at the lane tops
+    return ((a | 0x80808080u) - (b & 0x7f7f7f7fu)) ^ ((a ^ ~b) & 0x80808080u);
+  }
+  static SQYB_HD uint32_t div9(uint32_t a) {                 // x * 57 >> 9 == x / 9 for x < 256
+    uint32_t r = 0;
 #pragma unroll
-  for (int j = 1; j < 7; ++j) h[j] = (T)(c.v[j - 1] + (T)(c.v[j] + c.v[j + 1]));
-  h[7] = (T)(c.v[6] + (T)(c.v[7] + right));
+    for (int k = 0; k < 4; ++k) r |= ((((a >> (8 * k)) & 0xffu) * 57u) >> 9) << (8 * k);
+    return r;
+  }
+};
+
+// 3-tap sums (per lane, in the voxel type) of row r of the previous plane at x0 .. x0+7; rows start 16-byte aligned here.
+// The voxel in front of x0 and the one behind x0+7 come by linear offsets like naive_sum's: at a row end they are the
+// neighbouring row's.
+template <typename T, bool DECODE>
+SQYB_HD void diff_row_sums(const T* SQYB_RESTRICT in, const T* SQYB_RESTRICT nb, const DiffGeom& g, uint64_t plane, uint32_t r, uint32_t x0,
+                           uint32_t* h) {
+  using L = DiffLanes<T>;
+  constexpr int W = L::kWords;
+  const uint64_t row = plane - g.frame + (uint64_t)r * g.X + x0;
+  const DiffWords<T> c = *reinterpret_cast<const DiffWords<T>*>(nb + row);
+  const uint32_t left = row > 0 ? (uint32_t)nb[row - 1] : 0u;   // row == 0: z = 1, r = 0, x0 = 0 - feeds only voxels that are not coded
+  // r = Y-1 at the row end: the voxel behind it is row 0 of the plane being written - never coded, so `in` has it
+  const uint32_t right = (DECODE && row + 8 >= plane) ? (uint32_t)in[row + 8] : (uint32_t)nb[row + 8];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const uint32_t before = w > 0 ? c.w[w - 1] : left << (32 - L::kBits);     // its top lane = the voxel in front of this word
+    const uint32_t after = w + 1 < W ? c.w[w + 1] : right;                      // its bottom lane = the voxel behind it
+    const uint32_t l = (c.w[w] << L::kBits) | (before >> (32 - L::kBits));
+    const uint32_t rr = (c.w[w] >> L::kBits) | (after << (32 - L::kBits));
+    h[w] = L::add(c.w[w], L::add(l, rr));
+  }
 }
 
 // Thread t of plane z: 8 voxels x kDiffRows rows. `nb` holds the neighbours: `in` itself for encode, `out` for decode
 // (one plane per launch: every neighbour lies in the plane before).
 template <typename T, bool DECODE>
-SQYB_HD void diff_thread(const T* in, T* out, const T* nb, const DiffGeom& g, uint32_t z, uint32_t t) {
+SQYB_HD void diff_thread(const T* SQYB_RESTRICT in, T* SQYB_RESTRICT out, const T* SQYB_RESTRICT nb, const DiffGeom& g, uint32_t z, uint32_t t) {
   const uint32_t s = t / g.ppr, p = t - s * g.ppr;
   if (s >= g.strips) return;
   const uint32_t x0 = 8 * p, y0 = s * kDiffRows;
@@ -127,32 +182,51 @@ SQYB_HD void diff_thread(const T* in, T* out, const T* nb, const DiffGeom& g, ui
     return;
   }
 
-  T hm[8], hc[8], hp[8];
+  // The strip in packed lanes (two uint16 or four uint8 voxels per 32-bit word, voxel j of a pack in lane j): the kernel
+  // is bound by its instruction count, not by HBM, so every add, the /9 and the select work on whole words.
+  using L = DiffLanes<T>;
+  constexpr int W = L::kWords;
+  uint32_t own_mask[W], spill_mask[W];                         // lanes of this pack a coded row covers (diff_covered)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) hm[j] = hc[j] = hp[j] = 0;
+  for (int w = 0; w < W; ++w) own_mask[w] = spill_mask[w] = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t x = x0 + (uint32_t)j, lane = L::kLaneMask << (L::kBits * (j % L::kPerWord));
+    if (x >= 1 && x + 1 < g.Z) own_mask[j / L::kPerWord] |= lane;
+    if (x + g.X + 1 < g.Z) spill_mask[j / L::kPerWord] |= lane;
+  }
+  const bool last_row_spills = has_spill && y0 + rows == g.Y;   // that row looks into this plane's row 0: voxel by voxel below
+
+  uint32_t hm[W], hc[W], hp[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) hm[w] = hc[w] = hp[w] = 0;
   if (y0 >= 1) diff_row_sums<T, DECODE>(in, nb, g, plane, y0 - 1, x0, hm);
   diff_row_sums<T, DECODE>(in, nb, g, plane, y0, x0, hc);
 #pragma unroll
   for (int k = 0; k < kDiffRows; ++k) {
     if ((uint32_t)k >= rows) break;
-    const uint32_t y = y0 + k;
+    const uint32_t y = y0 + (uint32_t)k;
     const uint64_t i = plane + (uint64_t)y * g.X + x0;
     if (y + 1 < g.Y) diff_row_sums<T, DECODE>(in, nb, g, plane, y + 1, x0, hp);
-    if (y + 1 == g.Y && has_spill) {          // the last row takes the end of a spilled run and looks into this plane's row 0
-      for (uint32_t j = 0; j < 8; ++j) out[i + j] = diff_voxel<T, DECODE>(in, nb, g, plane, true, y, x0 + j);
-    } else {
-      const Pack8<T> v = *reinterpret_cast<const Pack8<T>*>(in + i);
-      Pack8<T> o;
+    if (!(last_row_spills && y + 1 == g.Y)) {
+      const DiffWords<T> v = *reinterpret_cast<const DiffWords<T>*>(in + i);
+      const bool own_row = y >= 1 && y + 1 < g.Y, spill_row = y >= 2;      // rows 0 and Y-1 (no spill): nothing coded
+      DiffWords<T> o;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const T sum = (T)(hm[j] + (T)(hc[j] + hp[j]));
-        const uint32_t q = diff_covered(g, y, x0 + j) ? (uint32_t)sum / 9u : 0u;   // rows 0 and Y-1 (no spill): never
-        o.v[j] = DECODE ? (T)(v.v[j] + q) : (T)(v.v[j] - q);
+      for (int w = 0; w < W; ++w) {
+        const uint32_t mask = (own_row ? own_mask[w] : 0u) | (spill_row ? spill_mask[w] : 0u);
+        const uint32_t q = L::div9(L::add(hm[w], L::add(hc[w], hp[w]))) & mask;
+        o.w[w] = DECODE ? L::add(v.w[w], q) : L::sub(v.w[w], q);
       }
-      *reinterpret_cast<Pack8<T>*>(out + i) = o;
+      *reinterpret_cast<DiffWords<T>*>(out + i) = o;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { hm[j] = hc[j]; hc[j] = hp[j]; }
+    for (int w = 0; w < W; ++w) { hm[w] = hc[w]; hc[w] = hp[w]; }
+  }
+  if (last_row_spills) {
+#pragma unroll 1
+    for (uint32_t j = 0; j < 8; ++j)
+      out[plane + (uint64_t)(g.Y - 1) * g.X + x0 + j] = diff_voxel<T, DECODE>(in, nb, g, plane, true, g.Y - 1, x0 + j);
   }
 }
 
