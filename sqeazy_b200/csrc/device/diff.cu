@@ -23,11 +23,17 @@ namespace sqyb {
 
 namespace {
 
-constexpr int kDiffThreads = 128;   // a 2048 x 2048 plane = 1024 CTAs: one wave of the 148 SMs at 7 CTAs per SM
+constexpr int kDiffThreads = 128;   // 12 CTAs per SM (<= 40 registers): a 2048 x 2048 plane = 1024 CTAs is one wave of the 148 SMs
 
 template <typename T, bool DECODE>
-__global__ void __launch_bounds__(kDiffThreads) diff_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ nb, DiffGeom g,
+__global__ void __launch_bounds__(kDiffThreads, 12) diff_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ nb, DiffGeom g,
                                                             uint32_t z0) {
+  if (DECODE) {
+    // decode launches follow each other plane by plane with programmatic stream serialization: the CTAs of the next plane
+    // are placed while this one drains and wait here until the plane before them is complete and visible
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
   diff_thread<T, DECODE>(in, out, nb, g, z0 + blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
@@ -37,7 +43,21 @@ int launch_planes(const T* in, T* out, const T* nb, const DiffGeom& g, uint32_t 
   const uint64_t blocks = (diff_threads_per_plane(g) + kDiffThreads - 1) / kDiffThreads;     // <= 2^20
   for (uint32_t done = 0; done < planes; done += 65535) {              // gridDim.y limit (not reached: Z <= 32767)
     const uint32_t now = planes - done < 65535 ? planes - done : 65535;
-    diff_kernel<T, DECODE><<<dim3((unsigned)blocks, now), kDiffThreads, 0, st>>>(in, out, nb, g, z0 + done);
+    if (DECODE) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)blocks, now);
+      cfg.blockDim = dim3(kDiffThreads);
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      const cudaError_t e = cudaLaunchKernelEx(&cfg, diff_kernel<T, DECODE>, in, out, nb, g, z0 + done);
+      if (e != cudaSuccess) return (int)e;
+    } else {
+      diff_kernel<T, DECODE><<<dim3((unsigned)blocks, now), kDiffThreads, 0, st>>>(in, out, nb, g, z0 + done);
+    }
     SQYB_COUNT_LAUNCH(1);
   }
   return (int)cudaGetLastError();

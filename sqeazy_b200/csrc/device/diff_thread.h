@@ -128,19 +128,18 @@ template <> struct DiffLanes<uint8_t> {
   }
 };
 
-// 3-tap sums (per lane, in the voxel type) of row r of the previous plane at x0 .. x0+7; rows start 16-byte aligned here.
-// The voxel in front of x0 and the one behind x0+7 come by linear offsets like naive_sum's: at a row end they are the
-// neighbouring row's.
-template <typename T, bool DECODE>
-SQYB_HD void diff_row_sums(const T* SQYB_RESTRICT in, const T* SQYB_RESTRICT nb, const DiffGeom& g, uint64_t plane, uint32_t r, uint32_t x0,
-                           uint32_t* h) {
+// 3-tap sums (per lane, in the voxel type) of 8 voxels of the previous plane starting at `p` (16-byte aligned). The voxel
+// in front of p[0] and the one behind p[7] come by linear offsets like naive_sum's: at a row end they are the neighbouring
+// row's. `p == nb` only for z = 1, first row, x0 = 0: the voxel in front does not exist and feeds no coded voxel (p[0] is
+// read instead). `behind` is where the voxel after p[7] is read from: p + 8, except for the end of the last row in decode -
+// that voxel is row 0 of the plane being written, never coded, so `in` has it.
+template <typename T>
+SQYB_HD void diff_row_sums(const T* SQYB_RESTRICT p, const T* SQYB_RESTRICT nb, const T* SQYB_RESTRICT behind, uint32_t* h) {
   using L = DiffLanes<T>;
   constexpr int W = L::kWords;
-  const uint64_t row = plane - g.frame + (uint64_t)r * g.X + x0;
-  const DiffWords<T> c = *reinterpret_cast<const DiffWords<T>*>(nb + row);
-  const uint32_t left = row > 0 ? (uint32_t)nb[row - 1] : 0u;   // row == 0: z = 1, r = 0, x0 = 0 - feeds only voxels that are not coded
-  // r = Y-1 at the row end: the voxel behind it is row 0 of the plane being written - never coded, so `in` has it
-  const uint32_t right = (DECODE && row + 8 >= plane) ? (uint32_t)in[row + 8] : (uint32_t)nb[row + 8];
+  const DiffWords<T> c = *reinterpret_cast<const DiffWords<T>*>(p);
+  const uint32_t left = (uint32_t)p[p != nb ? -1 : 0];
+  const uint32_t right = (uint32_t)*behind;
 #pragma unroll
   for (int w = 0; w < W; ++w) {
     const uint32_t before = w > 0 ? c.w[w - 1] : left << (32 - L::kBits);     // its top lane = the voxel in front of this word
@@ -183,45 +182,63 @@ SQYB_HD void diff_thread(const T* SQYB_RESTRICT in, T* SQYB_RESTRICT out, const 
   }
 
   // The strip in packed lanes (two uint16 or four uint8 voxels per 32-bit word, voxel j of a pack in lane j): the kernel
-  // is bound by its instruction count, not by HBM, so every add, the /9 and the select work on whole words.
+  // is bound by its instruction count, not by HBM, so every add, the /9 and the select work on whole words, addresses
+  // advance by a row, and the lanes a row covers are two masks ANDed with a per-row all-or-nothing word.
   using L = DiffLanes<T>;
   constexpr int W = L::kWords;
   uint32_t own_mask[W], spill_mask[W];                         // lanes of this pack a coded row covers (diff_covered)
+  if (x0 >= 1 && x0 + 8 < g.Z) {                                // inside the run of the row: all of them
 #pragma unroll
-  for (int w = 0; w < W; ++w) own_mask[w] = spill_mask[w] = 0;
+    for (int w = 0; w < W; ++w) own_mask[w] = 0xffffffffu;
+  } else {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint32_t x = x0 + (uint32_t)j, lane = L::kLaneMask << (L::kBits * (j % L::kPerWord));
-    if (x >= 1 && x + 1 < g.Z) own_mask[j / L::kPerWord] |= lane;
-    if (x + g.X + 1 < g.Z) spill_mask[j / L::kPerWord] |= lane;
+    for (int w = 0; w < W; ++w) own_mask[w] = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t x = x0 + (uint32_t)j;
+      if (x >= 1 && x + 1 < g.Z) own_mask[j / L::kPerWord] |= L::kLaneMask << (L::kBits * (j % L::kPerWord));
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < W; ++w) spill_mask[w] = 0;
+  if (has_spill) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (x0 + (uint32_t)j + g.X + 1 < g.Z) spill_mask[j / L::kPerWord] |= L::kLaneMask << (L::kBits * (j % L::kPerWord));
   }
   const bool last_row_spills = has_spill && y0 + rows == g.Y;   // that row looks into this plane's row 0: voxel by voxel below
 
+  const uint64_t first = plane + (uint64_t)y0 * g.X + x0;       // the strip's first pack; rows are g.X apart
+  const T* pi = in + first;
+  T* po = out + first;
+  const T* pn = nb + (first - g.frame);                         // the same pack one plane back
+  const bool row_end = x0 + 8 == g.X;
   uint32_t hm[W], hc[W], hp[W];
 #pragma unroll
   for (int w = 0; w < W; ++w) hm[w] = hc[w] = hp[w] = 0;
-  if (y0 >= 1) diff_row_sums<T, DECODE>(in, nb, g, plane, y0 - 1, x0, hm);
-  diff_row_sums<T, DECODE>(in, nb, g, plane, y0, x0, hc);
+  if (y0 >= 1) diff_row_sums<T>(pn - g.X, nb, pn - g.X + 8, hm);
+  diff_row_sums<T>(pn, nb, (DECODE && row_end && y0 + 1 == g.Y) ? in + plane : pn + 8, hc);
 #pragma unroll
   for (int k = 0; k < kDiffRows; ++k) {
     if ((uint32_t)k >= rows) break;
     const uint32_t y = y0 + (uint32_t)k;
-    const uint64_t i = plane + (uint64_t)y * g.X + x0;
-    if (y + 1 < g.Y) diff_row_sums<T, DECODE>(in, nb, g, plane, y + 1, x0, hp);
+    if (y + 1 < g.Y) diff_row_sums<T>(pn + g.X, nb, (DECODE && row_end && y + 2 == g.Y) ? in + plane : pn + g.X + 8, hp);
     if (!(last_row_spills && y + 1 == g.Y)) {
-      const DiffWords<T> v = *reinterpret_cast<const DiffWords<T>*>(in + i);
-      const bool own_row = y >= 1 && y + 1 < g.Y, spill_row = y >= 2;      // rows 0 and Y-1 (no spill): nothing coded
+      const DiffWords<T> v = *reinterpret_cast<const DiffWords<T>*>(pi);
+      const uint32_t own_row = (y >= 1 && y + 1 < g.Y) ? 0xffffffffu : 0u;      // rows 0 and Y-1 (no spill): nothing coded
+      const uint32_t spill_row = y >= 2 ? 0xffffffffu : 0u;
       DiffWords<T> o;
 #pragma unroll
       for (int w = 0; w < W; ++w) {
-        const uint32_t mask = (own_row ? own_mask[w] : 0u) | (spill_row ? spill_mask[w] : 0u);
+        const uint32_t mask = (own_mask[w] & own_row) | (spill_mask[w] & spill_row);
         const uint32_t q = L::div9(L::add(hm[w], L::add(hc[w], hp[w]))) & mask;
         o.w[w] = DECODE ? L::add(v.w[w], q) : L::sub(v.w[w], q);
       }
-      *reinterpret_cast<DiffWords<T>*>(out + i) = o;
+      *reinterpret_cast<DiffWords<T>*>(po) = o;
     }
 #pragma unroll
     for (int w = 0; w < W; ++w) { hm[w] = hc[w]; hc[w] = hp[w]; }
+    pi += g.X; po += g.X; pn += g.X;
   }
   if (last_row_spills) {
 #pragma unroll 1
