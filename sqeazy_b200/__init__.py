@@ -40,6 +40,9 @@ SQYX_SYMBOLS = [
     "sqyx_diff_device", "sqyx_diff_shape_supported",
 ]
 
+# include/sqeazy_h5_filter.h: what HDF5 looks up in a filter plugin
+H5_SYMBOLS = ["H5Z_filter_sqy", "H5PLget_plugin_type", "H5PLget_plugin_info"]
+
 _lib = None
 
 
@@ -334,6 +337,49 @@ def diff_device(src, dst, decode: bool = False, stream=None):
 
 def diff_shape_supported(z: int, y: int, x: int, sizeof_voxel: int = 2) -> bool:
     return bool(lib().sqyx_diff_shape_supported(c_int(sizeof_voxel), c_long(z), c_long(y), c_long(x)))
+
+
+H5Z_FILTER_SQY = 0o1307            # sqeazy_h5_filter.hpp:211 writes the id as the octal literal 01307 = 711
+H5Z_FLAG_REVERSE = 0x0100
+
+
+class H5ZClass2(ctypes.Structure):
+    """H5Z_class2_t as H5PLget_plugin_info() returns it (include/sqeazy_h5_filter.h)"""
+    _fields_ = [("version", c_int), ("id", c_int), ("encoder_present", c_uint), ("decoder_present", c_uint), ("name", c_char_p),
+                ("can_apply", c_void_p), ("set_local", c_void_p), ("filter", c_void_p)]
+
+
+def h5_plugin_info() -> H5ZClass2:
+    L = lib()
+    L.H5PLget_plugin_info.restype = POINTER(H5ZClass2)
+    return L.H5PLget_plugin_info().contents
+
+
+def h5_filter(chunk: np.ndarray, cd_header: bytes = b"", reverse: bool = False):
+    """Calls H5Z_filter_sqy the way HDF5 does: the chunk lives in a malloc()ed buffer that the filter replaces.
+    cd_header = the sqeazy header text the dataset was created with (hdf5_utils.hpp:728-737 packs it into cd_values).
+    Returns the new chunk as a uint8 array, or None when the filter reports failure (returns 0)."""
+    L = lib()
+    libc = ctypes.CDLL(None)
+    libc.malloc.restype = c_void_p
+    libc.malloc.argtypes = [ctypes.c_size_t]
+    libc.free.argtypes = [c_void_p]
+    L.H5Z_filter_sqy.restype = ctypes.c_size_t
+    L.H5Z_filter_sqy.argtypes = [c_uint, ctypes.c_size_t, c_void_p, ctypes.c_size_t, POINTER(ctypes.c_size_t), POINTER(c_void_p)]
+    raw = np.ascontiguousarray(chunk).view(np.uint8).ravel()
+    buf = c_void_p(libc.malloc(max(raw.size, 1)))
+    ctypes.memmove(buf, raw.ctypes.data, raw.size)
+    size = ctypes.c_size_t(raw.size)
+    cd = np.zeros((len(cd_header) + 3) // 4, dtype=np.uint32)
+    cd.view(np.uint8)[: len(cd_header)] = np.frombuffer(cd_header, dtype=np.uint8)
+    n = L.H5Z_filter_sqy(c_uint(H5Z_FLAG_REVERSE if reverse else 0), cd.size, cd.ctypes.data_as(c_void_p) if cd.size else None,
+                         raw.size, ctypes.byref(size), ctypes.byref(buf))
+    out = None
+    if n:
+        assert size.value == n
+        out = np.ctypeslib.as_array(ctypes.cast(buf, POINTER(ctypes.c_uint8)), shape=(n,)).copy()
+    libc.free(buf)
+    return out
 
 
 def remove_background_device(src, dst, threshold: int, stream=None):

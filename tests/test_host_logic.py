@@ -19,7 +19,10 @@ def test_library_exports_every_declared_symbol(sq):
         text = open(os.path.join(os.path.dirname(sq.LIB_PATH), "..", "include", hdr)).read()
         declared |= set(re.findall(r"\b(SQY_\w+|sqyx_\w+)\s*\(", text))
     assert declared == set(sq.SQY_SYMBOLS) | set(sq.SQYX_SYMBOLS)
-    for name in declared:
+    text = open(os.path.join(os.path.dirname(sq.LIB_PATH), "..", "include", "sqeazy_h5_filter.h")).read()
+    h5 = set(re.findall(r"\b(H5Z_filter_sqy|H5PLget_\w+)\s*\(", text))
+    assert h5 == set(sq.H5_SYMBOLS)
+    for name in declared | h5:
         assert getattr(L, name) is not None
 
 
