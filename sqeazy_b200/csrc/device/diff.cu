@@ -12,8 +12,8 @@
 // coordinates it keeps for uint16 / uint8 stacks) are refused.
 //
 // Encode is one launch over the volume: 4 B/voxel of HBM traffic, the previous plane is re-read from L2. A thread walks a
-// strip of 8 voxels x kDiffRows rows and keeps the 3-tap row sums of the previous plane it can reuse (kDiffRows + 2 row
-// loads of 16 bytes + 2 halo voxels for kDiffRows output rows). Decode is a recurrence along z only: one launch per coded
+// strip of 8 voxels x R rows (8 in encode, 4 in decode) and keeps the 3-tap row sums of the previous plane it can reuse
+// (R + 2 row loads of 16 bytes + 2 halo voxels for R output rows). Decode is a recurrence along z only: one launch per coded
 // plane (all voxels of a plane are independent), planes 0 and >= min(X, Z) are copies.
 #include "common.cuh"
 #include "diff_thread.h"
@@ -66,7 +66,7 @@ int launch_planes(const T* in, T* out, const T* nb, const DiffGeom& g, uint32_t 
 template <typename T>
 int diff_run(bool decode, const T* in, T* out, uint64_t Z, uint64_t Y, uint64_t X, cudaStream_t st) {
   if (!diff_shape_ok(Z, Y, X, (int)sizeof(T)) || in == out) return 1;
-  const DiffGeom g = diff_geom(Z, Y, X);
+  const DiffGeom g = diff_geom(Z, Y, X, decode);
   return diff_for_each_launch(decode, g, [&](uint32_t z0, uint32_t planes) {
     return decode ? launch_planes<T, true>(in, out, out, g, z0, planes, st) : launch_planes<T, false>(in, out, in, g, z0, planes, st);
   });

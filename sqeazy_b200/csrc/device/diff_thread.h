@@ -17,22 +17,25 @@
 
 namespace sqyb {
 
-constexpr int kDiffRows = 4;   // rows of a strip: a thread walks 8 voxels x kDiffRows rows and keeps the row sums it can reuse
+// rows of a strip: a thread walks 8 voxels x R rows and keeps the row sums it can reuse (R + 2 row loads for R output rows).
+// Encode is one big launch: tall strips. A decode launch is one plane: shorter strips keep enough threads in it.
+constexpr int kDiffRowsEncode = 8, kDiffRowsDecode = 4;
+constexpr int diff_rows(bool decode) { return decode ? kDiffRowsDecode : kDiffRowsEncode; }
 
 template <typename T> struct alignas(sizeof(T) * 8) Pack8 { T v[8]; };
 
 struct DiffGeom {
   uint32_t Z, Y, X, zend;   // zend = min(X, Z): the planes the reference codes are 1 .. zend-1
   uint64_t frame;           // Y * X
-  uint32_t ppr, strips;     // 8-voxel packs per row, strips of kDiffRows rows per plane
+  uint32_t ppr, strips;     // 8-voxel packs per row, strips of diff_rows() rows per plane
 };
 
-inline DiffGeom diff_geom(uint64_t Z, uint64_t Y, uint64_t X) {
+inline DiffGeom diff_geom(uint64_t Z, uint64_t Y, uint64_t X, bool decode) {
   DiffGeom g;
   g.Z = (uint32_t)Z; g.Y = (uint32_t)Y; g.X = (uint32_t)X; g.zend = (uint32_t)(X < Z ? X : Z);
   g.frame = Y * X;
   g.ppr = (uint32_t)((X + 7) / 8);
-  g.strips = (uint32_t)((Y + kDiffRows - 1) / kDiffRows);
+  g.strips = (uint32_t)((Y + diff_rows(decode) - 1) / diff_rows(decode));
   return g;
 }
 
@@ -150,10 +153,11 @@ SQYB_HD void diff_row_sums(const T* SQYB_RESTRICT p, const T* SQYB_RESTRICT nb, 
   }
 }
 
-// Thread t of plane z: 8 voxels x kDiffRows rows. `nb` holds the neighbours: `in` itself for encode, `out` for decode
+// Thread t of plane z: 8 voxels x diff_rows(DECODE) rows. `nb` holds the neighbours: `in` itself for encode, `out` for decode
 // (one plane per launch: every neighbour lies in the plane before).
 template <typename T, bool DECODE>
 SQYB_HD void diff_thread(const T* SQYB_RESTRICT in, T* SQYB_RESTRICT out, const T* SQYB_RESTRICT nb, const DiffGeom& g, uint32_t z, uint32_t t) {
+  constexpr int kDiffRows = DECODE ? kDiffRowsDecode : kDiffRowsEncode;
   const uint32_t s = t / g.ppr, p = t - s * g.ppr;
   if (s >= g.strips) return;
   const uint32_t x0 = 8 * p, y0 = s * kDiffRows;

@@ -11,7 +11,7 @@ template <typename T>
 static int run(int decode, const T* in, T* out, uint64_t Z, uint64_t Y, uint64_t X, int order) {
   using namespace sqyb;
   if (!diff_shape_ok(Z, Y, X, (int)sizeof(T))) return 1;
-  const DiffGeom g = diff_geom(Z, Y, X);
+  const DiffGeom g = diff_geom(Z, Y, X, decode != 0);
   std::memset(out, 0xA5, Z * Y * X * sizeof(T));
   return diff_for_each_launch(decode != 0, g, [&](uint32_t z0, uint32_t planes) {
     const uint32_t threads = (uint32_t)((diff_threads_per_plane(g) + 255) / 256 * 256);     // whole CTAs, like the grid
