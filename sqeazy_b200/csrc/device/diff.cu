@@ -26,7 +26,7 @@ namespace {
 constexpr int kDiffThreads = 128;   // 12 CTAs per SM (<= 40 registers): a 2048 x 2048 plane = 1024 CTAs is one wave of the 148 SMs
 
 template <typename T, bool DECODE>
-__global__ void __launch_bounds__(kDiffThreads, 12) diff_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ nb, DiffGeom g,
+__global__ void __launch_bounds__(kDiffThreads, DECODE ? 8 : 12) diff_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ nb, DiffGeom g,
                                                             uint32_t z0) {
   if (DECODE) {
     // decode launches follow each other plane by plane with programmatic stream serialization: the CTAs of the next plane

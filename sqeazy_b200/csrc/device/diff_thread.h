@@ -212,7 +212,71 @@ SQYB_HD void diff_thread(const T* SQYB_RESTRICT in, T* SQYB_RESTRICT out, const 
   }
   const bool last_row_spills = has_spill && y0 + rows == g.Y;   // that row looks into this plane's row 0: voxel by voxel below
 
-  const uint64_t first = plane + (uint64_t)y0 * g.X + x0;       // the strip's first pack; rows are g.X apart
+  if (DECODE) {
+    // A decode launch is one plane = one wave of CTAs: nothing hides a thread's memory round trips, so all loads of the strip
+    // leave together (R + 2 packs of the plane before with the voxels at their ends, R packs of the stored plane) and the
+    // arithmetic starts when they are back - one round trip per strip instead of one per row.
+    const uint64_t first = plane + (uint64_t)y0 * g.X + x0;
+    const T* pi = in + first;
+    T* po = out + first;
+    const T* pn = nb + (first - g.frame) - g.X;                 // row y0 - 1 of the plane before
+    const bool row_end = x0 + 8 == g.X;
+    DiffWords<T> c[kDiffRows + 2], v[kDiffRows];
+    uint32_t lf[kDiffRows + 2], rt[kDiffRows + 2];
+#pragma unroll
+    for (int r = 0; r < kDiffRows + 2; ++r) {
+      const uint32_t yy = y0 + (uint32_t)r;                     // this is row yy - 1
+      if (yy >= 1 && yy <= g.Y) {
+        const T* p = pn + (uint64_t)r * g.X;
+        c[r] = *reinterpret_cast<const DiffWords<T>*>(p);
+        lf[r] = (uint32_t)p[p != nb ? -1 : 0];
+        rt[r] = (uint32_t)((row_end && yy == g.Y) ? in[plane] : p[8]);   // behind the last row: row 0 of this plane, from `in`
+      } else {
+#pragma unroll
+        for (int w = 0; w < W; ++w) c[r].w[w] = 0;
+        lf[r] = rt[r] = 0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kDiffRows; ++k) {
+      if ((uint32_t)k < rows) v[k] = *reinterpret_cast<const DiffWords<T>*>(pi + (uint64_t)k * g.X);
+      else {
+#pragma unroll
+        for (int w = 0; w < W; ++w) v[k].w[w] = 0;
+      }
+    }
+#ifdef __CUDA_ARCH__
+    asm volatile("" ::: "memory");                              // the loads above stay above the stores below
+#endif
+    uint32_t h[kDiffRows + 2][W];
+#pragma unroll
+    for (int r = 0; r < kDiffRows + 2; ++r) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const uint32_t before = w > 0 ? c[r].w[w - 1] : lf[r] << (32 - L::kBits);
+        const uint32_t after = w + 1 < W ? c[r].w[w + 1] : rt[r];
+        const uint32_t l = (c[r].w[w] << L::kBits) | (before >> (32 - L::kBits));
+        const uint32_t rr = (c[r].w[w] >> L::kBits) | (after << (32 - L::kBits));
+        h[r][w] = L::add(c[r].w[w], L::add(l, rr));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kDiffRows; ++k) {
+      const uint32_t y = y0 + (uint32_t)k;
+      if ((uint32_t)k >= rows || (last_row_spills && y + 1 == g.Y)) continue;
+      const uint32_t own_row = (y >= 1 && y + 1 < g.Y) ? 0xffffffffu : 0u;
+      const uint32_t spill_row = y >= 2 ? 0xffffffffu : 0u;
+      DiffWords<T> o;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const uint32_t mask = (own_mask[w] & own_row) | (spill_mask[w] & spill_row);
+        const uint32_t q = L::div9(L::add(h[k][w], L::add(h[k + 1][w], h[k + 2][w]))) & mask;
+        o.w[w] = L::add(v[k].w[w], q);
+      }
+      *reinterpret_cast<DiffWords<T>*>(po + (uint64_t)k * g.X) = o;
+    }
+  } else {
+    const uint64_t first = plane + (uint64_t)y0 * g.X + x0;       // the strip's first pack; rows are g.X apart
   const T* pi = in + first;
   T* po = out + first;
   const T* pn = nb + (first - g.frame);                         // the same pack one plane back
@@ -243,6 +307,7 @@ SQYB_HD void diff_thread(const T* SQYB_RESTRICT in, T* SQYB_RESTRICT out, const 
 #pragma unroll
     for (int w = 0; w < W; ++w) { hm[w] = hc[w]; hc[w] = hp[w]; }
     pi += g.X; po += g.X; pn += g.X;
+  }
   }
   if (last_row_spills) {
 #pragma unroll 1
