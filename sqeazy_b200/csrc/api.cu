@@ -86,13 +86,21 @@ struct Arena {
   }
 };
 
-std::mutex g_mu;
-Arena g_arena[16];
+// One context per device: scratch arena, copy stream, batch lanes, and the lock that serialises the calls that use this
+// device. Calls on different devices run concurrently (round 1 had one process-wide lock).
 // batch entry points (sqyx_*_batch_device_*): every lane of a batch has its own stream and scratch, so the kernels of
 // different stacks share the SMs instead of queueing behind each other's tails
 constexpr int kBatchLanes = 8;
-Arena g_batch_arena[16][kBatchLanes];
-cudaStream_t g_batch_stream[16][kBatchLanes] = {};
+constexpr int kMaxDevices = 16;
+struct Dev {
+  std::mutex mu;
+  Arena arena;
+  cudaStream_t copy_stream = nullptr;
+  Arena batch_arena[kBatchLanes];
+  cudaStream_t batch_stream[kBatchLanes] = {};
+};
+Dev g_dev[kMaxDevices];
+std::mutex g_timer_mu;   // g_stage_ms
 
 // ---- optional per-stage CUDA-event timing (sqyx_enable_stage_timing) ----
 enum StageTimer { kTFilterSwap = 0, kTLz4Enc, kTHist, kTLutApply, kTLz4Dec, kTLutDec, kTSwapDec, kNumTimers };
@@ -117,7 +125,10 @@ struct ScopedStageTimer {
       cudaEventSynchronize(b);
       float ms = 0;
       cudaEventElapsedTime(&ms, a, b);
-      g_stage_ms[slot] += ms;
+      {
+        std::lock_guard<std::mutex> lk(g_timer_mu);
+        g_stage_ms[slot] += ms;
+      }
       cudaEventDestroy(a);
       cudaEventDestroy(b);
       a = b = nullptr;
@@ -126,7 +137,8 @@ struct ScopedStageTimer {
   ~ScopedStageTimer() { stop(); }
 };
 
-int current_arena(Arena** a) {
+// the device a single-device call works on: SQY_CUDA_DEVICE, else the calling thread's current device
+int pick_device(int* out) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
     std::fprintf(stderr, "[sqeazy_b200] no CUDA device available (this build has no CPU path)\n");
@@ -140,10 +152,30 @@ int current_arena(Arena** a) {
   } else if (cudaGetDevice(&dev) != cudaSuccess) {
     return 1;
   }
-  if (dev >= 16) return 1;
-  *a = &g_arena[dev];
+  if (dev >= kMaxDevices) return 1;
+  *out = dev;
   return 0;
 }
+
+// picks the call's device and holds its lock for the lifetime of the object
+struct DevLock {
+  Dev* dev = nullptr;
+  int id = -1;
+  std::unique_lock<std::mutex> lk;
+  int acquire() {
+    if (pick_device(&id)) return 1;
+    dev = &g_dev[id];
+    lk = std::unique_lock<std::mutex>(dev->mu);
+    return 0;
+  }
+  int acquire(int device) {   // a given device; made current for the calling thread
+    if (device < 0 || device >= kMaxDevices || cudaSetDevice(device) != cudaSuccess) return 1;
+    id = device;
+    dev = &g_dev[id];
+    lk = std::unique_lock<std::mutex>(dev->mu);
+    return 0;
+  }
+};
 
 uint64_t shape_product(const std::vector<uint64_t>& shape) {
   uint64_t n = 1;
@@ -360,14 +392,12 @@ int encode_device_impl(Arena& A, const Pipeline& pl_in, const void* d_src_any, c
 constexpr uint64_t kStreamSlabBytes = uint64_t(256) << 20;
 constexpr uint64_t kStreamMinBytes = uint64_t(512) << 20;
 constexpr uint64_t kStreamGrainVoxels = 131072;   // a 16 KiB block of a 1-bit plane covers 131072 voxels (8192 * P for wider atoms)
-cudaStream_t g_copy_stream[16] = {};
-
-int copy_stream(cudaStream_t* cs) {
+int copy_stream(cudaStream_t* cs) {   // of the current device; its lock is held
   int dev = 0;
   CK(cudaGetDevice(&dev));
-  if (dev >= 16) return 1;
-  if (!g_copy_stream[dev]) CK(cudaStreamCreateWithFlags(&g_copy_stream[dev], cudaStreamNonBlocking));
-  *cs = g_copy_stream[dev];
+  if (dev >= kMaxDevices) return 1;
+  if (!g_dev[dev].copy_stream) CK(cudaStreamCreateWithFlags(&g_dev[dev].copy_stream, cudaStreamNonBlocking));
+  *cs = g_dev[dev].copy_stream;
   return 0;
 }
 
@@ -680,7 +710,7 @@ int sqyx_enable_stage_timing(int on) {
 }
 
 int sqyx_stage_ms(float* out7, int reset) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(g_timer_mu);
   for (int i = 0; i < kNumTimers; ++i) {
     if (out7) out7[i] = g_stage_ms[i];
     if (reset) g_stage_ms[i] = 0;
@@ -691,9 +721,9 @@ int sqyx_stage_ms(float* out7, int reset) {
 long sqyx_host_l2_bytes(void) { return (long)host_l2_cache_bytes(); }
 
 int sqyx_last_lz4_stats(long* out4) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  Arena* A = nullptr;
-  if (current_arena(&A)) return 1;
+  DevLock dl;
+  if (dl.acquire()) return 1;
+  Arena* A = &dl.dev->arena;
   for (int i = 0; i < 4; ++i) out4[i] = A->last_stats[i];
   return 0;
 }
@@ -702,14 +732,12 @@ long sqyx_set_lz4_lane_max(long bytes) { return k_lz4_set_lane_max(bytes); }
 long sqyx_set_lz4_defer_min(long nblocks) { return k_lz4_set_defer_min(nblocks); }
 
 int sqyx_release_scratch(void) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  Arena* A = nullptr;
-  if (current_arena(&A)) return 1;
+  DevLock dl;
+  if (dl.acquire()) return 1;
+  Arena* A = &dl.dev->arena;
   cudaDeviceSynchronize();
   A->release();
-  int dev = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess && dev < 16)
-    for (int l = 0; l < kBatchLanes; ++l) g_batch_arena[dev][l].release();
+  for (int l = 0; l < kBatchLanes; ++l) dl.dev->batch_arena[l].release();
   staging_release();
   return 0;
 }
@@ -720,9 +748,9 @@ int sqyx_encode_device_ex_UI16(const char* pipeline, const void* d_src, const lo
     if (!pipeline || !shape || !d_dst || !dst_bytes || dst_capacity < 0) return 1;
     Pipeline pl;
     if (!build_pipeline_u16(pipeline, pl) || pl.empty()) return 1;
-    std::lock_guard<std::mutex> lk(g_mu);
-    Arena* A = nullptr;
-    if (current_arena(&A)) return 1;
+    DevLock dl;
+    if (dl.acquire()) return 1;
+    Arena* A = &dl.dev->arena;
     uint64_t out = 0;
     const int rc = encode_device_impl(*A, pl, static_cast<const uint16_t*>(d_src), to_shape(shape, shape_size),
                                       static_cast<uint8_t*>(d_dst), (uint64_t)dst_capacity, &out,
@@ -742,9 +770,9 @@ int sqyx_encode_device_UI16(const char* pipeline, const void* d_src, const long*
 int sqyx_decode_device_UI16(const void* d_blob, long blob_bytes, void* d_dst, long dst_capacity, void* stream) {
   try {
     if (!d_blob || blob_bytes <= 0 || !d_dst || dst_capacity < 0) return 1;
-    std::lock_guard<std::mutex> lk(g_mu);
-    Arena* A = nullptr;
-    if (current_arena(&A)) return 1;
+    DevLock dl;
+    if (dl.acquire()) return 1;
+    Arena* A = &dl.dev->arena;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Header hdr;
     if (parse_blob_header_device(static_cast<const uint8_t*>(d_blob), (uint64_t)blob_bytes, hdr, st)) return 1;
@@ -768,14 +796,13 @@ template <class Fn>
 int run_batch(int n, int* rcs, Fn&& one) {
   if (n < 0) return 1;
   if (n == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_mu);
-  Arena* A0 = nullptr;
-  if (current_arena(&A0)) return 1;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev >= 16) return 1;
+  DevLock dl;
+  if (dl.acquire()) return 1;
+  const int dev = dl.id;
+  Dev& D = *dl.dev;
   const int lanes = n < kBatchLanes ? n : kBatchLanes;
   for (int l = 0; l < lanes; ++l)
-    if (!g_batch_stream[dev][l] && cudaStreamCreateWithFlags(&g_batch_stream[dev][l], cudaStreamNonBlocking) != cudaSuccess) return 1;
+    if (!D.batch_stream[l] && cudaStreamCreateWithFlags(&D.batch_stream[l], cudaStreamNonBlocking) != cudaSuccess) return 1;
   const int timing = g_timing.exchange(0);   // the stage timers are per call, not per lane
   std::vector<int> rc((size_t)n, 1);
   std::vector<std::thread> th;
@@ -784,7 +811,7 @@ int run_batch(int n, int* rcs, Fn&& one) {
       if (cudaSetDevice(dev) != cudaSuccess) return;
       for (int i = l; i < n; i += lanes) {
         try {
-          rc[(size_t)i] = one(i, g_batch_arena[dev][l], g_batch_stream[dev][l]);
+          rc[(size_t)i] = one(i, D.batch_arena[l], D.batch_stream[l]);
         } catch (...) {
           rc[(size_t)i] = 1;
         }
@@ -843,9 +870,9 @@ int sqyx_encode_device_UI8(const char* pipeline, const void* d_src, const long* 
     if (!pipeline || !shape || !d_dst || !dst_bytes || dst_capacity < 0) return 1;
     Pipeline pl;
     if (!build_pipeline_u8(pipeline, pl) || pl.empty()) return 1;
-    std::lock_guard<std::mutex> lk(g_mu);
-    Arena* A = nullptr;
-    if (current_arena(&A)) return 1;
+    DevLock dl;
+    if (dl.acquire()) return 1;
+    Arena* A = &dl.dev->arena;
     uint64_t out = 0;
     const int rc = encode_device_impl(*A, pl, d_src, to_shape(shape, shape_size), static_cast<uint8_t*>(d_dst), (uint64_t)dst_capacity,
                                       &out, nullptr, static_cast<cudaStream_t>(stream));
@@ -859,9 +886,9 @@ int sqyx_encode_device_UI8(const char* pipeline, const void* d_src, const long* 
 int sqyx_decode_device_UI8(const void* d_blob, long blob_bytes, void* d_dst, long dst_capacity, void* stream) {
   try {
     if (!d_blob || blob_bytes <= 0 || !d_dst || dst_capacity < 0) return 1;
-    std::lock_guard<std::mutex> lk(g_mu);
-    Arena* A = nullptr;
-    if (current_arena(&A)) return 1;
+    DevLock dl;
+    if (dl.acquire()) return 1;
+    Arena* A = &dl.dev->arena;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Header hdr;
     if (parse_blob_header_device(static_cast<const uint8_t*>(d_blob), (uint64_t)blob_bytes, hdr, st)) return 1;
@@ -957,9 +984,9 @@ int sqyx_remove_background_UI16(const void* d_src, void* d_dst, long n, int thre
 int sqyx_estimate_background_UI16(const void* d_src, const long* shape3, long l2_bytes, float* supports4, int* threshold,
                                   void* stream) {
   if (!d_src || !shape3 || !supports4 || !threshold) return 1;
-  std::lock_guard<std::mutex> lk(g_mu);
-  Arena* A = nullptr;
-  if (current_arena(&A)) return 1;
+  DevLock dl;
+  if (dl.acquire()) return 1;
+  Arena* A = &dl.dev->arena;
   return estimate_background(*A, static_cast<const uint16_t*>(d_src), (uint64_t)shape3[0], (uint64_t)shape3[1], (uint64_t)shape3[2],
                              l2_bytes, supports4, threshold, static_cast<cudaStream_t>(stream));
 }
@@ -985,9 +1012,9 @@ int sqyx_quantiser_luts(const unsigned* hist, unsigned char* enc, unsigned short
 
 int sqyx_lut_apply_UI16(const void* d_src, void* d_codes, long n, const unsigned char* enc_host, void* stream) {
   if (n < 0 || !enc_host) return 1;
-  std::lock_guard<std::mutex> lk(g_mu);
-  Arena* A = nullptr;
-  if (current_arena(&A)) return 1;
+  DevLock dl;
+  if (dl.acquire()) return 1;
+  Arena* A = &dl.dev->arena;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   void* sp = nullptr;
   if (A->get(kSlotSmall, 4 * 65536 * sizeof(uint32_t) + 4096, &sp)) return 1;
@@ -999,9 +1026,9 @@ int sqyx_lut_apply_UI16(const void* d_src, void* d_codes, long n, const unsigned
 
 int sqyx_lut_decode_UI16(const void* d_codes, void* d_dst, long n, const unsigned short* dec_host, void* stream) {
   if (n < 0 || !dec_host) return 1;
-  std::lock_guard<std::mutex> lk(g_mu);
-  Arena* A = nullptr;
-  if (current_arena(&A)) return 1;
+  DevLock dl;
+  if (dl.acquire()) return 1;
+  Arena* A = &dl.dev->arena;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   void* sp = nullptr;
   if (A->get(kSlotSmall, 4 * 65536 * sizeof(uint32_t) + 4096, &sp)) return 1;
@@ -1016,9 +1043,9 @@ long sqyx_lz4_bound(long nbytes) { return nbytes < 0 ? -1 : (long)lz4_payload_bo
 int sqyx_lz4_encode(const void* d_src, long nbytes, void* d_dst, long dst_capacity, long* payload_bytes, void* stream) {
   if (nbytes < 0 || !d_dst || !payload_bytes) return 1;
   if ((uint64_t)dst_capacity < lz4_payload_bound((uint64_t)nbytes)) return 1;
-  std::lock_guard<std::mutex> lk(g_mu);
-  Arena* A = nullptr;
-  if (current_arena(&A)) return 1;
+  DevLock dl;
+  if (dl.acquire()) return 1;
+  Arena* A = &dl.dev->arena;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   void* ws = nullptr;
   if (A->get(kSlotWs, k_lz4_encode_workspace_bytes((uint64_t)nbytes), &ws)) return 1;
@@ -1034,9 +1061,9 @@ int sqyx_lz4_encode(const void* d_src, long nbytes, void* d_dst, long dst_capaci
 
 int sqyx_lz4_decode(const void* d_src, long nbytes, void* d_dst, long dst_bytes, long* decoded_bytes, void* stream) {
   if (nbytes < 0 || dst_bytes < 0 || !d_src || !d_dst) return 1;
-  std::lock_guard<std::mutex> lk(g_mu);
-  Arena* A = nullptr;
-  if (current_arena(&A)) return 1;
+  DevLock dl;
+  if (dl.acquire()) return 1;
+  Arena* A = &dl.dev->arena;
   uint64_t got = 0;
   const int rc = lz4_decode_checked(*A, static_cast<const uint8_t*>(d_src), (uint64_t)nbytes, static_cast<uint8_t*>(d_dst),
                                     (uint64_t)dst_bytes, &got, static_cast<cudaStream_t>(stream));
@@ -1265,9 +1292,9 @@ static int host_encode(int elem, const char* pipeline, const char* src, long* sh
     const std::vector<uint64_t> shp = to_shape(shape, shape_size);
     const uint64_t N = shape_product(shp), raw_bytes = (uint64_t)elem * N;
     const uint64_t cap = max_encoded_size(pl, raw_bytes);
-    std::lock_guard<std::mutex> lk(g_mu);
-    Arena* A = nullptr;
-    if (current_arena(&A)) return 1;
+    DevLock dl;
+    if (dl.acquire()) return 1;
+    Arena* A = &dl.dev->arena;
     if (streamable_encode(pl, shp, N) && !g_timing.load()) {
       uint64_t out = 0;
       if (host_encode_streamed(*A, pl, src, shp, N, dst, cap, &out, nthreads)) return 1;
@@ -1307,9 +1334,9 @@ static int host_decode(int elem, const char* src, long srclength, char* dst, int
     }
     if (sizeof_typename(hdr.raw_type) != (unsigned)elem) return 1;
     const uint64_t raw_bytes = (uint64_t)elem * shape_product(hdr.shape);
-    std::lock_guard<std::mutex> lk(g_mu);
-    Arena* A = nullptr;
-    if (current_arena(&A)) return 1;
+    DevLock dl;
+    if (dl.acquire()) return 1;
+    Arena* A = &dl.dev->arena;
     void *d_in = nullptr, *d_out = nullptr;
     const uint64_t payload_bytes = (uint64_t)srclength - hdr.size;
     // the payload is staged at a 256-byte aligned device address, whatever the header length was

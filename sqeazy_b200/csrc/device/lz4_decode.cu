@@ -57,6 +57,7 @@ struct DecCtl {          // lives at the start of the workspace
   // fast path: the stream is exactly one frame of this library -> the block table is built by many CTAs
   uint32_t fast, fast_nblk, fast_bb, fast_pad;
   unsigned long long fast_idx, fast_first, fast_raw;
+  unsigned long long fast_end;   // first byte behind the frame's EndMark, as promised by the index header
   unsigned long long total_decoded;
   uint32_t nlinked;      // blocks that belong to block-linked frames
   uint32_t deferred;     // 1: those blocks are left to lz4_decode_deferred_kernel + the two resolve passes (k_lz4_decode_linked)
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(kDirThreads) lz4_directory_kernel(const uint8_
                   ctl->fast_idx = body + sizeof(SqybIndexHeader);
                   ctl->fast_first = fstart + kLz4FrameHeaderBytes;
                   ctl->fast_raw = raw;
+                  ctl->fast_end = fstart + fbytes;
                   sh_nb = nblk;
                   sh_pos = src_bytes;
                   sh_mode = 2;
@@ -278,7 +280,13 @@ __global__ void __launch_bounds__(kDirThreads) lz4_directory_kernel(const uint8_
         running += total;
         __syncthreads();
       }
-      if (tid == 0) sh_nb = nb0 + nblk;
+      // The index words are untrusted input: the block offsets derived from them are only used when they add up to exactly
+      // the frame the index header promised (which was checked against src_bytes above). Every src_off + csize then lies
+      // inside the stream.
+      if (tid == 0) {
+        sh_nb = nb0 + nblk;
+        if (first_hdr + running + kLz4EndMarkBytes != sh_pos) sh_err = kErrBadBlock;
+      }
     }
     __syncthreads();
   }
@@ -745,11 +753,11 @@ __device__ __forceinline__ uint32_t index_word(const uint8_t* idx, bool aligned,
   return aligned ? __ldg(reinterpret_cast<const uint32_t*>(idx) + i) : rd32(idx + 4ull * i);
 }
 
-__global__ void __launch_bounds__(256) lz4_tile_sums_kernel(const uint8_t* __restrict__ src, const DecCtl* ctl,
+__global__ void __launch_bounds__(256) lz4_tile_sums_kernel(const uint8_t* __restrict__ src, DecCtl* ctl,
                                                             unsigned long long* __restrict__ tile_sums) {
   __shared__ uint32_t wsum[8];
   if (ctl->error || !ctl->fast) return;
-  const uint32_t nblk = ctl->fast_nblk, ntiles = (nblk + kTile - 1) / kTile;
+  const uint32_t nblk = ctl->fast_nblk, bb = ctl->fast_bb, ntiles = (nblk + kTile - 1) / kTile;
   const uint8_t* idx = src + ctl->fast_idx;
   const bool aligned = (((uintptr_t)idx) & 3) == 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -758,7 +766,12 @@ __global__ void __launch_bounds__(256) lz4_tile_sums_kernel(const uint8_t* __res
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const uint32_t i = t * kTile + k * 256 + tid;
-      if (i < nblk) s += 4u + (index_word(idx, aligned, i) & 0x7FFFFFFFu);
+      if (i < nblk) {
+        const uint32_t sz = index_word(idx, aligned, i) & 0x7FFFFFFFu;
+        // untrusted index: no block is larger than the block size (bb <= 65536 keeps the 32-bit tile sums exact)
+        if (sz > bb) atomicMax(&ctl->error, (uint32_t)kErrBadBlock);
+        s += 4u + (sz > bb ? bb : sz);
+      }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
@@ -826,6 +839,10 @@ __global__ void __launch_bounds__(256) lz4_expand_kernel(const uint8_t* __restri
     const uint32_t tbase = wbase + incl - s;
 #pragma unroll
     for (int k = 0; k < 16; ++k) pre[tid * 16 + k] = tbase + loc[k];
+    // the offsets are only good when the sizes of the (untrusted) index add up to exactly the frame its header promised:
+    // the thread that ends the last tile checks it, the decoders look at ctl->error before they touch the table
+    if (t == ntiles - 1 && tid == 255 && base + tbase + s + kLz4EndMarkBytes != ctl->fast_end)
+      atomicMax(&ctl->error, (uint32_t)kErrBadBlock);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k) {

@@ -5,7 +5,8 @@
 // the device with one DMA; pageable ones (a plain malloc / std::vector / Java heap buffer: what the sqy CLI and the
 // BridJ bindings pass) are moved through a ring of page-locked chunks, `nthreads` host threads filling chunk c+1
 // while the DMA engine moves chunk c. With nthreads == 1 the driver's own pageable path is used (it is the same
-// single-threaded copy).
+// single-threaded copy). There is one ring per device; the caller holds that device's lock (api.cu). A slot remembers
+// across calls and streams whether a DMA on it is still outstanding.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -18,7 +19,8 @@ namespace sqyb {
 // d2h: on return the host buffer is complete when the path was staged; otherwise it is complete after `st` is synchronised.
 int staged_h2d(void* d_dst, const void* h_src, size_t bytes, int nthreads, cudaStream_t st);
 int staged_d2h(void* h_dst, const void* d_src, size_t bytes, int nthreads, cudaStream_t st);
-void staging_release();          // frees the page-locked ring (sqyx_release_scratch)
+void staging_release();          // frees the page-locked ring of the current device (sqyx_release_scratch)
+bool host_buffer_is_pageable(const void* p);   // not page-locked / registered with CUDA
 int staging_threads(int nthreads);   // the reference's rule: <= 0 or more than the machine has => all cores (capped at 16 here)
 
 }  // namespace sqyb

@@ -164,3 +164,47 @@ def test_random_mixed_streams_from_liblz4_and_own_encoder(sq, cuda, ref, decoder
         h = out.cpu().numpy()
         assert np.array_equal(h[: a.size], a)
         assert np.all(h[a.size:] == 0x42)
+
+
+@pytest.mark.parametrize("nblocks", [40, 9000], ids=["directory-scan", "tiled-table-build"])
+def test_corrupt_index_words_are_refused(sq, cuda, nblocks):
+    """The block offsets of this library's frames are prefix sums of the index words in the skippable frame — untrusted
+    input. Both table builders (directory CTA below 8192 blocks, lz4_tile_sums_kernel + lz4_expand_kernel above) must
+    refuse an index whose sizes do not add up to exactly the frame the index header promises, before any block is read."""
+    n = 16384 * nblocks - 77
+    g = cuda.Generator(device="cuda")
+    g.manual_seed(nblocks)
+    sparse = cuda.rand(n, generator=g, device="cuda") < 0.02
+    a = sparse.to(cuda.uint8) * cuda.randint(1, 256, (n,), generator=g, device="cuda", dtype=cuda.uint8)
+    payload = sq.lz4_encode_device(a).cpu().numpy()
+    words = payload[40: 40 + 4 * nblocks].view(np.uint32)
+
+    def try_decode(p):
+        out = cuda.full((n + 4096,), 0x11, dtype=cuda.uint8, device="cuda")
+        try:
+            got = sq.lz4_decode_device(dev(cuda, p), out[:n])
+        except sq.SqeazyError:
+            got = None
+        assert bool((out[n:] == 0x11).all()), "decoder wrote past the end of the output"
+        return got, out
+
+    for k, (pos, new) in enumerate([(5, int(words[5]) + 1000), (nblocks // 2, 0x7FFFFFFF), (nblocks - 1, 0xFFFFFFFF),
+                                    (3, 0), (nblocks - 2, int(words[nblocks - 2]) - 1)]):
+        bad = payload.copy()
+        bad[40: 40 + 4 * nblocks].view(np.uint32)[pos] = new
+        got, _ = try_decode(bad)
+        assert got is None, f"corrupt index word {k} was accepted"
+    # sizes that still add up but belong to other blocks: no out-of-bounds access; an error or garbage, never a crash
+    bad = payload.copy()
+    w = bad[40: 40 + 4 * nblocks].view(np.uint32)
+    i = int(np.argmax(w[:-1] != w[1:]))
+    w[i], w[i + 1] = w[i + 1], w[i]
+    try_decode(bad)
+    # an index that claims a frame longer than the stream is not trusted at all: the LZ4 frame behind it is still valid and
+    # is walked like a foreign one (or the stream is refused)
+    bad = payload.copy()
+    bad[32:40].view(np.uint64)[0] += 16
+    got, out = try_decode(bad)
+    assert got is None or (got == n and cuda.equal(out[:n], a))
+    got, out = try_decode(payload)
+    assert got == n and cuda.equal(out[:n], a)
