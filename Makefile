@@ -12,7 +12,7 @@ CU_SRCS   := $(CSRC)/api.cu $(CSRC)/staging.cu $(CSRC)/device/bitswap.cu $(CSRC)
 CPP_SRCS  := $(CSRC)/host/text.cpp $(CSRC)/host/numerics.cpp $(CSRC)/host/pipeline.cpp $(CSRC)/host/h5_filter.cpp
 CU_OBJS   := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
 CPP_OBJS  := $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP_SRCS))
-HDRS      := $(wildcard $(CSRC)/*.hpp $(CSRC)/device/*.h $(CSRC)/device/*.cuh $(CSRC)/host/*.hpp include/*.h)
+HDRS      := $(wildcard $(CSRC)/*.hpp $(CSRC)/*.inl $(CSRC)/device/*.h $(CSRC)/device/*.cuh $(CSRC)/host/*.hpp include/*.h)
 
 REF       := /root/reference/src/cpp/src
 LZ4SO     := /usr/lib/x86_64-linux-gnu/liblz4.so.1
@@ -30,7 +30,7 @@ $(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDRS)
 	$(CXX) -O2 -std=c++17 -fPIC -ffp-contract=off -Wall -c $< -o $@
 
 $(LIB): $(CU_OBJS) $(CPP_OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static
+	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static -ldl
 
 # ---- sqy command line tool: a plain C++ client of the C ABI (no CUDA in this translation unit)
 $(SQY): $(CSRC)/cli/sqy.cpp $(CSRC)/cli/tiff_min.hpp include/sqeazy.h $(LIB)

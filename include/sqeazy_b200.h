@@ -118,6 +118,20 @@ int sqyx_device_count(void);
 /* makes `device` current for the calling thread inside this library's CUDA runtime instance (one process
  * per GPU callers set it once; all sqyx_ and SQY_ calls then use that device) */
 int sqyx_set_device(int device);
+/* Multi-GPU inside ONE call. The host-buffer entry points of sqeazy.h (SQY_PipelineEncode_UI16 /
+ * SQY_Decode_UI16; reference: src/cpp/src/sqeazy.cpp:108-142, 281-307) shard one stack of
+ * `[remove_background | rmestbkrd ->] bitswapN -> lz4` or `quantiser -> lz4` over a set of GPUs: contiguous z-slabs
+ * (boundaries at multiples of 131072 voxels, >= 128 MiB of LZ4 input per GPU), every GPU fed over its own PCIe link,
+ * ONE blob out — byte-identical to the single-GPU blob. The quantiser's 65536-bin histogram is summed with
+ * ncclAllReduce (libnccl.so.2 bound at run time; SQY_NO_NCCL=1 or no NCCL: summed on the host).
+ * The set: sqyx_set_devices(n, ids) (n = 0: back to the default), else the environment variable SQY_CUDA_DEVICES
+ * ("all" or "0,1,2"), else SQY_CUDA_DEVICE, else every visible device. sqyx_set_device(d) pins all calls to d. */
+int sqyx_set_devices(int n, const int* devices);
+/* out3 = {GPUs the most recent SQY_ host call was sharded over (0: single-device route), 1 if its histogram all-reduce went
+ * through NCCL, number of (plane, GPU) pieces merged} */
+int sqyx_last_shard_info(long* out3);
+/* cumulative number of in-library NCCL histogram all-reduces */
+long sqyx_nccl_allreduces(void);
 /* cumulative number of CUDA kernels launched by this library in this process */
 long sqyx_kernel_launches(void);
 /* block statistics of the most recent LZ4 encode on this thread's device:

@@ -37,7 +37,7 @@ SQYX_SYMBOLS = [
     "sqyx_rmest_frame_portion", "sqyx_encode_device_UI8", "sqyx_decode_device_UI8", "sqyx_bitswap_encode_UI8",
     "sqyx_bitswap_decode_UI8", "sqyx_remove_background_UI8", "sqyx_decode_batch_device_UI16", "sqyx_encode_batch_device_UI16",
     "sqyx_bitshuffle_encode_UI16", "sqyx_bitshuffle_decode_UI16", "sqyx_bitshuffle_encode_UI8", "sqyx_bitshuffle_decode_UI8", "sqyx_set_lz4_defer_min",
-    "sqyx_diff_device", "sqyx_diff_shape_supported",
+    "sqyx_diff_device", "sqyx_diff_shape_supported", "sqyx_set_devices", "sqyx_last_shard_info", "sqyx_nccl_allreduces",
 ]
 
 # include/sqeazy_h5_filter.h: what HDF5 looks up in a filter plugin
@@ -57,7 +57,7 @@ def lib() -> ctypes.CDLL:
         L.SQY_Pipeline_Possible_UI16.restype = c_bool
         L.SQY_Pipeline_Possible_UI8.restype = c_bool
         L.SQY_Pipeline_Possible.restype = c_bool
-        for name in ("sqyx_lz4_bound", "sqyx_kernel_launches", "sqyx_host_l2_bytes", "sqyx_rmest_frame_portion"):
+        for name in ("sqyx_lz4_bound", "sqyx_kernel_launches", "sqyx_host_l2_bytes", "sqyx_rmest_frame_portion", "sqyx_nccl_allreduces"):
             getattr(L, name).restype = c_long
         L.sqyx_histogram_support.restype = c_float
         L.sqyx_histogram_support.argtypes = [c_void_p, c_float]
@@ -216,6 +216,28 @@ def set_device(index: int):
     """binds the library's CUDA runtime to `index` for this thread (torch.cuda.set_device does not reach it)"""
     if lib().sqyx_set_device(c_int(index)) != 0:
         raise SqeazyError(f"sqyx_set_device({index}) failed")
+
+
+def set_devices(indices=None):
+    """GPUs over which the host-buffer calls (`encode` / `decode`) may shard ONE stack (z-slabs, one blob). None or [] = the
+    default again: SQY_CUDA_DEVICES, else every visible device. `set_device(i)` pins the calls to GPU i."""
+    ids = list(indices or [])
+    arr = (c_int * max(len(ids), 1))(*ids)
+    if lib().sqyx_set_devices(c_int(len(ids)), arr) != 0:
+        raise SqeazyError(f"sqyx_set_devices({ids}) failed")
+
+
+def last_shard_info():
+    """how the most recent host-buffer call on this process was spread: GPUs used (0 = single-device route), whether the
+    histogram all-reduce went through NCCL, number of (plane, GPU) pieces merged"""
+    out = (c_long * 3)()
+    lib().sqyx_last_shard_info(out)
+    return {"gpus": int(out[0]), "nccl": bool(out[1]), "pieces": int(out[2])}
+
+
+def nccl_allreduces() -> int:
+    """cumulative number of in-library NCCL histogram all-reduces"""
+    return int(lib().sqyx_nccl_allreduces())
 
 
 def encode_device(pipeline: str, volume, out=None, global_hist=None, stream=None):

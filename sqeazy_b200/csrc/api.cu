@@ -4,10 +4,12 @@
 // (dynamic_pipeline.hpp:619-690, 772-846). No CPU compute path exists here: without a CUDA device
 // every compute entry point fails with 1.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
 #include <climits>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -137,7 +139,11 @@ struct ScopedStageTimer {
   ~ScopedStageTimer() { stop(); }
 };
 
-// the device a single-device call works on: SQY_CUDA_DEVICE, else the calling thread's current device
+std::mutex g_set_mu;
+std::vector<int> g_set;          // set by sqyx_set_devices / sqyx_set_device; empty = not pinned by the caller
+
+// the device a single-device call works on: SQY_CUDA_DEVICE, else a device set of one (sqyx_set_devices), else the calling
+// thread's current device
 int pick_device(int* out) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
@@ -149,8 +155,18 @@ int pick_device(int* out) {
     dev = std::atoi(env);
     if (dev < 0 || dev >= n) return 1;
     if (cudaSetDevice(dev) != cudaSuccess) return 1;
-  } else if (cudaGetDevice(&dev) != cudaSuccess) {
-    return 1;
+  } else {
+    int pinned = -1;
+    {
+      std::lock_guard<std::mutex> lk(g_set_mu);
+      if (g_set.size() == 1) pinned = g_set[0];
+    }
+    if (pinned >= 0) {
+      dev = pinned;
+      if (dev >= n || cudaSetDevice(dev) != cudaSuccess) return 1;
+    } else if (cudaGetDevice(&dev) != cudaSuccess) {
+      return 1;
+    }
   }
   if (dev >= kMaxDevices) return 1;
   *out = dev;
@@ -184,27 +200,42 @@ uint64_t shape_product(const std::vector<uint64_t>& shape) {
 }
 
 // ---- rmestbkrd threshold: GPU histograms of the sampled faces/rows + host support formula ----
-int estimate_background(Arena& A, const uint16_t* d_src, uint64_t Z, uint64_t Y, uint64_t X, long l2_bytes, float* supports,
-                        int* threshold, cudaStream_t st) {
-  if (Z == 0 || Y == 0 || X == 0) return 1;
-  const size_t l2 = l2_bytes >= 0 ? (size_t)l2_bytes : host_l2_cache_bytes();
+// what the estimate reads, as device pointers: the first `portion` voxels of the z = 0 and z = Z-1 faces and the rows y = 0 /
+// y = Y-1 at z in {1, Z/2, Z-2} (nullptr: that z does not exist). The callers whose stack is not resident as a whole (streamed
+// and sharded host paths) send just these pieces.
+struct EstimateSamples {
+  const uint16_t* face[2];
+  const uint16_t* row[2][3];
+  uint64_t portion, X;
+};
+
+EstimateSamples estimate_samples_of(const uint16_t* d_src, uint64_t Z, uint64_t Y, uint64_t X, size_t l2) {
+  EstimateSamples S;
   const uint64_t frame = Y * X;
-  const uint64_t portion = rmest_frame_portion(frame, l2);
+  S.portion = rmest_frame_portion(frame, l2);
+  S.X = X;
+  S.face[0] = d_src;
+  S.face[1] = d_src + (Z - 1) * frame;
+  // rows y = 0 and y = Y-1 at z in {1, Z/2, Z-2}, background_scheme_utils.hpp:79-103 (z indices are used as given, like the reference)
+  const uint64_t zs[3] = {1, Z / 2, Z - 2};
+  const uint64_t ys[2] = {0, Y - 1};
+  for (int i = 0; i < 2; ++i)
+    for (int k = 0; k < 3; ++k)   // Z < 3: the reference would read out of bounds; we skip those rows
+      S.row[i][k] = zs[k] >= Z ? nullptr : d_src + zs[k] * frame + ys[i] * X;
+  return S;
+}
+
+int estimate_background_samples(Arena& A, const EstimateSamples& S, float* supports, int* threshold, cudaStream_t st) {
   void* p = nullptr;
   if (A.get(kSlotSmall, 4 * 65536 * sizeof(uint32_t) + 4096, &p)) return 1;
   uint32_t* d_h = static_cast<uint32_t*>(p);
   CK(cudaMemsetAsync(d_h, 0, 4 * 65536 * sizeof(uint32_t), st));
   // z = 0 and z = Z-1 faces (first `portion` elements), background_scheme_utils.hpp:57-77
-  CKK(k_histogram_u16(d_src, portion, d_h, st));
-  CKK(k_histogram_u16(d_src + (Z - 1) * frame, portion, d_h + 65536, st));
-  // rows y = 0 and y = Y-1 at z in {1, Z/2, Z-2}, :79-103 (z indices are used as given, like the reference)
-  const uint64_t zs[3] = {1, Z / 2, Z - 2};
-  const uint64_t ys[2] = {0, Y - 1};
+  CKK(k_histogram_u16(S.face[0], S.portion, d_h, st));
+  CKK(k_histogram_u16(S.face[1], S.portion, d_h + 65536, st));
   for (int i = 0; i < 2; ++i)
-    for (int k = 0; k < 3; ++k) {
-      if (zs[k] >= Z) continue;  // Z < 3: the reference would read out of bounds; we skip those rows
-      CKK(k_histogram_u16(d_src + zs[k] * frame + ys[i] * X, X, d_h + (2 + i) * 65536, st));
-    }
+    for (int k = 0; k < 3; ++k)
+      if (S.row[i][k]) CKK(k_histogram_u16(S.row[i][k], S.X, d_h + (2 + i) * 65536, st));
   // support index of the four histograms on the device; 64 bytes come back instead of 1 MiB of bins
   uint32_t* d_idx = d_h + 4 * 65536;
   CKK(k_support_index(d_h, 4, 0.99f, d_idx, st));
@@ -218,6 +249,36 @@ int estimate_background(Arena& A, const uint16_t* d_src, uint64_t Z, uint64_t Y,
   }
   *threshold = (int)(uint16_t)mn;  // remove_background_scheme(raw_type) ctor truncates
   return 0;
+}
+
+int estimate_background(Arena& A, const uint16_t* d_src, uint64_t Z, uint64_t Y, uint64_t X, long l2_bytes, float* supports,
+                        int* threshold, cudaStream_t st) {
+  if (Z == 0 || Y == 0 || X == 0) return 1;
+  const size_t l2 = l2_bytes >= 0 ? (size_t)l2_bytes : host_l2_cache_bytes();
+  return estimate_background_samples(A, estimate_samples_of(d_src, Z, Y, X, l2), supports, threshold, st);
+}
+
+// the same from a stack in HOST memory: only the sampled pieces cross the bus, packed into `d_scratch` (>= 4*portion + 12*X bytes)
+int estimate_background_host(Arena& A, const uint16_t* h_src, uint64_t Z, uint64_t Y, uint64_t X, uint16_t* d_scratch, int* threshold,
+                             cudaStream_t st) {
+  if (Z == 0 || Y == 0 || X == 0) return 1;
+  const EstimateSamples H = estimate_samples_of(h_src, Z, Y, X, host_l2_cache_bytes());
+  EstimateSamples D = H;
+  uint16_t* q = d_scratch;
+  for (int f = 0; f < 2; ++f) {
+    CK(cudaMemcpyAsync(q, H.face[f], 2 * H.portion, cudaMemcpyHostToDevice, st));
+    D.face[f] = q;
+    q += H.portion;
+  }
+  for (int i = 0; i < 2; ++i)
+    for (int k = 0; k < 3; ++k) {
+      if (!H.row[i][k]) continue;
+      CK(cudaMemcpyAsync(q, H.row[i][k], 2 * X, cudaMemcpyHostToDevice, st));
+      D.row[i][k] = q;
+      q += X;
+    }
+  float sup[4];
+  return estimate_background_samples(A, D, sup, threshold, st);
 }
 
 // ---- encode ----
@@ -462,10 +523,10 @@ int lz4_decode_checked(Arena& A, const uint8_t* src, uint64_t nbytes, uint8_t* d
 // host while the next one is decoded; only the first slab's kernels run in front of the bus. Returns -1 when the blob is not
 // of that kind (the caller takes the general route), 0 on success, an error code otherwise.
 int decode_streamed(Arena& A, const Pipeline& pl, const uint8_t* d_payload, uint64_t payload_bytes, uint16_t* d_dst, uint64_t N,
-                    cudaStream_t st, HostSink* host) {
+                    cudaStream_t st, HostSink* host, uint64_t slab_voxels = kStreamSlabBytes / 2, uint64_t min_bytes = kStreamMinBytes) {
   const uint64_t raw_bytes = 2 * N;
   if (pl.elem != 2 || !pl.has_sink || pl.sink.kind != StageKind::Lz4 || pl.has_tail || g_timing.load()) return -1;
-  if (raw_bytes < kStreamMinBytes || N % kStreamGrainVoxels) return -1;
+  if (raw_bytes < min_bytes || N % kStreamGrainVoxels) return -1;
   int w = 0, nswaps = 0;
   for (const Stage& s : pl.head) {
     if (s.kind == StageKind::Bitswap) { w = s.w; nswaps++; }
@@ -484,7 +545,7 @@ int decode_streamed(Arena& A, const Pipeline& pl, const uint8_t* d_payload, uint
   cudaStream_t cs = nullptr;
   if (copy_stream(&cs)) return 1;
   // at most 32 slabs (one work counter each)
-  uint64_t slab = kStreamSlabBytes / 2;
+  uint64_t slab = slab_voxels;
   while ((N + slab - 1) / slab > 32) slab *= 2;
   const uint32_t blocks_per_plane = (uint32_t)(raw_bytes / P / kLz4BlockBytes);
   EventList events;
@@ -515,6 +576,9 @@ int decode_streamed(Arena& A, const Pipeline& pl, const uint8_t* d_payload, uint
   return 0;
 }
 
+int decode_streamed_codes(Arena& A, const Pipeline& pl, const uint8_t* d_payload, uint64_t payload_bytes, uint16_t* d_dst, uint64_t N,
+                          cudaStream_t st, HostSink* host, uint64_t slab_voxels, uint64_t min_bytes);   // sharded.inl
+
 int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const uint8_t* d_payload, uint64_t payload_bytes,
                        void* d_dst_any, uint64_t dst_cap, cudaStream_t st, HostSink* host = nullptr) {
   const uint64_t N = shape_product(hdr.shape);
@@ -524,7 +588,9 @@ int decode_device_impl(Arena& A, const Header& hdr, const Pipeline& pl, const ui
   if (dst_cap < raw_bytes) return 1;
   if (N == 0) return 0;
   if (host) {
-    const int rc = decode_streamed(A, pl, d_payload, payload_bytes, d_dst, N, st, host);
+    int rc = decode_streamed(A, pl, d_payload, payload_bytes, d_dst, N, st, host);
+    if (rc >= 0) return rc;
+    rc = decode_streamed_codes(A, pl, d_payload, payload_bytes, d_dst, N, st, host, kStreamSlabBytes / 2, kStreamMinBytes);
     if (rc >= 0) return rc;
   }
 
@@ -687,6 +753,8 @@ std::vector<uint64_t> to_shape(const long* shape, unsigned n) {
   return v;
 }
 
+#include "sharded.inl"
+
 }  // namespace
 
 // =================================================================================================
@@ -700,7 +768,37 @@ int sqyx_device_count(void) {
   return n;
 }
 
-int sqyx_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? 0 : 1; }
+int sqyx_set_device(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) return 1;
+  std::lock_guard<std::mutex> lk(g_set_mu);
+  g_set.assign(1, device);      // a caller that names its device (one process per GPU) is not sharded over the others
+  return 0;
+}
+
+int sqyx_set_devices(int n, const int* devices) {
+  int have = 0;
+  if (n < 0 || (n > 0 && !devices) || cudaGetDeviceCount(&have) != cudaSuccess) return 1;
+  std::vector<int> v;
+  for (int i = 0; i < n; ++i) {
+    if (devices[i] < 0 || devices[i] >= have || devices[i] >= kMaxDevices) return 1;
+    if (std::find(v.begin(), v.end(), devices[i]) == v.end()) v.push_back(devices[i]);
+  }
+  std::sort(v.begin(), v.end());
+  std::lock_guard<std::mutex> lk(g_set_mu);
+  g_set = v;                    // empty: back to the default (SQY_CUDA_DEVICES / every visible device)
+  return 0;
+}
+
+int sqyx_last_shard_info(long* out3) {
+  if (!out3) return 1;
+  std::lock_guard<std::mutex> lk(g_shard_stats_mu);
+  out3[0] = g_shard_stats.gpus;
+  out3[1] = g_shard_stats.nccl;
+  out3[2] = g_shard_stats.pieces;
+  return 0;
+}
+
+long sqyx_nccl_allreduces(void) { return g_nccl_allreduces.load(); }
 
 long sqyx_kernel_launches(void) { return sqyb::g_kernel_launches.load(); }
 
@@ -1292,6 +1390,20 @@ static int host_encode(int elem, const char* pipeline, const char* src, long* sh
     const std::vector<uint64_t> shp = to_shape(shape, shape_size);
     const uint64_t N = shape_product(shp), raw_bytes = (uint64_t)elem * N;
     const uint64_t cap = max_encoded_size(pl, raw_bytes);
+    if (elem == 2) {
+      // one stack over several GPUs (and the streamed quantiser path on one): sharded.inl
+      {
+        std::lock_guard<std::mutex> lk(g_shard_stats_mu);
+        g_shard_stats = ShardStats();
+      }
+      uint64_t out = 0;
+      const int rc = host_encode_sharded(pl, src, shp, N, dst, cap, &out, nthreads);
+      if (rc > 0) return 1;
+      if (rc == 0) {
+        *dstlength = (long)out;
+        return 0;
+      }
+    }
     DevLock dl;
     if (dl.acquire()) return 1;
     Arena* A = &dl.dev->arena;
@@ -1334,6 +1446,14 @@ static int host_decode(int elem, const char* src, long srclength, char* dst, int
     }
     if (sizeof_typename(hdr.raw_type) != (unsigned)elem) return 1;
     const uint64_t raw_bytes = (uint64_t)elem * shape_product(hdr.shape);
+    if (elem == 2) {
+      {
+        std::lock_guard<std::mutex> lk(g_shard_stats_mu);
+        g_shard_stats = ShardStats();
+      }
+      const int rc = host_decode_sharded(hdr, pl, src, (uint64_t)srclength, dst, nthreads);
+      if (rc >= 0) return rc;
+    }
     DevLock dl;
     if (dl.acquire()) return 1;
     Arena* A = &dl.dev->arena;

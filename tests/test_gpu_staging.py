@@ -48,7 +48,7 @@ def test_staging_uint8(sq, cuda):
 
 
 @pytest.mark.parametrize("pipeline", ["bitswap1->lz4", "rmestbkrd->bitswap1->lz4", "remove_background(threshold=110)->bitswap4->lz4",
-                                      "rmbkrd(threshold=104)->bitswap2->lz4"])
+                                      "rmbkrd(threshold=104)->bitswap2->lz4", "quantiser->lz4"])
 @pytest.mark.parametrize("kind", ["pageable", "pinned"])
 def test_streamed_host_paths_match_the_device_path(sq, cuda, pipeline, kind):
     """stacks of >= 512 MiB take the streamed host paths (api.cu: host_encode_streamed, the host sink of decode_device_impl):
