@@ -100,6 +100,10 @@ int sqyx_lut_decode_UI16(const void* d_codes, void* d_dst, long n, const unsigne
  * reference: encoders/lz4.hpp:214-242 (encode), :257-339 (decode), :166-188 (bound) */
 long sqyx_lz4_bound(long nbytes);
 int sqyx_lz4_encode(const void* d_src, long nbytes, void* d_dst, long dst_capacity, long* payload_bytes, void* stream);
+/* pitch_bytes: distance in the stream between vertically adjacent voxels (a row of a bit plane of 2048-voxel rows: 256),
+ * offered to the match finder as a fixed offset beside 1..4; must be a multiple of 32, 0 = none. The pipelines pass
+ * X * w / 8 (bit planes) or X (8-bit codes). Output bytes are a pure function of (input, pitch_bytes). */
+int sqyx_lz4_encode_ex(const void* d_src, long nbytes, void* d_dst, long dst_capacity, long* payload_bytes, long pitch_bytes, void* stream);
 int sqyx_lz4_decode(const void* d_src, long nbytes, void* d_dst, long dst_bytes, long* decoded_bytes, void* stream);
 
 /* ---- uint8 volumes (the *_UI8 entry points of sqeazy.h on device pointers) ----

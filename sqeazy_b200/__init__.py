@@ -37,7 +37,7 @@ SQYX_SYMBOLS = [
     "sqyx_rmest_frame_portion", "sqyx_encode_device_UI8", "sqyx_decode_device_UI8", "sqyx_bitswap_encode_UI8",
     "sqyx_bitswap_decode_UI8", "sqyx_remove_background_UI8", "sqyx_decode_batch_device_UI16", "sqyx_encode_batch_device_UI16",
     "sqyx_bitshuffle_encode_UI16", "sqyx_bitshuffle_decode_UI16", "sqyx_bitshuffle_encode_UI8", "sqyx_bitshuffle_decode_UI8", "sqyx_set_lz4_defer_min",
-    "sqyx_diff_device", "sqyx_diff_shape_supported", "sqyx_set_devices", "sqyx_last_shard_info", "sqyx_nccl_allreduces",
+    "sqyx_diff_device", "sqyx_diff_shape_supported", "sqyx_set_devices", "sqyx_last_shard_info", "sqyx_nccl_allreduces", "sqyx_lz4_encode_ex",
 ]
 
 # include/sqeazy_h5_filter.h: what HDF5 looks up in a filter plugin
@@ -517,15 +517,16 @@ def lz4_bound(nbytes: int) -> int:
     return int(lib().sqyx_lz4_bound(c_long(nbytes)))
 
 
-def lz4_encode_device(src, out=None, stream=None):
-    """src: CUDA tensor (any dtype, contiguous) -> uint8 CUDA view of the LZ4 frame stream"""
+def lz4_encode_device(src, out=None, stream=None, pitch: int = 0):
+    """src: CUDA tensor (any dtype, contiguous) -> uint8 CUDA view of the LZ4 frame stream. pitch: bytes between vertically
+    adjacent voxels in the stream (multiple of 32; 0 = no hint), see sqyx_lz4_encode_ex"""
     import torch
     nbytes = src.numel() * src.element_size()
     cap = lz4_bound(nbytes)
     if out is None or out.numel() < cap:
         out = torch.empty(cap, dtype=torch.uint8, device=src.device)
     n = c_long(0)
-    rc = lib().sqyx_lz4_encode(_dp(src), c_long(nbytes), _dp(out), c_long(out.numel()), ctypes.byref(n), _stream_handle(stream))
+    rc = lib().sqyx_lz4_encode_ex(_dp(src), c_long(nbytes), _dp(out), c_long(out.numel()), ctypes.byref(n), c_long(pitch), _stream_handle(stream))
     if rc != 0:
         raise SqeazyError("sqyx_lz4_encode failed")
     return out[: n.value]

@@ -193,6 +193,20 @@ struct DevLock {
   }
 };
 
+// LZ4 pitch hint (kernels.h): bytes between vertically adjacent voxels in the stream the `lz4` stage sees — a function of
+// pipeline and shape only, so every route (device, streamed, sharded) writes the same bytes
+uint32_t lz4_pitch_hint(const Pipeline& pl, const std::vector<uint64_t>& shape) {
+  if (shape.size() < 2 || !pl.has_sink) return 0;
+  const uint64_t X = shape.back();
+  uint64_t pitch = 0;
+  if (pl.sink.kind == StageKind::Quantiser && pl.has_tail && pl.head.empty()) pitch = X;                 // rows of 8-bit codes
+  else if (pl.sink.kind == StageKind::Lz4 && !pl.head.empty() && pl.head.back().kind == StageKind::Bitswap) {
+    const uint64_t bits = X * (uint64_t)pl.head.back().w;                                                 // bits of one row in one plane
+    if (bits % 8 == 0) pitch = bits / 8;
+  } else if (pl.sink.kind == StageKind::Lz4 && pl.head.empty()) pitch = X * (uint64_t)pl.elem;           // raw voxels
+  return pitch <= 8192 ? (uint32_t)pitch : 0u;
+}
+
 uint64_t shape_product(const std::vector<uint64_t>& shape) {
   uint64_t n = 1;
   for (uint64_t d : shape) n *= d;
@@ -367,7 +381,7 @@ int encode_device_impl(Arena& A, const Pipeline& pl_in, const void* d_src_any, c
     if (A.get(kSlotWs, k_lz4_encode_workspace_bytes(nbytes), &ws)) return 1;
     {
       ScopedStageTimer tm(kTLz4Enc, st);
-      CKK(k_lz4_encode(src, nbytes, payload, ws, st));
+      CKK(k_lz4_encode(src, nbytes, payload, ws, lz4_pitch_hint(pl, shape), st));
     }
     unsigned long long hres[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(hres, ws, 32, cudaMemcpyDeviceToHost, st));
@@ -1138,7 +1152,7 @@ int sqyx_lut_decode_UI16(const void* d_codes, void* d_dst, long n, const unsigne
 
 long sqyx_lz4_bound(long nbytes) { return nbytes < 0 ? -1 : (long)lz4_payload_bound((uint64_t)nbytes); }
 
-int sqyx_lz4_encode(const void* d_src, long nbytes, void* d_dst, long dst_capacity, long* payload_bytes, void* stream) {
+int sqyx_lz4_encode_ex(const void* d_src, long nbytes, void* d_dst, long dst_capacity, long* payload_bytes, long pitch_bytes, void* stream) {
   if (nbytes < 0 || !d_dst || !payload_bytes) return 1;
   if ((uint64_t)dst_capacity < lz4_payload_bound((uint64_t)nbytes)) return 1;
   DevLock dl;
@@ -1147,7 +1161,7 @@ int sqyx_lz4_encode(const void* d_src, long nbytes, void* d_dst, long dst_capaci
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   void* ws = nullptr;
   if (A->get(kSlotWs, k_lz4_encode_workspace_bytes((uint64_t)nbytes), &ws)) return 1;
-  CKK(k_lz4_encode(static_cast<const uint8_t*>(d_src), (uint64_t)nbytes, static_cast<uint8_t*>(d_dst), ws, st));
+  CKK(k_lz4_encode(static_cast<const uint8_t*>(d_src), (uint64_t)nbytes, static_cast<uint8_t*>(d_dst), ws, pitch_bytes > 0 && pitch_bytes <= 8192 ? (uint32_t)pitch_bytes : 0u, st));
   unsigned long long hres[4] = {0, 0, 0, 0};
   CK(cudaMemcpyAsync(hres, ws, 32, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -1155,6 +1169,10 @@ int sqyx_lz4_encode(const void* d_src, long nbytes, void* d_dst, long dst_capaci
   const uint32_t* stats = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(hres) + 16);
   A->last_stats[0] = stats[0]; A->last_stats[1] = stats[1]; A->last_stats[2] = stats[2]; A->last_stats[3] = (long)hres[0];
   return 0;
+}
+
+int sqyx_lz4_encode(const void* d_src, long nbytes, void* d_dst, long dst_capacity, long* payload_bytes, void* stream) {
+  return sqyx_lz4_encode_ex(d_src, nbytes, d_dst, dst_capacity, payload_bytes, 0, stream);
 }
 
 int sqyx_lz4_decode(const void* d_src, long nbytes, void* d_dst, long dst_bytes, long* decoded_bytes, void* stream) {
@@ -1355,7 +1373,7 @@ int host_encode_streamed(Arena& A, const Pipeline& pl, const char* src, const st
     // plane piece of this slab: bytes [2*first/P, 2*(first+count)/P) of every plane
     CKK(k_lz4_encode_blocks(reinterpret_cast<const uint8_t*>(d_planes), raw_bytes, payload, ws,
                             (uint32_t)(2 * first / P / kLz4BlockBytes), (uint32_t)(2 * count / P / kLz4BlockBytes), (uint32_t)P,
-                            blocks_per_plane, st));
+                            blocks_per_plane, lz4_pitch_hint(pl, shape), st));
   }
   CKK(k_lz4_encode_end(reinterpret_cast<const uint8_t*>(d_planes), raw_bytes, payload, ws, st));
   unsigned long long hres[4] = {0, 0, 0, 0};

@@ -52,13 +52,16 @@ int k_lut_decode(const uint8_t* in, uint16_t* out, uint64_t n, const uint16_t* l
 // lz4_encode.cu
 size_t k_lz4_encode_workspace_bytes(uint64_t raw_bytes);
 // workspace[0..8) receives the payload size (u64) when the stream has drained; [16,28) block-kind counters
-int k_lz4_encode(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, cudaStream_t st);
+// pitch_bytes: distance in the stream between vertically adjacent voxels (a row of a bit plane: X * w / 8 bytes; a row of
+// 8-bit codes: X bytes), tried as a match offset like the short offsets 1..4; 0 (or not a multiple of 32): none. The
+// compressed bytes are a pure function of (input bytes, pitch_bytes).
+int k_lz4_encode(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, uint32_t pitch_bytes, cudaStream_t st);
 // the same in three steps, for input that becomes available piece by piece: begin (frame prefix), any number of block
 // sets — `nsets` sets of `count` consecutive 16 KiB blocks, set j starting at block first + j * set_stride (the pieces of
 // the 16/w bit planes that one z-slab contributes) —, end (offsets + compaction). Every block exactly once.
 int k_lz4_encode_begin(uint64_t raw_bytes, uint8_t* dst, void* workspace, cudaStream_t st);
 int k_lz4_encode_blocks(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, uint32_t first, uint32_t count,
-                        uint32_t nsets, uint32_t set_stride, cudaStream_t st);
+                        uint32_t nsets, uint32_t set_stride, uint32_t pitch_bytes, cudaStream_t st);
 int k_lz4_encode_end(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, cudaStream_t st);
 
 // lz4_decode.cu

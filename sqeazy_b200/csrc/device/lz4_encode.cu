@@ -4,18 +4,24 @@
 // (encoders/lz4.hpp:214-242, encoders/lz4_utils.hpp:99-173 encode_serial, :193-274 encode_parallel,
 // :175-190 remove_blanks). Output = valid LZ4 frame bytes (see lz4_format.h); compressed-byte parity
 // with liblz4 is not defined by the reference — validity, round trip through the
-// reference decoder and the compression ratio are.
+// reference decoder and the compression ratio are. The output is a pure function of the input bytes
+// (and the pitch hint): no result depends on the order in which threads run.
 //
 // Per block (16 KiB of input staged in shared memory by 512 threads):
 //   load    : 128-bit coalesced loads -> smem; all-equal blocks take a closed-form path
-//   phase A : every position finds a match candidate in parallel: offsets 1..4 from registers first, then a
-//             4096-entry shared-memory hash table holding positions of earlier 512-byte rounds; the first 3
-//             bytes after the 4-byte match give a 2-bit length code; a warp's 32 positions are one segment,
-//             so three ballots leave candidate mask + code planes per 32-byte segment
-//   phase B : every THREAD parses its own 32-byte segment greedily with bit operations only (no shuffles,
-//             no shared memory for matches shorter than 7), starting where a run that crosses the segment border
-//             would end; a match may overshoot into later segments of the warp's 1 KiB sub-block, whose entry
-//             points move until the warp's parse is stable (2.7 rounds per warp on bit planes, measured)
+//   phase A0: byte-equality bit masks E_q for five fixed offsets — 1, 2, 4, 3 and the row pitch of the stack in this
+//             stream (a 2048-voxel row of a bit plane is 256 bytes: what differs from the row above is what the
+//             sample scattered differently) — one bit per position, 32 positions per thread
+//   phase A1: fixed-offset candidates (>= 5 equal bytes) and their 2-bit length codes by shifts / ANDs on the masks
+//   phase A2: the positions without such a candidate (a few per cent of a sparse plane) are COMPACTED into a list and
+//             looked up in a shared-memory hash table of earlier positions, one wave per 1 KiB sub-block: the table
+//             holds the sub-blocks in front (atomicMax inserts behind a barrier => deterministic), all 512 threads
+//             work on list entries instead of 16 warps each meeting 32 barriers for a handful of lookups
+//   phase B : every THREAD parses its own 32-byte segment greedily with bit operations only; the length of a run
+//             (fixed-offset match) is read off the masks in O(1): ones to the end of the segment, whole segments by
+//             a per-warp "all ones" bit set, the rest from one more mask word. Hash matches are extended the same way
+//             where both sides sit in runs, 4 bytes at a time where not. A match may overshoot into later segments
+//             of the warp's 1 KiB sub-block, whose entry points move until the warp's parse is stable
 //   phase C : warp scans chain literal carries and encoded sizes (segments without a match hand their
 //             literals to the next sequence)
 //   phase D : every thread emits its own sequences; trailing literals are copied by the thread that owns
@@ -38,23 +44,29 @@ constexpr int kSegs = kB / 32;           // 32-byte segments, one per thread
 constexpr int kPad = 256;
 constexpr int kHashLog = 12;
 constexpr int kInf = 0x7FFFFFFF;
-constexpr int kEarlyRounds = 8;          // early-store test after the hash rounds of the first 4 KiB ...
+constexpr int kNumOff = 5;               // fixed offsets, in priority order: 1, 2, 4, 3, pitch
+constexpr int kListMax = 8192;           // positions that may look up the hash table (more: the rest goes without)
+constexpr int kEarlyBytes = 4096;        // early-store test after the hash waves of the first 4 KiB ...
 constexpr int kEarlyMin = 128;           // ... a block with fewer candidates than this is stored
+constexpr uint32_t kNoCand = 0xFFFFu;
 
 static_assert(kSegs == kThreads, "one segment per thread");
+static_assert(kSub == 1024 && kSegs / kWarps == 32, "a warp's 32 segments are one sub-block = one hash wave");
 
 struct __align__(16) EncSmem {
   uint32_t data[(kB + kPad) / 4];
   union {
-    uint16_t cand[kB];                   // phase A/B: candidate position per input position
-    uint32_t out[(kB + 64) / 4];         // phase D: encoded bytes (every cand read happens before the first out write)
+    uint16_t list[kListMax];             // phase A2: positions that look up; then, in place: candidate | code << 14 (kNoCand: none)
+    uint32_t out[(kB + 64) / 4];         // phase D: encoded bytes (every list read happens before the first out write)
   };
   union {
-    uint16_t htab[1 << kHashLog];        // phase A2 only
+    uint32_t htab[1 << kHashLog];        // phase A2 only: position + 1 of the last listed position with this hash (0: none)
     int seg_litbase[kSegs];              // phase D: dest(p) = seg_litbase + p for the literal run ending at the segment's first match
   };
-  uint32_t E[4][kSegs + 4];              // E[d-1][t] bit j: data[32t+j] == data[32t+j-d]   (d = 1..4, the short offsets)
-  uint32_t segHM[kSegs], segHC0[kSegs], segHC1[kSegs];   // per segment: hash-candidate mask and 2-bit length code planes
+  uint32_t E[kNumOff][kSegs + 4];        // E[q][t] bit j: data[32t+j] == data[32t+j-off(q)]
+  uint32_t segHM[kSegs];                 // per segment: positions with a hash candidate (>= 5 bytes)
+  uint32_t full[kNumOff][kWarps];        // per warp: segments whose E[q] word is all ones
+  int wave_start[kWarps + 1];            // list index of every sub-block's first entry
   int w_T[kWarps], w_has[kWarps], w_carry_in[kWarps], w_size[kWarps], w_off[kWarps], w_first[kWarps], w_next[kWarps];
   int final_off, final_lit, total;
   int early;                             // candidates seen by the early-store test
@@ -79,23 +91,52 @@ __device__ __forceinline__ int put_ext(uint8_t* p, int v) {
   return k;
 }
 
+// number of consecutive ones of E[q] from position x on (at least `cap` is reported as >= cap): the ones left in x's
+// segment, then whole segments by the per-warp "all ones" sets, then the ones at the start of the first other segment
+__device__ __forceinline__ int run_ones(const EncSmem& S, int q, int x, int cap) {
+  int t = x >> 5;
+  const int b = x & 31;
+  const uint32_t z = ~(S.E[q][t] >> b);          // zeros where the run goes on; the shifted-in bits end it at the segment border
+  const int r = z ? __ffs(z) - 1 : 32;           // (z == 0 only for b == 0 and a full word)
+  if (r < 32 - b) return r;
+  int len = 32 - b;
+  ++t;
+  while (len < cap && t < kSegs) {
+    const int l = t & 31;
+    const uint32_t nf = ~(S.full[q][t >> 5] >> l);   // zeros: full segments from t on (border of the warp: shifted-in bits)
+    int k = nf ? __ffs(nf) - 1 : 32;
+    if (k > 32 - l) k = 32 - l;
+    len += 32 * k;
+    t += k;
+    if (k < 32 - l) {                            // segment t is not full: its leading ones end the run
+      const uint32_t e = S.E[q][t];
+      len += __ffs(~e) - 1;
+      break;
+    }
+  }
+  return len;
+}
+
 // The general path of a block (phases A0..D on the bytes in S.data), kept out of line: the closed-form path of all-equal
 // blocks — 56 % of a background-removed stack, bound by bytes in flight — then keeps the short prologue and the register
 // allocation of a kernel that does nothing else. Returns the encoded size; `stored` when the block does not shrink.
-__device__ __noinline__ int encode_general(EncSmem& S, const int n, bool& stored_out) {
+// pitch_words: row pitch of the stack in this stream in 32-bit words (a multiple of 8), 0 = none.
+__device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pitch_words, bool& stored_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint8_t* data8 = reinterpret_cast<uint8_t*>(S.data);
   uint8_t* out8 = reinterpret_cast<uint8_t*>(S.out);
   int csize = 0;
   bool stored = false;
-  // (set here and not beside the block load: one more shared-memory store in the prologue cost the closed-form path of
-  //  all-equal blocks 7 %, 3.31 instead of 3.55 TB/s; two barriers lie between this store and the first atomicAdd)
+  // (set here and not beside the block load: shared-memory stores in the prologue delay the loads of the closed-form path
+  //  of all-equal blocks, which is bound by bytes in flight; barriers lie between these stores and their first use)
   if (tid == 0) S.early = 0;
-  // ---------------- phase A0: byte-equality bit masks for the offsets 1..4 ----------------
-  // In bit-plane data runs and 2/4-byte periods carry the long matches. A thread compares its 32-byte segment with
-  // itself shifted by d bytes (__vcmpeq4 on 8 words) and keeps one bit per position; a match of length L at i with
-  // offset d is then simply L consecutive ones in E_d starting at bit i — found, measured and extended with shifts,
-  // ANDs and ffs on registers, never touching the bytes again.
+#pragma unroll
+  for (int k = 0; k < (1 << kHashLog) / kThreads; ++k) S.htab[tid + k * kThreads] = 0u;
+  // ---------------- phase A0: byte-equality bit masks for the fixed offsets ----------------
+  // In bit-plane data runs, 2/4-byte periods and the row above carry the long matches. A thread compares its 32-byte
+  // segment with itself shifted by the offset (__vcmpeq4 on 8 words) and keeps one bit per position; a match of length L
+  // at i with offset off(q) is then simply L consecutive ones in E_q starting at bit i — found, measured and extended
+  // with shifts, ANDs and ffs on registers, never touching the bytes again.
   const int seg_lo = tid * 32;
   {
     uint32_t W[9];
@@ -105,7 +146,8 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, bool& stored
     const int lim = n - kLz4LastLiterals - seg_lo;     // match bytes never touch the last 5 bytes of the block
     const uint32_t tailmask = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : (1u << lim) - 1u);
 #pragma unroll
-    for (int d = 1; d <= 4; ++d) {
+    for (int q = 0; q < 4; ++q) {
+      const int d = q == 0 ? 1 : (q == 1 ? 2 : (q == 2 ? 4 : 3));
       uint32_t e = 0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -114,22 +156,33 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, bool& stored
         e |= (((eq & 0x08040201u) * 0x01010101u) >> 24) << (4 * k);
       }
       if (tid == 0) e &= ~((1u << d) - 1u);            // no source in front of the block
-      S.E[d - 1][tid] = e & tailmask;
+      S.E[q][tid] = e & tailmask;
     }
-    if (tid < 4) S.E[tid][kSegs] = 0;
+    {
+      uint32_t e = 0;
+      if (pitch_words > 0 && 8 * tid >= pitch_words) {   // (whole segments: the pitch is a multiple of 32 bytes)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t eq = __vcmpeq4(W[k + 1], S.data[8 * tid + k - pitch_words]);
+          e |= (((eq & 0x08040201u) * 0x01010101u) >> 24) << (4 * k);
+        }
+      }
+      S.E[4][tid] = e & tailmask;
+    }
+    if (tid < kNumOff) S.E[tid][kSegs] = 0;
   }
   __syncthreads();
 
-  // ---------------- phase A1: short-offset candidates of this thread's segment (registers only) ----------------
-  uint32_t Ms = 0, D0 = 0, D1 = 0, C0 = 0, C1 = 0;     // candidate mask, offset-1 planes, length code planes
+  // ---------------- phase A1: fixed-offset candidates of this thread's segment (registers only) ----------------
+  uint32_t Ms = 0, D0 = 0, D1 = 0, D2 = 0, C0 = 0, C1 = 0;   // candidate mask, offset index planes, length code planes
+  uint32_t wants = 0;                                        // positions that look up the hash table
   {
     uint32_t L6 = 0, L7 = 0, L8 = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int d = q == 0 ? 1 : (q == 1 ? 2 : (q == 2 ? 4 : 3));   // priority order
+    for (int q = 0; q < kNumOff; ++q) {
       // matches never cross the warp's 1 KiB sub-block: the last segment sees no successor
-      const unsigned long long e =
-          (unsigned long long)S.E[d - 1][tid] | ((unsigned long long)(lane == 31 ? 0u : S.E[d - 1][tid + 1]) << 32);
+      const uint32_t own = S.E[q][tid];
+      const unsigned long long e = (unsigned long long)own | ((unsigned long long)(lane == 31 ? 0u : S.E[q][tid + 1]) << 32);
       const unsigned long long r5 = e & (e >> 1) & (e >> 2) & (e >> 3) & (e >> 4);
       const unsigned long long r6 = r5 & (e >> 5), r7 = r6 & (e >> 6), r8 = r7 & (e >> 7);
       const uint32_t sel = (uint32_t)r5 & ~Ms;         // at least 5 bytes and no better-ranked offset yet
@@ -137,90 +190,135 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, bool& stored
       L6 |= sel & (uint32_t)r6;
       L7 |= sel & (uint32_t)r7;
       L8 |= sel & (uint32_t)r8;
-      if ((d - 1) & 1) D0 |= sel;
-      if ((d - 1) & 2) D1 |= sel;
+      if (q & 1) D0 |= sel;
+      if (q & 2) D1 |= sel;
+      if (q & 4) D2 |= sel;
+      const uint32_t fullset = __ballot_sync(0xffffffffu, own == 0xffffffffu);
+      if (lane == 0) S.full[q][warp] = fullset;
     }
     const int lim = n - kLz4MFLimit + 1 - seg_lo;      // a match starts at most 12 bytes before the block end
     const uint32_t valid = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : (1u << lim) - 1u);
     Ms &= valid;
     C0 = (L6 ^ L7 ^ L8) & Ms;                          // code = number of the planes L6,L7,L8 that are set: 5,6,7,>=8 bytes
     C1 = L7 & Ms;
-    S.segHM[tid] = ~Ms & valid;                        // positions that still want a hash candidate
-    S.segHC0[tid] = 0;                                 // (a segment nobody looks up in keeps HM = wants = 0 and these zeros)
-    S.segHC1[tid] = 0;
+    wants = ~Ms & valid;
+    S.segHM[tid] = 0;
   }
-  int ncand = __reduce_add_sync(0xffffffffu, __popc(Ms));   // this warp's candidates so far (warp-uniform)
-  // (the barrier between A1 and A2 carries the one bit the early-store test needs first: a warp that is already rich in
-  //  short-offset candidates — every compressible bit-plane block — settles it for the CTA at no cost)
-  const int rich = __syncthreads_or(ncand >= kEarlyMin);
+  const int ncand_short = __reduce_add_sync(0xffffffffu, __popc(Ms));   // this warp's candidates so far (warp-uniform)
 
-  // ---------------- phase A2: hash candidates for the positions without a short-offset match ----------------
-  // 32 rounds of 512 positions against a 4096-entry table of earlier positions. This warp covers segment 16 r + warp in
-  // round r; `myrounds` has the rounds in which that segment looks anything up (a quarter of them on bit planes), in the
-  // others the warp only meets the round's barrier. Only the positions that look up are inserted.
-  const uint32_t myrounds = __ballot_sync(0xffffffffu, S.segHM[lane * kWarps + warp] != 0u);
-  int nfound = Ms != 0;
-  // Early store: a block whose candidates (short-offset ones of the whole block + hash candidates of the first
-  // kEarlyRounds rounds = 4 KiB) are fewer than one per 32 sampled bytes is noise — camera-noise bit planes, 8-bit
-  // quantiser codes — and would shrink by < 3 % (tools/lz4_model.c: such blocks have < 70 candidates and end at
-  // 0.97..1.00 of their size, everything that compresses to <= 0.82 has > 600). It is stored without the remaining
-  // rounds, the parse and the emission, which is also what makes its decode a plain copy.
-  bool early_stored = false;
-  auto hash_round = [&](int r) {
-    if ((myrounds >> r) & 1u) {
-      const int seg = r * kWarps + warp;
-      const uint32_t ns = S.segHM[seg];
-      const int i = r * kThreads + tid;
-      bool found = false;
-      int code = 0;
-      if ((ns >> lane) & 1u) {
-        const uint32_t v = load4(S.data, i);
-        const uint32_t h = (v * 2654435761u) >> (32 - kHashLog);
-        // the table is read and written without a barrier in between: an entry may already belong to this round
-        // (any earlier position with the same 4 bytes is a valid source; c < i and the compare make it safe)
-        const uint32_t c = S.htab[h];
-        if (c < (uint32_t)i && load4(S.data, (int)c) == v) {
-          const int maxlen = min((i & ~(kSub - 1)) + kSub, n - kLz4LastLiterals) - i;
-          const uint32_t x = load4(S.data, i + 4) ^ load4(S.data, (int)c + 4);
-          int len = 4 + (x ? ((__ffs(x) - 1) >> 3) : 4);
-          if (len > maxlen) len = maxlen;
-          // 4-byte matches save one byte and cost a sequence on both ends of the codec: dropping them keeps the ratio
-          // within ~1 % on bit planes, improves it on background-removed stacks and matches liblz4 on noisy 8-bit
-          // codes (tools/lz4_model.c), while halving the number of sequences
-          if (len >= 5) {
-            found = true;
-            code = len - 5 < 3 ? len - 5 : 3;   // 0,1,2: exact length 5,6,7; 3: at least 8, extended in phase B
-            S.cand[i] = (uint16_t)c;
+  // ---------------- phase A2: hash candidates for the positions without a fixed-offset match ----------------
+  // The wanting positions of the block are compacted, in order, into S.list (exclusive scan of the per-thread counts).
+  // Wave w = the entries of sub-block w: all threads look their entries up in a table that holds the listed positions of
+  // the sub-blocks in front (sources inside the sub-block come from the fixed offsets), then insert them with atomicMax —
+  // the last position with a hash wins whatever the thread order. An entry is overwritten by its result.
+  int mybase;
+  {
+    const int cnt = __popc(wants);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) S.w_size[warp] = incl;
+    // (the barrier carries the one bit the early-store test needs first: a warp that is already rich in fixed-offset
+    //  candidates — every compressible bit-plane block — settles it for the CTA at no cost)
+    const int rich = __syncthreads_or(ncand_short >= kEarlyMin);
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += S.w_size[w];
+    mybase = wbase + incl - cnt;
+    if (lane == 0) S.wave_start[warp] = wbase;
+    if (tid == kThreads - 1) S.wave_start[kWarps] = wbase + incl;
+    {
+      uint32_t m = wants;
+      int e = mybase;
+      while (m && e < kListMax) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        S.list[e++] = (uint16_t)(seg_lo + j);
+      }
+    }
+    const bool test_early = !rich && n > kEarlyBytes;
+    if (test_early && lane == 0 && ncand_short) atomicAdd(&S.early, ncand_short);
+    __syncthreads();
+
+    // Early store: a block whose candidates (fixed-offset ones of the whole block + hash candidates of the first 4 KiB)
+    // are fewer than one per 32 sampled bytes is noise — camera-noise bit planes, 8-bit quantiser codes — and would
+    // shrink by < 3 % (tools/lz4_model.c: such blocks have < 70 candidates and end at 0.97..1.00 of their size, everything
+    // that compresses to <= 0.82 has > 600). It is stored without the remaining waves, the parse and the emission,
+    // which is also what makes its decode a plain copy.
+    bool early_stored = false;
+#pragma unroll 1
+    for (int wave = 0; wave < kWarps; ++wave) {
+      const int s = S.wave_start[wave];
+      const int t = min(S.wave_start[wave + 1], kListMax);
+      const bool last = wave == kWarps - 1;
+      if (s < t) {                       // (uniform over the CTA)
+        int pi[2];                       // up to 1024 entries per wave: two per thread
+        uint32_t ph[2];
+#pragma unroll
+        for (int slot = 0; slot < 2; ++slot) {
+          const int e = s + tid + slot * kThreads;
+          pi[slot] = -1;
+          bool found = false;
+          if (e < t) {
+            const int i = (int)S.list[e];
+            const uint32_t v = load4(S.data, i);
+            const uint32_t h = (v * 2654435761u) >> (32 - kHashLog);
+            pi[slot] = i;
+            ph[slot] = h;
+            uint32_t res = kNoCand;
+            const uint32_t c1 = wave > 0 ? S.htab[h] : 0u;
+            if (c1) {
+              const int c = (int)c1 - 1;
+              if (load4(S.data, c) == v) {
+                const int maxlen = min((i & ~(kSub - 1)) + kSub, n - kLz4LastLiterals) - i;
+                const uint32_t x = load4(S.data, i + 4) ^ load4(S.data, c + 4);
+                int len = 4 + (x ? ((__ffs(x) - 1) >> 3) : 4);
+                if (len > maxlen) len = maxlen;
+                // 4-byte matches save one byte and cost a sequence on both ends of the codec: dropping them keeps the
+                // ratio within ~1 % on bit planes, improves it on background-removed stacks and matches liblz4 on noisy
+                // 8-bit codes (tools/lz4_model.c), while halving the number of sequences
+                if (len >= 5) {
+                  found = true;
+                  res = (uint32_t)c | ((uint32_t)(len - 5 < 3 ? len - 5 : 3) << 14);   // code 0,1,2: exactly 5,6,7 bytes; 3: >= 8
+                  atomicOr(&S.segHM[i >> 5], 1u << (i & 31));
+                }
+              }
+            }
+            S.list[e] = (uint16_t)res;
+          }
+          if (test_early && wave < kEarlyBytes / kSub) {
+            const uint32_t fm = __ballot_sync(0xffffffffu, found);
+            if (lane == 0 && fm) atomicAdd(&S.early, __popc(fm));
           }
         }
-        S.htab[h] = (uint16_t)i;
+        // (the inserts follow behind the barrier below)
+        const bool early_check = test_early && wave == kEarlyBytes / kSub - 1;
+        __syncthreads();                 // this wave's results, candidate bits and the early counter are complete
+        if (early_check) {
+          early_stored = S.early < kEarlyMin;
+          if (early_stored) break;
+        }
+        if (!last) {
+#pragma unroll
+          for (int slot = 0; slot < 2; ++slot)
+            if (pi[slot] >= 0) atomicMax(&S.htab[ph[slot]], (uint32_t)pi[slot] + 1u);
+          __syncthreads();               // the table holds this sub-block before the next one looks anything up
+        }
+      } else if (test_early && wave == kEarlyBytes / kSub - 1) {
+        __syncthreads();
+        early_stored = S.early < kEarlyMin;
+        if (early_stored) break;
       }
-      const uint32_t HM = __ballot_sync(0xffffffffu, found);
-      const uint32_t HC0 = __ballot_sync(0xffffffffu, found && (code & 1));
-      const uint32_t HC1 = __ballot_sync(0xffffffffu, found && (code & 2));
-      if (lane == 0) {
-        S.segHM[seg] = HM;
-        S.segHC0[seg] = HC0;
-        S.segHC1[seg] = HC1;
-      }
-      nfound |= HM != 0;
-      if (!rich) ncand += __popc(HM);
     }
-    __syncthreads();   // one barrier per round keeps the warps within a round of each other
-  };
-  int r0 = 0, r1 = (rich || n <= kEarlyRounds * kThreads) ? kB / kThreads : kEarlyRounds;
-  while (true) {
-#pragma unroll 1
-    for (int r = r0; r < r1; ++r) hash_round(r);
-    if (r1 == kB / kThreads) break;
-    if (lane == 0 && ncand) atomicAdd(&S.early, ncand);
-    __syncthreads();
-    early_stored = S.early < kEarlyMin;
-    if (early_stored) break;
-    r0 = r1;
-    r1 = kB / kThreads;
+    if (early_stored) {
+      stored_out = true;
+      return 0;
+    }
   }
-  const int any_found = early_stored ? 0 : __syncthreads_or(nfound);
+  const uint32_t HM = S.segHM[tid];
+  const int any_found = __syncthreads_or((Ms | HM) != 0u);
 
   if (!any_found) {
     stored = true;
@@ -229,111 +327,72 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, bool& stored
     // A match may overshoot into the following segments of the same warp; their entry point moves and
     // they re-parse until the warp's parse is stable (lane k is final after at most k+1 rounds).
     const int limit = min((warp + 1) * kSub, n - kLz4LastLiterals);
-    const uint32_t M = Ms | S.segHM[tid];              // hash candidates exist only where no short-offset one does
-    C0 |= S.segHC0[tid];
-    C1 |= S.segHC1[tid];
+    const uint32_t M = Ms | HM;                        // hash candidates exist only where no fixed-offset one does
     uint32_t Sel = 0;
     unsigned long long lens = 0;       // lengths of the long matches of this segment, 11 bits each, in order
     // First guess of where the parse enters this segment: if the previous segment ends inside a run with period d
     // (its last five bytes continue one), the match that covers them runs on to the end of the ones of E_d here. A
-    // segment in the middle of a long run then has nothing to parse (and nothing to measure: every lane of a run
-    // scanning to its end was 5 % of the kernel), and half of the repair parses of the cascade disappear. A wrong
-    // guess is corrected like any other moved entry point.
+    // segment in the middle of a long run then has nothing to parse, and half of the repair parses of the cascade
+    // disappear. A wrong guess is corrected like any other moved entry point.
     int entry = 0, exit_abs = seg_lo + 32;
     if (lane > 0) {
 #pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        const uint32_t prevE = S.E[d][tid - 1], curE = S.E[d][tid];
+      for (int q = 0; q < kNumOff; ++q) {
+        const uint32_t prevE = S.E[q][tid - 1], curE = S.E[q][tid];
         if ((prevE >> 27) == 31u) entry = max(entry, curE == 0xffffffffu ? 32 : __ffs(~curE) - 1);
       }
     }
     bool need = true;
     while (true) {                     // cascade rounds
-      int pos = entry, nlong = 0, pj = 0, plen = 0;
-      const bool parsing = need;       // lanes whose entry did not move keep the parse of an earlier round
-      bool done = !need, pend = false;
-      if (need) { Sel = 0; lens = 0; }
-      while (true) {
-        if (!done && !pend) {
-          // thread-serial parse: bit operations only; a long match gets at most 16 more bytes here
-          while (true) {
-            if (pos >= 32) { done = true; break; }
-            const uint32_t mm = M & (0xffffffffu << pos);
-            if (!mm) { done = true; break; }
-            const int j = __ffs(mm) - 1;
-            const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
-            int len = 5 + code;
-            if (code == 3 && ((Ms >> j) & 1u)) {
-              // short-offset match: count the ones that follow in E_d, 32 positions per step
-              const int i = seg_lo + j, maxlen = limit - i;
-              const uint32_t* Ed = S.E[((D0 >> j) & 1u) | (((D1 >> j) & 1u) << 1)];
+      if (need) {
+        // thread-serial parse: bit operations, the masks and (for hash matches) a few words of the block
+        int pos = entry, nlong = 0;
+        Sel = 0;
+        lens = 0;
+        while (pos < 32) {
+          const uint32_t mm = M & (0xffffffffu << pos);
+          if (!mm) break;
+          const int j = __ffs(mm) - 1;
+          const int i = seg_lo + j, maxlen = limit - i;
+          int code, len;
+          if ((Ms >> j) & 1u) {
+            code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
+            len = 5 + code;
+            if (code == 3) {           // a run: its length is in the masks
+              const int q = ((D0 >> j) & 1u) | (((D1 >> j) & 1u) << 1) | (((D2 >> j) & 1u) << 2);
+              len = run_ones(S, q, i, maxlen);
+            }
+          } else {
+            const int e = mybase + __popc(wants & ((1u << j) - 1u));
+            const uint32_t ce = S.list[e];
+            const int c = (int)(ce & 0x3FFFu);
+            code = (int)(ce >> 14);
+            len = 5 + code;
+            C0 = (C0 & ~(1u << j)) | ((uint32_t)(code & 1) << j);      // phases C and D read the code from the planes
+            C1 = (C1 & ~(1u << j)) | ((uint32_t)(code >> 1) << j);
+            if (code == 3) {
+              // both sides inside runs (the zeros around an isolated byte of a sparse plane): equal as far as both runs go
               len = 8;
               while (len < maxlen) {
-                const int p = i + len, avail = 32 - (p & 31);
-                const uint32_t z = ~(Ed[p >> 5] >> (p & 31));     // zeros where the match goes on
-                const int ones = z ? __ffs(z) - 1 : 32;
-                if (ones < avail) { len += ones; break; }
-                len += avail;
-              }
-              if (len > maxlen) len = maxlen;
-              lens |= (unsigned long long)len << (11 * nlong);
-              nlong++;
-            } else if (code == 3) {
-              const int i = seg_lo + j, c = (int)S.cand[i], maxlen = limit - i;
-              len = 8;
-              bool open = true;
-#pragma unroll 1
-              for (int it = 0; it < 4; ++it) {
-                if (len >= maxlen) { open = false; break; }
+                const int k = min(run_ones(S, 0, i + len, maxlen - len), run_ones(S, 0, c + len, maxlen - len));
+                len += k;
+                if (len >= maxlen) break;
                 const uint32_t x = load4(S.data, i + len) ^ load4(S.data, c + len);
-                if (x) { len += (__ffs(x) - 1) >> 3; open = false; break; }
+                if (x) { len += (__ffs(x) - 1) >> 3; break; }
                 len += 4;
               }
-              if (len >= maxlen) { len = maxlen; open = false; }
-              if (open) { pend = true; pj = j; plen = len; break; }   // still matching: the warp finishes it
-              lens |= (unsigned long long)len << (11 * nlong);
-              nlong++;
             }
-            Sel |= 1u << j;
-            pos = j + len;
-          }
-        }
-        uint32_t pm = __ballot_sync(0xffffffffu, pend);
-        if (!pm) break;                // no lane is waiting => every lane is done
-        while (pm) {
-          const int l = __ffs(pm) - 1;
-          pm &= pm - 1;
-          const int i = __shfl_sync(0xffffffffu, seg_lo + pj, l);
-          const int c = (int)S.cand[i], maxlen = limit - i;
-          int len = __shfl_sync(0xffffffffu, plen, l);
-          while (len < maxlen) {       // 128 bytes per step
-            const int k = len + lane * 4;
-            const uint32_t x = load4(S.data, i + k) ^ load4(S.data, c + k);
-            const uint32_t bm = __ballot_sync(0xffffffffu, x != 0);
-            if (bm) {
-              const int f = __ffs(bm) - 1;
-              const uint32_t d = __shfl_sync(0xffffffffu, x, f);
-              len += f * 4 + ((__ffs(d) - 1) >> 3);
-              break;
-            }
-            len += 128;
           }
           if (len > maxlen) len = maxlen;
-          if (lane == l) {
+          if (code == 3) {
             lens |= (unsigned long long)len << (11 * nlong);
             nlong++;
-            Sel |= 1u << pj;
-            pos = pj + len;
-            pend = false;
           }
-          // later lanes whose pending match starts inside [i, i+len) parsed a stale speculation: drop them all at
-          // once (their entry point moves in the cascade step, so they are parsed again)
-          const bool stale = pend && lane > l && seg_lo + pj < i + len;
-          if (stale) { pend = false; done = true; pos = 0; Sel = 0; lens = 0; }
-          pm &= ~__ballot_sync(0xffffffffu, stale);
+          Sel |= 1u << j;
+          pos = j + len;
         }
+        exit_abs = seg_lo + (pos > 32 ? pos : 32);
       }
-      if (parsing) exit_abs = seg_lo + (pos > 32 ? pos : 32);
       int incl = exit_abs;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -419,7 +478,13 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, bool& stored
           const int j = __ffs(m) - 1;
           m &= m - 1;
           const int i = seg_lo + j;
-          const uint32_t off = ((Ms >> j) & 1u) ? 1u + ((D0 >> j) & 1u) + 2u * ((D1 >> j) & 1u) : (uint32_t)(i - (int)S.cand[i]);
+          uint32_t off;
+          if ((Ms >> j) & 1u) {
+            const uint32_t q = ((D0 >> j) & 1u) | (((D1 >> j) & 1u) << 1) | (((D2 >> j) & 1u) << 2);
+            off = q == 0 ? 1u : (q == 1 ? 2u : (q == 2 ? 4u : (q == 3 ? 3u : 4u * (uint32_t)pitch_words)));
+          } else {
+            off = (uint32_t)(i - (int)(S.list[mybase + __popc(wants & ((1u << j) - 1u))] & 0x3FFFu));
+          }
           offs[k >> 1] |= off << (16 * (k & 1));
         }
       }
@@ -490,7 +555,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, bool& stored
 
 __global__ void __launch_bounds__(kThreads, 3)
 lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* __restrict__ dst, uint32_t nblocks,
-                  uint8_t* __restrict__ staging, uint32_t* __restrict__ stats, uint32_t first, uint32_t set_stride) {
+                  uint8_t* __restrict__ staging, uint32_t* __restrict__ stats, uint32_t first, uint32_t set_stride, int pitch_words) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EncSmem& S = *reinterpret_cast<EncSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -538,7 +603,6 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
     }
   }
   if (tid < kPad / 4) S.data[kB / 4 + tid] = 0;
-  for (int i = tid; i < (1 << kHashLog) / 2; i += kThreads) reinterpret_cast<uint32_t*>(S.htab)[i] = 0xFFFFFFFFu;
   const int all_same = __syncthreads_and(same ? 1 : 0);
 
   int csize = 0;        // encoded bytes (without the 4-byte block header)
@@ -569,7 +633,7 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
     __syncthreads();
     csize = S.total;
   } else {
-    csize = encode_general(S, n, stored);
+    csize = encode_general(S, n, pitch_words, stored);
     if (stored) { csize = n; kind = 2; }
   }
   __syncthreads();
@@ -793,15 +857,20 @@ int k_lz4_encode_begin(uint64_t raw_bytes, uint8_t* dst, void* workspace, cudaSt
   return (int)cudaGetLastError();
 }
 
+// pitch hint -> words; only multiples of 32 bytes well inside a block qualify (whole segments, sources inside the block)
+static int pitch_words_of(uint32_t pitch_bytes) {
+  return (pitch_bytes >= 32u && pitch_bytes <= (uint32_t)kB / 2 && pitch_bytes % 32u == 0u) ? (int)(pitch_bytes / 4u) : 0;
+}
+
 int k_lz4_encode_blocks(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, uint32_t first, uint32_t count,
-                        uint32_t nsets, uint32_t set_stride, cudaStream_t st) {
+                        uint32_t nsets, uint32_t set_stride, uint32_t pitch_bytes, cudaStream_t st) {
   EncWs W;
   if (int e = enc_ws(raw_bytes, workspace, W)) return e;
   if (!count || !nsets) return 0;
   if (nsets > 65535u || (uint64_t)first + (uint64_t)(nsets - 1) * set_stride + count > W.nblocks) return -2;
   SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
   lz4_encode_kernel<<<dim3(count, nsets), kThreads, sizeof(EncSmem), st>>>(src, raw_bytes, dst, W.nblocks, W.staging, W.stats, first,
-                                                                            set_stride);
+                                                                            set_stride, pitch_words_of(pitch_bytes));
   SQYB_COUNT_LAUNCH(1);
   return (int)cudaGetLastError();
 }
@@ -820,11 +889,11 @@ int k_lz4_encode_end(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void*
   return (int)cudaGetLastError();
 }
 
-int k_lz4_encode(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, cudaStream_t st) {
+int k_lz4_encode(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, uint32_t pitch_bytes, cudaStream_t st) {
   EncWs W;
   if (int e = enc_ws(raw_bytes, workspace, W)) return e;
   if (int e = k_lz4_encode_begin(raw_bytes, dst, workspace, st)) return e;
-  if (int e = k_lz4_encode_blocks(src, raw_bytes, dst, workspace, 0, W.nblocks, 1, 0, st)) return e;
+  if (int e = k_lz4_encode_blocks(src, raw_bytes, dst, workspace, 0, W.nblocks, 1, 0, pitch_bytes, st)) return e;
   return k_lz4_encode_end(src, raw_bytes, dst, workspace, st);
 }
 

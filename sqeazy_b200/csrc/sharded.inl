@@ -249,6 +249,7 @@ int host_encode_sharded(const Pipeline& pl_in, const char* src, const std::vecto
   char* payload = dst + reserve;
   const uint64_t prefix = lz4_prefix_bytes(nblocks);
   const int T = std::max(1, staging_threads(nthreads) / G);
+  const uint32_t pitch_hint = lz4_pitch_hint(pl_in, shape);
 
   DevSetLock locks;
   locks.acquire(plan.dev);
@@ -329,7 +330,7 @@ int host_encode_sharded(const Pipeline& pl_in, const char* src, const std::vecto
         } else {
           CKK(k_bitswap_encode_range(w, W.d_in, static_cast<uint16_t*>(d_planes), W.n, first, count, thr, st));
           CKK(k_lz4_encode_blocks(static_cast<const uint8_t*>(d_planes), W.sbytes, W.d_out, W.ws, (uint32_t)(2 * first / P / kLz4BlockBytes),
-                                  (uint32_t)(2 * count / P / kLz4BlockBytes), P, (uint32_t)W.bpp, st));
+                                  (uint32_t)(2 * count / P / kLz4BlockBytes), P, (uint32_t)W.bpp, pitch_hint, st));
         }
       }
       if (kind != ShardKind::QuantLz4) CKK(k_lz4_encode_end(static_cast<const uint8_t*>(d_planes), W.sbytes, W.d_out, W.ws, st));
@@ -360,7 +361,7 @@ int host_encode_sharded(const Pipeline& pl_in, const char* src, const std::vecto
       uint8_t* d_lut = reinterpret_cast<uint8_t*>(static_cast<uint32_t*>(sp) + 65536);
       CK(cudaMemcpyAsync(d_lut, lut_enc.data(), 65536, cudaMemcpyHostToDevice, st));
       CKK(k_lut_apply(W.d_in, static_cast<uint8_t*>(codes), W.n, d_lut, st));
-      CKK(k_lz4_encode(static_cast<const uint8_t*>(codes), W.sbytes, W.d_out, W.ws, st));
+      CKK(k_lz4_encode(static_cast<const uint8_t*>(codes), W.sbytes, W.d_out, W.ws, pitch_hint, st));
       return 0;
     };
     // block words of this GPU -> host, piece sizes

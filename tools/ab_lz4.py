@@ -33,7 +33,11 @@ for name, x in inputs.items():
         for lname, L in libs:
             n = c_long(0)
             def run():
-                rc = L.sqyx_lz4_encode(c_void_p(x.data_ptr()), c_long(x.numel()), c_void_p(outbuf.data_ptr()), c_long(outbuf.numel()), ctypes.byref(n), st)
+                if hasattr(L, "sqyx_lz4_encode_ex"):
+                    pitch = 2048 if name == "quantiser codes" else 256
+                    rc = L.sqyx_lz4_encode_ex(c_void_p(x.data_ptr()), c_long(x.numel()), c_void_p(outbuf.data_ptr()), c_long(outbuf.numel()), ctypes.byref(n), c_long(pitch), st)
+                else:
+                    rc = L.sqyx_lz4_encode(c_void_p(x.data_ptr()), c_long(x.numel()), c_void_p(outbuf.data_ptr()), c_long(outbuf.numel()), ctypes.byref(n), st)
                 assert rc == 0
             run(); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
