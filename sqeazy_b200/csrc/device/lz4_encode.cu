@@ -45,10 +45,12 @@ constexpr int kPad = 256;
 constexpr int kHashLog = 12;
 constexpr int kInf = 0x7FFFFFFF;
 constexpr int kNumOff = 5;               // fixed offsets, in priority order: 1, 2, 4, 3, pitch
-constexpr int kListMax = 8192;           // positions that may look up the hash table (more: the rest goes without)
+constexpr int kListMax = 15104;          // positions that may look up the hash table (more: the rest goes without; sized so that
+                                         // three CTAs still fit an SM — only all-noise blocks list more, and those are stored)
 constexpr int kEarlyBytes = 4096;        // early-store test after the hash waves of the first 4 KiB ...
 constexpr int kEarlyMin = 128;           // ... a block with fewer candidates than this is stored
 constexpr uint32_t kNoCand = 0xFFFFu;
+constexpr uint32_t kNoPos = 0xFFFFFFFFu;
 
 static_assert(kSegs == kThreads, "one segment per thread");
 static_assert(kSub == 1024 && kSegs / kWarps == 32, "a warp's 32 segments are one sub-block = one hash wave");
@@ -60,8 +62,11 @@ struct __align__(16) EncSmem {
     uint32_t out[(kB + 64) / 4];         // phase D: encoded bytes (every list read happens before the first out write)
   };
   union {
-    uint32_t htab[1 << kHashLog];        // phase A2 only: position + 1 of the last listed position with this hash (0: none)
-    int seg_litbase[kSegs];              // phase D: dest(p) = seg_litbase + p for the literal run ending at the segment's first match
+    uint32_t htab[1 << kHashLog];        // phase A2 only: FIRST listed position of the block with this hash (kNoPos: none)
+    struct {
+      int seg_litbase[kSegs];            // phase D: dest(p) = seg_litbase + p for the literal run ending at the segment's first match
+      uint16_t lead[kNumOff][kSegs];     // phase B: ones of E[q] from the first position of segment t on, to the end of the warp's sub-block at most
+    };
   };
   uint32_t E[kNumOff][kSegs + 4];        // E[q][t] bit j: data[32t+j] == data[32t+j-off(q)]
   uint32_t segHM[kSegs];                 // per segment: positions with a hash candidate (>= 5 bytes)
@@ -71,6 +76,8 @@ struct __align__(16) EncSmem {
   int final_off, final_lit, total;
   int early;                             // candidates seen by the early-store test
 };
+
+static_assert(sizeof(EncSmem) <= (228 * 1024 - 3 * 1024) / 3, "three CTAs per SM (1 KiB of each CTA's share is the system's)");
 
 __device__ __forceinline__ int ext_bytes(int v) {
   if (v < 15) return 0;          // by far the common case: keep the division off the hot path
@@ -91,30 +98,15 @@ __device__ __forceinline__ int put_ext(uint8_t* p, int v) {
   return k;
 }
 
-// number of consecutive ones of E[q] from position x on (at least `cap` is reported as >= cap): the ones left in x's
-// segment, then whole segments by the per-warp "all ones" sets, then the ones at the start of the first other segment
-__device__ __forceinline__ int run_ones(const EncSmem& S, int q, int x, int cap) {
-  int t = x >> 5;
-  const int b = x & 31;
+// number of consecutive ones of E[q] from position x on, inside the sub-block of x: the ones left in x's segment, then
+// what the table says about the segments behind it (S.lead: computed once per segment with ballots and a shuffle, so that
+// the few lanes that measure a run do not walk the masks themselves)
+__device__ __forceinline__ int run_ones(const EncSmem& S, int q, int x) {
+  const int t = x >> 5, b = x & 31;
   const uint32_t z = ~(S.E[q][t] >> b);          // zeros where the run goes on; the shifted-in bits end it at the segment border
   const int r = z ? __ffs(z) - 1 : 32;           // (z == 0 only for b == 0 and a full word)
-  if (r < 32 - b) return r;
-  int len = 32 - b;
-  ++t;
-  while (len < cap && t < kSegs) {
-    const int l = t & 31;
-    const uint32_t nf = ~(S.full[q][t >> 5] >> l);   // zeros: full segments from t on (border of the warp: shifted-in bits)
-    int k = nf ? __ffs(nf) - 1 : 32;
-    if (k > 32 - l) k = 32 - l;
-    len += 32 * k;
-    t += k;
-    if (k < 32 - l) {                            // segment t is not full: its leading ones end the run
-      const uint32_t e = S.E[q][t];
-      len += __ffs(~e) - 1;
-      break;
-    }
-  }
-  return len;
+  if (r < 32 - b || (t & 31) == 31) return min(r, 32 - b);
+  return 32 - b + (int)S.lead[q][t + 1];
 }
 
 // The general path of a block (phases A0..D on the bytes in S.data), kept out of line: the closed-form path of all-equal
@@ -131,7 +123,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
   //  of all-equal blocks, which is bound by bytes in flight; barriers lie between these stores and their first use)
   if (tid == 0) S.early = 0;
 #pragma unroll
-  for (int k = 0; k < (1 << kHashLog) / kThreads; ++k) S.htab[tid + k * kThreads] = 0u;
+  for (int k = 0; k < (1 << kHashLog) / kThreads; ++k) S.htab[tid + k * kThreads] = kNoPos;
   // ---------------- phase A0: byte-equality bit masks for the fixed offsets ----------------
   // In bit-plane data runs, 2/4-byte periods and the row above carry the long matches. A thread compares its 32-byte
   // segment with itself shifted by the offset (__vcmpeq4 on 8 words) and keeps one bit per position; a match of length L
@@ -229,7 +221,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
     mybase = wbase + incl - cnt;
     if (lane == 0) S.wave_start[warp] = wbase;
     if (tid == kThreads - 1) S.wave_start[kWarps] = wbase + incl;
-    {
+    auto write_list = [&]() {
       uint32_t m = wants;
       int e = mybase;
       while (m && e < kListMax) {
@@ -237,84 +229,87 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
         m &= m - 1;
         S.list[e++] = (uint16_t)(seg_lo + j);
       }
-    }
+    };
+    // a block that may turn out to be noise lists its first 4 KiB only before that is known (in noise every position
+    // wants a lookup: 32 stores per thread)
     const bool test_early = !rich && n > kEarlyBytes;
+    if (!test_early || tid < kEarlyBytes / 32) write_list();
     if (test_early && lane == 0 && ncand_short) atomicAdd(&S.early, ncand_short);
     __syncthreads();
 
+    // The table keeps the FIRST listed position of the block per hash (atomicMin: the same whatever the thread order),
+    // filled before anything is looked up: a position finds the earliest occurrence of its four bytes — in its own
+    // sub-block as well — and the whole phase is two sweeps over the list with all 512 threads instead of a wave per
+    // sub-block (16 x 2 barriers, most threads idle). tools/lz4_model2.c (FIRST=1): ratio +0.1..0.5 % over the waves.
+    const int total = min(S.wave_start[kWarps], kListMax);
+    auto insert = [&](int from, int to) {
+      for (int e = from + tid; e < to; e += kThreads) {
+        const int i = (int)S.list[e];
+        const uint32_t h = (load4(S.data, i) * 2654435761u) >> (32 - kHashLog);
+        atomicMin(&S.htab[h], (uint32_t)i);
+      }
+    };
+    auto lookup = [&](int from, int to) -> int {
+      int nfound = 0;
+      for (int e = from + tid; e < to; e += kThreads) {
+        const int i = (int)S.list[e];
+        const uint32_t v = load4(S.data, i);
+        const uint32_t c = S.htab[(v * 2654435761u) >> (32 - kHashLog)];
+        uint32_t res = kNoCand;
+        if (c < (uint32_t)i && load4(S.data, (int)c) == v) {
+          const int maxlen = min((i & ~(kSub - 1)) + kSub, n - kLz4LastLiterals) - i;
+          const uint32_t x = load4(S.data, i + 4) ^ load4(S.data, (int)c + 4);
+          int len = 4 + (x ? ((__ffs(x) - 1) >> 3) : 4);
+          if (len > maxlen) len = maxlen;
+          // 4-byte matches save one byte and cost a sequence on both ends of the codec: dropping them keeps the
+          // ratio within ~1 % on bit planes, improves it on background-removed stacks and matches liblz4 on noisy
+          // 8-bit codes (tools/lz4_model.c), while halving the number of sequences
+          if (len >= 5) {
+            ++nfound;
+            res = c | ((uint32_t)(len - 5 < 3 ? len - 5 : 3) << 14);   // code 0,1,2: exactly 5,6,7 bytes; 3: >= 8
+            atomicOr(&S.segHM[i >> 5], 1u << (i & 31));
+          }
+        }
+        S.list[e] = (uint16_t)res;       // the entry is overwritten by its result
+      }
+      return nfound;
+    };
     // Early store: a block whose candidates (fixed-offset ones of the whole block + hash candidates of the first 4 KiB)
     // are fewer than one per 32 sampled bytes is noise — camera-noise bit planes, 8-bit quantiser codes — and would
     // shrink by < 3 % (tools/lz4_model.c: such blocks have < 70 candidates and end at 0.97..1.00 of their size, everything
-    // that compresses to <= 0.82 has > 600). It is stored without the remaining waves, the parse and the emission,
-    // which is also what makes its decode a plain copy.
-    bool early_stored = false;
-#pragma unroll 1
-    for (int wave = 0; wave < kWarps; ++wave) {
-      const int s = S.wave_start[wave];
-      const int t = min(S.wave_start[wave + 1], kListMax);
-      const bool last = wave == kWarps - 1;
-      if (s < t) {                       // (uniform over the CTA)
-        int pi[2];                       // up to 1024 entries per wave: two per thread
-        uint32_t ph[2];
-#pragma unroll
-        for (int slot = 0; slot < 2; ++slot) {
-          const int e = s + tid + slot * kThreads;
-          pi[slot] = -1;
-          bool found = false;
-          if (e < t) {
-            const int i = (int)S.list[e];
-            const uint32_t v = load4(S.data, i);
-            const uint32_t h = (v * 2654435761u) >> (32 - kHashLog);
-            pi[slot] = i;
-            ph[slot] = h;
-            uint32_t res = kNoCand;
-            const uint32_t c1 = wave > 0 ? S.htab[h] : 0u;
-            if (c1) {
-              const int c = (int)c1 - 1;
-              if (load4(S.data, c) == v) {
-                const int maxlen = min((i & ~(kSub - 1)) + kSub, n - kLz4LastLiterals) - i;
-                const uint32_t x = load4(S.data, i + 4) ^ load4(S.data, c + 4);
-                int len = 4 + (x ? ((__ffs(x) - 1) >> 3) : 4);
-                if (len > maxlen) len = maxlen;
-                // 4-byte matches save one byte and cost a sequence on both ends of the codec: dropping them keeps the
-                // ratio within ~1 % on bit planes, improves it on background-removed stacks and matches liblz4 on noisy
-                // 8-bit codes (tools/lz4_model.c), while halving the number of sequences
-                if (len >= 5) {
-                  found = true;
-                  res = (uint32_t)c | ((uint32_t)(len - 5 < 3 ? len - 5 : 3) << 14);   // code 0,1,2: exactly 5,6,7 bytes; 3: >= 8
-                  atomicOr(&S.segHM[i >> 5], 1u << (i & 31));
-                }
-              }
-            }
-            S.list[e] = (uint16_t)res;
-          }
-          if (test_early && wave < kEarlyBytes / kSub) {
-            const uint32_t fm = __ballot_sync(0xffffffffu, found);
-            if (lane == 0 && fm) atomicAdd(&S.early, __popc(fm));
-          }
-        }
-        // (the inserts follow behind the barrier below)
-        const bool early_check = test_early && wave == kEarlyBytes / kSub - 1;
-        __syncthreads();                 // this wave's results, candidate bits and the early counter are complete
-        if (early_check) {
-          early_stored = S.early < kEarlyMin;
-          if (early_stored) break;
-        }
-        if (!last) {
-#pragma unroll
-          for (int slot = 0; slot < 2; ++slot)
-            if (pi[slot] >= 0) atomicMax(&S.htab[ph[slot]], (uint32_t)pi[slot] + 1u);
-          __syncthreads();               // the table holds this sub-block before the next one looks anything up
-        }
-      } else if (test_early && wave == kEarlyBytes / kSub - 1) {
-        __syncthreads();
-        early_stored = S.early < kEarlyMin;
-        if (early_stored) break;
+    // that compresses to <= 0.82 has > 600). It is stored without the rest of the list, the parse and the emission,
+    // which is also what makes its decode a plain copy. (Positions of the first 4 KiB find the same sources in a table
+    // that holds the first 4 KiB only as in the full one: a first occurrence lies in front of them.)
+    int done = 0;
+    if (test_early) {
+      done = min(S.wave_start[kEarlyBytes / kSub], kListMax);
+      insert(0, done);
+      __syncthreads();
+      const int nf = __reduce_add_sync(0xffffffffu, lookup(0, done));
+      if (lane == 0 && nf) atomicAdd(&S.early, nf);
+      __syncthreads();
+      if (S.early < kEarlyMin) {
+        stored_out = true;
+        return 0;
       }
+      if (tid >= kEarlyBytes / 32) write_list();
+      __syncthreads();
     }
-    if (early_stored) {
-      stored_out = true;
-      return 0;
+    insert(done, total);
+    __syncthreads();
+    lookup(done, total);
+    __syncthreads();
+  }
+  // ones at the start of every segment and beyond, for run_ones (htab is free now)
+  {
+#pragma unroll
+    for (int q = 0; q < kNumOff; ++q) {
+      const uint32_t own = S.E[q][tid];
+      const int lead = own == 0xffffffffu ? 32 : __ffs(~own) - 1;
+      const uint32_t nf = ~(S.full[q][warp] >> lane);          // zeros: full segments from this one on (shifted-in bits: the warp ends)
+      const int k = min(nf ? __ffs(nf) - 1 : 32, 32 - lane);   // full segments in a row, this one included
+      const int tail = __shfl_sync(0xffffffffu, lead, (lane + k) & 31);   // leading ones of the first segment that is not full
+      S.lead[q][tid] = (uint16_t)(32 * k + (lane + k < 32 ? tail : 0));
     }
   }
   const uint32_t HM = S.segHM[tid];
@@ -360,7 +355,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
             len = 5 + code;
             if (code == 3) {           // a run: its length is in the masks
               const int q = ((D0 >> j) & 1u) | (((D1 >> j) & 1u) << 1) | (((D2 >> j) & 1u) << 2);
-              len = run_ones(S, q, i, maxlen);
+              len = run_ones(S, q, i);
             }
           } else {
             const int e = mybase + __popc(wants & ((1u << j) - 1u));
@@ -374,7 +369,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
               // both sides inside runs (the zeros around an isolated byte of a sparse plane): equal as far as both runs go
               len = 8;
               while (len < maxlen) {
-                const int k = min(run_ones(S, 0, i + len, maxlen - len), run_ones(S, 0, c + len, maxlen - len));
+                const int k = min(run_ones(S, 0, i + len), run_ones(S, 0, c + len));
                 len += k;
                 if (len >= maxlen) break;
                 const uint32_t x = load4(S.data, i + len) ^ load4(S.data, c + len);
