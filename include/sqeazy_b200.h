@@ -148,10 +148,6 @@ int sqyx_enable_stage_timing(int on);
 int sqyx_stage_ms(float* out7, int reset);
 /* value of compass-style L2 probe used by rmestbkrd on this host */
 long sqyx_host_l2_bytes(void);
-/* LZ4 decode policy: independent blocks that decode to at most `bytes` bytes are decoded one block per THREAD
- * (lane-serial decoder), larger and linked blocks one block per warp. 0 = warp decoder only, negative = query.
- * Default 0 (or the environment variable SQYB_LZ4_LANE_MAX). Returns the previous value. */
-long sqyx_set_lz4_lane_max(long bytes);
 /* block-LINKED LZ4 frames (the reference's serial mode, the sqy CLI default): streams with at least `nblocks` linked blocks
  * are decoded with deferred cross-block references (all blocks at once; default 8), smaller ones block after block.
  * 0 = never defer, < 0 = query. Returns the previous value. */

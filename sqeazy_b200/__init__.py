@@ -33,7 +33,7 @@ SQYX_SYMBOLS = [
     "sqyx_bitswap_decode_UI16", "sqyx_remove_background_UI16", "sqyx_estimate_background_UI16", "sqyx_histogram_UI16",
     "sqyx_quantiser_luts", "sqyx_lut_apply_UI16", "sqyx_lut_decode_UI16", "sqyx_lz4_bound", "sqyx_lz4_encode",
     "sqyx_lz4_decode", "sqyx_device_count", "sqyx_kernel_launches", "sqyx_last_lz4_stats", "sqyx_host_l2_bytes",
-    "sqyx_release_scratch", "sqyx_set_lz4_lane_max", "sqyx_set_device", "sqyx_enable_stage_timing", "sqyx_stage_ms", "sqyx_histogram_support",
+    "sqyx_release_scratch", "sqyx_set_device", "sqyx_enable_stage_timing", "sqyx_stage_ms", "sqyx_histogram_support",
     "sqyx_rmest_frame_portion", "sqyx_encode_device_UI8", "sqyx_decode_device_UI8", "sqyx_bitswap_encode_UI8",
     "sqyx_bitswap_decode_UI8", "sqyx_remove_background_UI8", "sqyx_decode_batch_device_UI16", "sqyx_encode_batch_device_UI16",
     "sqyx_bitshuffle_encode_UI16", "sqyx_bitshuffle_decode_UI16", "sqyx_bitshuffle_encode_UI8", "sqyx_bitshuffle_decode_UI8", "sqyx_set_lz4_defer_min",
@@ -97,12 +97,21 @@ def max_compressed_length_3d(pipeline: str, shape) -> int:
     return n.value
 
 
+def _check_out(out: np.ndarray, dtype, need_bytes: int, what: str):
+    """a caller-supplied destination goes to the C API as a bare pointer: refuse anything it could overrun"""
+    if not isinstance(out, np.ndarray) or out.dtype != np.dtype(dtype) or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]:
+        raise SqeazyError(f"{what}: `out` must be a writeable C-contiguous {np.dtype(dtype).name} array")
+    if out.nbytes < need_bytes:
+        raise SqeazyError(f"{what}: `out` holds {out.nbytes} bytes, {need_bytes} are needed")
+
+
 def encode(pipeline: str, volume: np.ndarray, nthreads: int = 1, out: np.ndarray | None = None) -> np.ndarray:
     """SQY_PipelineEncode_UI16: uint16 volume (any rank, C order) -> blob bytes (uint8 array)."""
     vol = np.ascontiguousarray(volume, dtype=np.uint16)
     cap = max_compressed_length(pipeline, vol.nbytes)
-    if out is None or out.size < cap:
+    if out is None:
         out = np.empty(cap, dtype=np.uint8)
+    _check_out(out, np.uint8, cap, "encode")
     shp = (c_long * vol.ndim)(*vol.shape)
     n = c_long(0)
     rc = lib().SQY_PipelineEncode_UI16(pipeline.encode("latin-1"), _vp(vol), shp, c_uint(vol.ndim), _vp(out), ctypes.byref(n),
@@ -193,6 +202,7 @@ def decode(blob: np.ndarray, nthreads: int = 1, out: np.ndarray | None = None) -
     nbytes = decompressed_length(blob)
     if out is None:
         out = np.empty(nbytes // 2, dtype=np.uint16)
+    _check_out(out, np.uint16, nbytes, "decode")
     rc = lib().SQY_Decode_UI16(_vp(blob), c_long(blob.size), _vp(out), c_int(nthreads))
     if rc != 0:
         raise SqeazyError(f"SQY_Decode_UI16 returned {rc}")
@@ -550,13 +560,6 @@ def last_lz4_stats():
     o = (c_long * 4)()
     lib().sqyx_last_lz4_stats(o)
     return {"general_blocks": o[0], "constant_blocks": o[1], "stored_blocks": o[2], "payload_bytes": o[3]}
-
-
-def set_lz4_lane_max(nbytes: int) -> int:
-    """decoded-size limit of the lane-serial LZ4 block decoder (0 = warp-per-block only); returns the previous value"""
-    f = lib().sqyx_set_lz4_lane_max
-    f.restype = c_long
-    return int(f(c_long(int(nbytes))))
 
 
 def set_lz4_defer_min(nblocks: int) -> int:

@@ -5,6 +5,7 @@
 // every compute entry point fails with 1.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost nothing unless a profiler injects its library
 
 #include <algorithm>
 #include <atomic>
@@ -109,12 +110,22 @@ enum StageTimer { kTFilterSwap = 0, kTLz4Enc, kTHist, kTLutApply, kTLz4Dec, kTLu
 std::atomic<int> g_timing{0};
 float g_stage_ms[kNumTimers] = {0};
 
+// every stage of a call is also an NVTX range (the reference's tracing is wall-clock timers around the stage
+// calls, verbs/bench.hpp:181-194): `nsys` / `ncu --nvtx` show filter+transpose, LZ4, histogram, LUT per call
+const char* const kStageNames[kNumTimers] = {"sqy:filter+bitswap encode", "sqy:lz4 encode", "sqy:histogram", "sqy:lut apply",
+                                             "sqy:lz4 decode", "sqy:lut decode", "sqy:bitswap decode"};
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct ScopedStageTimer {
   cudaEvent_t a = nullptr, b = nullptr;
   cudaStream_t st;
   int slot;
   bool on;
-  ScopedStageTimer(int slot_, cudaStream_t st_) : st(st_), slot(slot_), on(g_timing.load() != 0) {
+  NvtxRange range;
+  ScopedStageTimer(int slot_, cudaStream_t st_) : st(st_), slot(slot_), on(g_timing.load() != 0), range(kStageNames[slot_]) {
     if (on) {
       cudaEventCreate(&a);
       cudaEventCreate(&b);
@@ -840,7 +851,6 @@ int sqyx_last_lz4_stats(long* out4) {
   return 0;
 }
 
-long sqyx_set_lz4_lane_max(long bytes) { return k_lz4_set_lane_max(bytes); }
 long sqyx_set_lz4_defer_min(long nblocks) { return k_lz4_set_defer_min(nblocks); }
 
 int sqyx_release_scratch(void) {
@@ -1397,6 +1407,7 @@ int host_encode_streamed(Arena& A, const Pipeline& pl, const char* src, const st
 
 static int host_encode(int elem, const char* pipeline, const char* src, long* shape, unsigned shape_size, char* dst, long* dstlength,
                        int nthreads) {
+  NvtxRange range(elem == 1 ? "SQY_PipelineEncode_UI8" : "SQY_PipelineEncode_UI16");
   try {
     if (!pipeline || !src || !shape || !dst || !dstlength) return 1;
     Pipeline pl;
@@ -1449,6 +1460,7 @@ static int host_encode(int elem, const char* pipeline, const char* src, long* sh
 }
 
 static int host_decode(int elem, const char* src, long srclength, char* dst, int nthreads) {
+  NvtxRange range(elem == 1 ? "SQY_Decode_UI8" : "SQY_Decode_UI16");
   try {
     if (!src || !dst || srclength <= 0) return 1;
     const Header hdr = unpack_header(src, (size_t)srclength);

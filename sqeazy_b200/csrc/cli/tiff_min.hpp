@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -48,7 +49,16 @@ inline std::string tiff_read(const std::string& path, TiffStack& out) {
   out.shape.clear();
   out.data.clear();
   uint64_t pages = 0, W = 0, H = 0;
+  // a classic TIFF is at most 4 GiB: its size bounds the page data, and every IFD lies strictly inside it; an IFD chain
+  // that returns to an offset already walked (a cycle) is refused instead of being followed for ever
+  if (fseek(r.f, 0, SEEK_END) != 0) return "unable to size " + path;
+  const uint64_t file_bytes = (uint64_t)ftell(r.f);
+  std::vector<uint64_t> seen;
   while (ifd != 0) {
+    if (ifd + 6 > file_bytes) return "IFD offset outside the file";
+    if (std::find(seen.begin(), seen.end(), ifd) != seen.end()) return "IFD chain loops";
+    seen.push_back(ifd);
+    if (seen.size() > (1u << 20)) return "too many TIFF pages";
     unsigned char nb[2];
     if (!r.at(ifd, nb, 2)) return "truncated IFD";
     const unsigned n = r.u16(nb);
@@ -90,7 +100,9 @@ inline std::string tiff_read(const std::string& path, TiffStack& out) {
       return true;
     };
     if (!table(so_count, so_type, so_off, offs) || !table(sb_count, sb_type, sb_off, lens)) return "truncated strip table";
+    if (W > file_bytes || H > file_bytes || W * H > file_bytes) return "TIFF page larger than the file";
     const uint64_t page_bytes = W * H * (bits / 8);
+    if (page_bytes > file_bytes) return "TIFF page larger than the file";
     const size_t base = out.data.size();
     out.data.resize(base + page_bytes);
     uint64_t got = 0;

@@ -82,7 +82,6 @@ size_t k_lz4_decode_linked_workspace_bytes(uint64_t dst_bytes);
 int k_lz4_decode_linked(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint64_t dst_bytes, void* workspace, void* origins,
                         cudaStream_t st);
 // decoded-size limit of the lane-serial block decoder (0 = warp-per-block decoder only); returns the previous value
-long k_lz4_set_lane_max(long bytes);
 // linked blocks from which a stream takes the deferred-reference path (default 8, 0 = never); returns the previous value
 long k_lz4_set_defer_min(long nblocks);
 int k_lz4_decode_status(void* workspace, uint32_t* error, uint64_t* total_decoded, uint32_t* deferred_blocks, cudaStream_t st);

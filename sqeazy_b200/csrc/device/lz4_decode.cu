@@ -12,16 +12,14 @@
 //   sizes     : only for foreign blocks whose decoded size is not implied (last block of a frame):
 //               a warp per block walks the tokens without copying.
 //   offsets   : one CTA prefix-sums decoded sizes into output offsets and validates the total (skipped on the fast path).
-//   classify  : a warp per block: stored blocks are copied, closed-form run blocks filled (16-byte stores); the rest
-//               is queued for the block decoders.
-//   decode    : persistent grid, a warp per block of any size. Sequence headers are parsed 32 at a time (every lane
+//   decode    : persistent grid, a warp per block of any size; stored blocks are copied and closed-form run blocks
+//               filled with 16-byte stores in passing. Sequence headers are parsed 32 at a time (every lane
 //               parses the bytes at ip+lane as if a token started there, the real chain is followed with one shuffle
 //               per sequence), literals are copied by the lanes that own them, matches are replayed in order. The
 //               last 2 KiB of output live in a shared-memory ring (match sources), the compressed stream in a 1 KiB
 //               ring; complete 512-byte chunks are flushed with 16-byte stores. Far matches and bytes in front of a
 //               linked block are read back from global memory; linked blocks wait on their predecessor's flag only
 //               when a match reaches in front of the block.
-//   (lanes)   : optional one-block-per-THREAD decoder (lz4_lane.inl), off by default — see lane_max_bytes().
 #include "common.cuh"
 #include "kernels.h"
 #include "lz4_format.h"
@@ -51,9 +49,7 @@ struct DecCtl {          // lives at the start of the workspace
   uint32_t ticket_size;
   uint32_t ticket_decode;
   uint32_t need_sizes;   // number of blocks whose decoded size must be measured
-  uint32_t nwork;        // blocks queued for the lane-serial decoder
-  uint32_t ticket_lane;
-  uint32_t nwarp;        // blocks left to the warp-per-block decoder
+  uint32_t reserved[3];
   // fast path: the stream is exactly one frame of this library -> the block table is built by many CTAs
   uint32_t fast, fast_nblk, fast_bb, fast_pad;
   unsigned long long fast_idx, fast_first, fast_raw;
@@ -73,11 +69,7 @@ struct DecTables {
   uint32_t* dsize;               // decoded size (0 = unknown until the size pass)
   uint32_t* link;                // previous block of the same linked frame or kNoLink
   uint32_t* done;                // completion flags for linked frames
-  uint32_t* kind;                // who decodes the block (BlockKind), written by lz4_classify_kernel
-  uint32_t* work;                // queue of the lane-serial decoder
 };
-
-enum BlockKind : uint32_t { kKindWarp = 0, kKindDone = 1, kKindLane = 2 };
 
 __device__ __forceinline__ uint32_t rd32(const uint8_t* p) {
   return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
@@ -898,126 +890,12 @@ __global__ void __launch_bounds__(kDirThreads) lz4_offsets_kernel(DecCtl* ctl, D
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// classification: a warp per block. Stored blocks are copied and closed-form run blocks (what the encoder emits for
-// an all-equal block: token 0x1F, byte, offset 1, length bytes, token 0x50, five bytes) are filled here with
-// coalesced 16-byte stores; other independent blocks are queued for the lane-serial decoder; linked blocks and
-// blocks above `lane_max` decoded bytes stay with the warp-per-block decoder.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lz4_classify_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, DecCtl* ctl,
-                                                           DecTables T, uint32_t lane_max) {
-  if (ctl->error) return;
-  const int lane = threadIdx.x & 31;
-  const uint32_t nblocks = ctl->nblocks;
-  const uint32_t wpb = blockDim.x >> 5;
-  for (uint32_t b = blockIdx.x * wpb + (threadIdx.x >> 5); b < nblocks; b += gridDim.x * wpb) {
-    const uint32_t word = T.word[b];
-    const uint32_t csize = word & 0x7FFFFFFFu;
-    const uint32_t dsize = T.dsize[b];
-    const uint32_t link = T.link[b];
-    const uint8_t* s = src + T.src_off[b];
-    uint8_t* d = dst + T.dst_off[b];
-    uint32_t kind = kKindWarp, err = 0;
-    if (link == kNoLink) {
-      if (word & kLz4StoredFlag) {
-        if (csize != dsize) err = kErrSizeMismatch;
-        else warp_copy_from_stream(d, s, csize, lane);
-        kind = kKindDone;
-      } else if (csize >= 12 && csize <= 96 && dsize >= 64 && (((uintptr_t)d) & 15) == 0 && __ldg(s) == 0x1Fu &&
-                 __ldg(s + 2) == 1u && __ldg(s + 3) == 0u) {
-        const uint32_t v = __ldg(s + 1);
-        uint32_t ip = 4, mlen = 15 + 4, x;
-        do { x = ip < csize ? __ldg(s + ip) : 0u; ip++; mlen += x; } while (x == 255u && ip < csize);
-        bool ok = ip + 6 == csize && 1u + mlen + 5u == dsize && __ldg(s + ip) == 0x50u;
-        for (uint32_t k = 0; ok && k < 5; ++k) ok = __ldg(s + ip + 1 + k) == v;
-        if (ok) {
-          const uint32_t v4 = v * 0x01010101u;
-          const uint4 fill = make_uint4(v4, v4, v4, v4);
-          const uint32_t nv = dsize >> 4;
-          for (uint32_t q = lane; q < nv; q += 32) st_stream(reinterpret_cast<uint4*>(d) + q, fill);
-          for (uint32_t k = (nv << 4) + lane; k < dsize; k += 32) d[k] = (uint8_t)v;
-          kind = kKindDone;
-        }
-      }
-      if (kind == kKindWarp && dsize <= lane_max && csize > 0 && (((uintptr_t)d) & 15) == 0) kind = kKindLane;
-    }
-    __syncwarp();
-    if (lane == 0) {
-      T.kind[b] = kind;
-      if (err) atomicMax(&ctl->error, err);
-      if (kind == kKindDone) { __threadfence(); atomicExch(T.done + b, 1u); }
-      else if (kind == kKindLane) T.work[atomicAdd(&ctl->nwork, 1u)] = b;
-      else atomicAdd(&ctl->nwarp, 1u);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// lane-serial decoder (lz4_lane.inl): every thread takes blocks from the queue until it is empty
-// ------------------------------------------------------------------------------------------------
-constexpr uint32_t kLaneThreads = 128;
-constexpr uint32_t kLaneCtasPerSM = 12;
-constexpr uint32_t kLaneStride = kLaneThreads;
-#define SQYB_LANE_FN __device__ __forceinline__
-__device__ __forceinline__ uint32_t lane_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
-__device__ __forceinline__ uint32_t lane_funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_l(lo, hi, sh); }
-__device__ __forceinline__ int lane_ffs(uint32_t x) { return __ffs((int)x); }
-// 16-byte aligned chunk of the compressed stream. A chunk that only partly overlaps [sbeg, send) is still loaded whole:
-// an aligned 16-byte access never crosses a page, so it cannot fault, and the bytes outside the stream are never
-// interpreted (every position is checked against the block's end). Chunks entirely outside read as zero.
-__device__ __forceinline__ uint4 lane_load_chunk(const uint8_t* a, const uint8_t* sbeg, const uint8_t* send) {
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (a + 16 > sbeg && a < send) v = __ldg(reinterpret_cast<const uint4*>(a));
-  return v;
-}
-__device__ __forceinline__ uint32_t lane_load_out32(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint32_t*>(p)); }
-__device__ __forceinline__ void lane_store_out16(uint8_t* p, const uint4& v) { st_stream(reinterpret_cast<uint4*>(p), v); }
-#include "lz4_lane.inl"
-
-__global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSM) lz4_decode_lanes_kernel(const uint8_t* __restrict__ src,
-                                                                                         uint64_t src_bytes,
-                                                                                         uint8_t* __restrict__ dst, DecCtl* ctl,
-                                                                                         DecTables T) {
-  extern __shared__ __align__(16) uint32_t lane_smem[];   // 32 words per thread, word j of thread t at [j * kLaneThreads + t]
-  if (ctl->error) return;
-  const uint32_t nwork = ctl->nwork;
-  uint32_t* base = lane_smem + threadIdx.x;
-  const uint8_t* send = src + src_bytes;
-  Lane L;
-  L.mode = kLaneIdle;
-  L.A = src; L.d = dst; L.ip = L.end = L.op = L.dcap = L.rem = L.off = L.cur = L.acc = 0; L.pre = make_uint4(0, 0, 0, 0);
-  uint32_t b = 0;
-  bool alive = true;
-  // every lane stays in the loop until the whole warp has run out of work: the vote at the top is the point where the
-  // lanes reconverge after the divergent steps of the previous iteration
-  while (true) {
-    if (alive && (L.mode & 15u) == kLaneIdle) {
-      const uint32_t idx = atomicAdd(&ctl->ticket_lane, 1u);
-      alive = idx < nwork;
-      if (alive) {
-        b = T.work[idx];
-        lane_begin(L, base, src + T.src_off[b], T.word[b] & 0x7FFFFFFFu, dst + T.dst_off[b], T.dsize[b], src, send);
-      }
-    }
-    if (!__any_sync(0xffffffffu, alive)) break;
-    if (alive) {
-      const uint32_t rc = lane_step(L, base, src, send);
-      if ((L.mode & 15u) == kLaneIdle) {
-        if (rc) atomicMax(&ctl->error, rc);
-        __threadfence();
-        atomicExch(T.done + b, 1u);
-      }
-    }
-  }
-}
-
-// `classified`: lz4_classify_kernel ran first (only when the lane-serial decoder is switched on) and this kernel takes
-// the blocks it left. Otherwise every block is taken here and the stored / closed-form blocks are handled inline: their
-// 16-byte-store fills are memory-bound and hide under the issue-bound decoding of the other warps, whereas a separate
-// classification pass in front of this kernel cost 0.63 ms per 4 GiB.
+// Every block is taken here; the stored / closed-form blocks are handled inline: their 16-byte-store fills are
+// memory-bound and hide under the issue-bound decoding of the other warps, whereas a separate classification pass in
+// front of this kernel cost 0.63 ms per 4 GiB.
 __global__ void __launch_bounds__(kWinWarps * 32, 5) lz4_decode_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
                                                                         uint8_t* __restrict__ dst, DecCtl* ctl, DecTables T,
-                                                                        int classified, uint32_t first, uint32_t count,
+                                                                        uint32_t first, uint32_t count,
                                                                         uint32_t nsets, uint32_t set_stride, uint32_t slot) {
   extern __shared__ __align__(16) unsigned char dsm[];
   if (ctl->error) return;
@@ -1025,7 +903,6 @@ __global__ void __launch_bounds__(kWinWarps * 32, 5) lz4_decode_kernel(const uin
   uint8_t* win = dsm + (size_t)warp * kWinWarpSmem;
   uint8_t* ring8 = win + kWin;
   const uint32_t nblocks = ctl->nblocks;
-  if (classified && ctl->nwarp == 0) return;
   // count != 0: only `nsets` sets of `count` consecutive blocks, set j starting at first + j * set_stride (the blocks of all
   // bit planes that make up one z-slab), with a work counter of their own
   const uint32_t total = count ? count * nsets : nblocks;
@@ -1040,7 +917,6 @@ __global__ void __launch_bounds__(kWinWarps * 32, 5) lz4_decode_kernel(const uin
       b = first + j * set_stride + (b - j * count);
       if (b >= nblocks) continue;
     }
-    if (classified && T.kind[b] != kKindWarp) continue;
     const uint32_t word = T.word[b];
     const uint32_t csize = word & 0x7FFFFFFFu;
     const uint32_t dsize = T.dsize[b];
@@ -1399,27 +1275,6 @@ __global__ void __launch_bounds__(256) lz4_resolve_rest_kernel(uint8_t* __restri
 
 }  // namespace
 
-// Independent blocks that decode to at most this many bytes go to the lane-serial decoder. Default 0 = off: measured on
-// B200 (profiles/README.md) it needs ~2.5x fewer instructions than the warp decoder but runs at 8-12 of 32 lanes and
-// has too few independent streams to hide its latencies (one lane per 16 KiB block), so it is slower at every size
-// tried. SQYB_LZ4_LANE_MAX / sqyx_set_lz4_lane_max() switch it on for measurements and tests.
-static std::atomic<long> g_lane_max{-1};
-static uint32_t lane_max_bytes() {
-  long v = g_lane_max.load(std::memory_order_relaxed);
-  if (v < 0) {
-    const char* e = std::getenv("SQYB_LZ4_LANE_MAX");
-    v = e ? std::strtol(e, nullptr, 10) : 0;
-    if (v < 0) v = 0;
-    g_lane_max.store(v, std::memory_order_relaxed);
-  }
-  return (uint32_t)(v > 0x7FFFFFFF ? 0x7FFFFFFF : v);
-}
-long k_lz4_set_lane_max(long bytes) {
-  const long prev = (long)lane_max_bytes();
-  if (bytes >= 0) g_lane_max.store(bytes, std::memory_order_relaxed);
-  return prev;
-}
-
 // number of block-linked blocks from which a stream takes the deferred-reference path (0 = never: every linked block waits
 // for its predecessor, the behaviour before that path existed). sqyx_set_lz4_defer_min() lets tests and benches run both.
 static std::atomic<long> g_defer_min{(long)kDeferMin};
@@ -1433,7 +1288,7 @@ size_t k_lz4_decode_capacity(uint64_t dst_bytes) { return (size_t)(dst_bytes / k
 
 size_t k_lz4_decode_workspace_bytes(uint64_t dst_bytes) {
   const size_t cap = k_lz4_decode_capacity(dst_bytes);
-  return 256 + cap * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4) + 8 * (cap / kTile + 2) + 256;
+  return 256 + cap * (8 + 8 + 4 + 4 + 4 + 4) + 8 * (cap / kTile + 2) + 256;
 }
 
 // Enqueues the whole decode; the status lands in workspace (see k_lz4_decode_status).
@@ -1448,8 +1303,6 @@ static DecTables dec_tables(void* workspace, uint64_t dst_bytes, unsigned long l
   T.dsize = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
   T.link = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
   T.done = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
-  T.kind = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
-  T.work = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
   if (tile_sums_out) *tile_sums_out = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(p) + 7) & ~(uintptr_t)7);
   return T;
 }
@@ -1511,8 +1364,6 @@ int k_lz4_decode_tables(const uint8_t* src, uint64_t src_bytes, uint64_t dst_byt
   T.dsize = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
   T.link = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
   T.done = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
-  T.kind = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
-  T.work = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
   unsigned long long* tile_sums = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(p) + 7) & ~(uintptr_t)7);
   const uint32_t tiles = (uint32_t)(cap / kTile + 1), tile_grid = tiles < 1024u ? tiles : 1024u;
   SQYB_CUDA_OK(cudaMemsetAsync(ctl, 0, sizeof(DecCtl), st));
@@ -1533,16 +1384,8 @@ int k_lz4_decode_run(const uint8_t* src, uint64_t src_bytes, uint8_t* dst, uint6
                      uint32_t count, uint32_t nsets, uint32_t set_stride, uint32_t slot, cudaStream_t st) {
   DecCtl* ctl = reinterpret_cast<DecCtl*>(workspace);
   const DecTables T = dec_tables(workspace, dst_bytes, nullptr);
-  const bool lanes = count == 0 && lane_max_bytes() > 0;
-  if (lanes) {
-    lz4_classify_kernel<<<kNumSMs * 8, 256, 0, st>>>(src, dst, ctl, T, lane_max_bytes());
-    const size_t lane_smem = 32 * sizeof(uint32_t) * kLaneThreads;
-    SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_decode_lanes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    lz4_decode_lanes_kernel<<<kNumSMs * kLaneCtasPerSM, kLaneThreads, lane_smem, st>>>(src, src_bytes, dst, ctl, T);
-    SQYB_COUNT_LAUNCH(2);
-  }
   const size_t win_smem = kWinWarps * kWinWarpSmem;
-  lz4_decode_kernel<<<kNumSMs * 5, kWinWarps * 32, win_smem, st>>>(src, src_bytes, dst, ctl, T, lanes ? 1 : 0, first, count, nsets,
+  lz4_decode_kernel<<<kNumSMs * 5, kWinWarps * 32, win_smem, st>>>(src, src_bytes, dst, ctl, T, first, count, nsets,
                                                                     set_stride, slot);
   SQYB_COUNT_LAUNCH(1);
   return (int)cudaGetLastError();

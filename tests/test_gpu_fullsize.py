@@ -17,7 +17,12 @@ def roomy(sq, cuda):
     cuda.cuda.empty_cache()
 
 
-def test_cfg2_full_size(sq, cuda, roomy):
+def _oracle_slabs(Z, frames=16):
+    """z-ranges the oracle restates at full size: the first frames, a slab in the middle of the shell, the last frames"""
+    return [(0, frames), (Z // 2 - frames // 2, Z // 2 + frames // 2), (Z - frames, Z)]
+
+
+def test_cfg2_full_size(sq, cuda, port, roomy):
     """rmestbkrd->bitswap1->lz4 on 2048x2048x512 uint16 = 2^31 voxels, 4 GiB"""
     from sqeazy_b200.synth import torch_volume
 
@@ -39,6 +44,17 @@ def test_cfg2_full_size(sq, cuda, roomy):
     assert cuda.equal(out, expect)
     ratio = vol.numel() * 2 / blob.numel()
     assert 10 < ratio < 40
+    # the reference cannot index 2^31 voxels (dynamic_pipeline.hpp:514), so the ORACLE pins the full-size result
+    # slab by slab: the threshold of the whole stack from the faces / rows it samples (background_scheme_utils.hpp:35-105),
+    # then remove_background (remove_background_scheme_impl.hpp:73-95) on three 16-frame slabs of the decoded stack
+    h_vol = vol.cpu().numpy().view(np.uint16)
+    supports = port.darkest_face_supports(h_vol, sq.host_l2_bytes())
+    assert int(np.uint16(supports.min())) == thr
+    for z0, z1 in _oracle_slabs(shape[0]):
+        want = port.remove_background(h_vol[z0:z1], thr)
+        got = out[z0:z1].cpu().numpy().view(np.uint16)
+        assert np.array_equal(got, want), (z0, z1)
+    del h_vol
     # idempotence of the lossy filter + a lossless pipeline on the result returns it unchanged
     blob2 = sq.encode_device("bitswap1->lz4", out)
     back = cuda.empty_like(vol)
@@ -47,7 +63,7 @@ def test_cfg2_full_size(sq, cuda, roomy):
     del blob, blob2, back, out, expect, vol
 
 
-def test_cfg3_full_size(sq, cuda, roomy):
+def test_cfg3_full_size(sq, cuda, port, roomy):
     """quantiser->lz4 on 2048x2048x1024 uint16 = 2^32 voxels, 8 GiB raw, 4 GiB of 8-bit codes"""
     from sqeazy_b200.synth import torch_volume
 
@@ -75,6 +91,15 @@ def test_cfg3_full_size(sq, cuda, roomy):
     sq.decode_device(blob, out)
     assert cuda.equal(out, expect)
     assert 1.9 < vol.numel() * 2 / blob.numel() < 4
+    # the oracle at full size: LUTs of the WHOLE stack's histogram (quantiser_utils.hpp:227-306), then LUT apply and decode
+    # (quantiser_scheme_impl.hpp:206-223, 245-282) on three 16-frame slabs
+    o_enc, o_dec = port.quantiser_luts(h)
+    assert np.array_equal(o_enc, enc) and np.array_equal(o_dec, dec)
+    for z0, z1 in _oracle_slabs(shape[0]):
+        slab = vol[z0:z1].cpu().numpy().view(np.uint16)
+        want = port.lut_decode(port.lut_apply(slab, o_enc), o_dec)
+        got = out[z0:z1].cpu().numpy().view(np.uint16)
+        assert np.array_equal(got.reshape(-1), want.reshape(-1)), (z0, z1)
     del blob, out, expect, vol
 
 
@@ -170,3 +195,23 @@ def test_lossless_pipeline_on_eight_gib(sq, cuda, roomy):
     assert cuda.equal(out, vol)
     assert 2.0 < vol.numel() * 2 / blob.numel() < 4.0
     del blob, out, vol
+
+
+def test_cfg2_slab_ratio_against_the_reference_on_the_same_voxels(sq, cuda, ref):
+    """on background-removed, very compressible stacks the blob may be at most 10 % larger than the reference's
+    (ratio >= 0.90 x): 16 KiB independent blocks against liblz4's 64 KiB window inside 256 KiB blocks. Same 2^26 voxels through
+    both encoders (the reference's own stage chain, dynamic_pipeline.hpp:560-690 re-driven by oracle/ref_harness.cpp), and the
+    reference's decode chain (lz4.hpp:257-339 + bitplane_reorder_scalar.hpp:81-116) must read the GPU's blob."""
+    from sqeazy_b200.synth import numpy_volume
+
+    vol = numpy_volume((16, 2048, 2048), "scmos", index=0)
+    theirs, _ = ref.pipeline_encode_stages(1, vol, 8)
+    blob = sq.encode("rmestbkrd->bitswap1->lz4", vol)
+    hs = sq.header_size(blob)
+    ours = blob.size - hs
+    assert ours <= theirs.size / 0.90, (ours, theirs.size, vol.nbytes / ours, vol.nbytes / theirs.size)
+    rc, back_theirs, _ = ref.pipeline_decode_stages(1, theirs, vol.size)
+    rc2, back_ours, _ = ref.pipeline_decode_stages(1, blob[hs:], vol.size)
+    assert rc == 0 and rc2 == 0
+    assert np.array_equal(back_ours, back_theirs)
+    assert np.array_equal(sq.decode(blob).reshape(-1), back_theirs.reshape(-1))

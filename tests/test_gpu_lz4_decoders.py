@@ -1,6 +1,5 @@
-"""Both LZ4 block decoders of the library — one block per THREAD (lane-serial, lz4_lane.inl) and one block per warp
-(sliding window) — must produce identical bytes on this library's frames, on liblz4's frames (reference encoder,
-encoders/lz4_utils.hpp:99-274) and on the oracle's frames; corrupt streams must fail cleanly on both."""
+"""The LZ4 block decoder of the library (one block per warp, sliding window) on this library's frames, on liblz4's frames
+(reference encoder, encoders/lz4_utils.hpp:99-274) and on the oracle's frames; corrupt streams must fail cleanly."""
 import numpy as np
 import pytest
 
@@ -9,19 +8,8 @@ from test_gpu_parity import dev, host16, lz4_inputs
 
 pytestmark = pytest.mark.gpu
 
-WARP_ONLY = 0
-LANES_FOR_ALL = 1 << 30
-
-
-@pytest.fixture(params=[WARP_ONLY, LANES_FOR_ALL], ids=["warp", "lanes"])
-def decoder(request, sq, cuda):
-    prev = sq.set_lz4_lane_max(request.param)
-    yield request.param
-    sq.set_lz4_lane_max(prev)
-
-
 @pytest.mark.parametrize("name", [k for k in lz4_inputs().keys() if k != "empty"])
-def test_own_frames(sq, cuda, port, decoder, name):
+def test_own_frames(sq, cuda, port, name):
     a = lz4_inputs()[name]
     if a is None:
         a = port.bitswap_encode(1, numpy_volume((8, 256, 256), "scmos", index=5)).view(np.uint8)
@@ -34,8 +22,8 @@ def test_own_frames(sq, cuda, port, decoder, name):
 
 
 @pytest.mark.parametrize("period", [1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 31, 32, 33, 39, 40, 41, 48, 63, 64, 65, 1000, 70000])
-def test_foreign_frames_with_any_offset(sq, cuda, port, decoder, period):
-    """256 KiB blocks from the oracle's encoder: ring-served, doubling, fill and far copies of the lane decoder"""
+def test_foreign_frames_with_any_offset(sq, cuda, port, period):
+    """256 KiB blocks from the oracle's encoder: single-step, periodic and far copies"""
     rng = np.random.default_rng(period)
     a = np.tile(rng.integers(0, 256, size=period, dtype=np.uint8), (300000 // period) + 2)[:300001]
     a[100000:100040] = rng.integers(0, 256, size=40, dtype=np.uint8)   # break the period once
@@ -45,7 +33,7 @@ def test_foreign_frames_with_any_offset(sq, cuda, port, decoder, period):
     assert np.array_equal(out.cpu().numpy(), a)
 
 
-def test_reference_frames(sq, cuda, ref, decoder):
+def test_reference_frames(sq, cuda, ref):
     """liblz4 frames made by the reference's lz4_scheme: serial (linked: always the warp decoder), parallel, 64 KiB blocks"""
     vol = numpy_volume((10, 256, 512), "ref", index=9)
     planes = ref.bitswap_encode(1, vol)
@@ -56,22 +44,7 @@ def test_reference_frames(sq, cuda, ref, decoder):
         assert np.array_equal(host16(out), planes), (nthreads, config)
 
 
-def test_decoders_agree_on_bit_planes(sq, cuda, port):
-    planes = port.bitswap_encode(1, numpy_volume((16, 512, 512), "scmos", index=3)).view(np.uint8)
-    payload = sq.lz4_encode_device(dev(cuda, planes))
-    outs = []
-    for mode in (WARP_ONLY, LANES_FOR_ALL, 65536):
-        prev = sq.set_lz4_lane_max(mode)
-        try:
-            out = cuda.zeros(planes.size, dtype=cuda.uint8, device="cuda")
-            assert sq.lz4_decode_device(payload, out) == planes.size
-            outs.append(out.cpu().numpy())
-        finally:
-            sq.set_lz4_lane_max(prev)
-    assert np.array_equal(outs[0], planes) and np.array_equal(outs[1], planes) and np.array_equal(outs[2], planes)
-
-
-def test_corrupt_blocks_fail_cleanly(sq, cuda, port, decoder):
+def test_corrupt_blocks_fail_cleanly(sq, cuda, port):
     """bit flips inside the compressed blocks: the decode either fails or returns the promised size (LZ4 has no checksum
     here), never crashes or writes out of bounds, and the library keeps working afterwards"""
     rng = np.random.default_rng(99)
