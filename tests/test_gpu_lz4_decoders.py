@@ -124,8 +124,8 @@ def _mixed_content(rng, n):
 
 
 @pytest.mark.parametrize("seed", range(10))
-def test_random_mixed_streams_from_liblz4_and_own_encoder(sq, cuda, ref, decoder, seed):
-    """the batch walk, the single-sequence path, near / far / overlapping copies and the length chains of both decoders
+def test_random_mixed_streams_from_liblz4_and_own_encoder(sq, cuda, ref, seed):
+    """the batch walk, the single-sequence path, near / far / overlapping copies and the length chains
     on streams with every kind of sequence: liblz4 frames (64 KiB and 256 KiB blocks, linked and independent) and our own"""
     rng = np.random.default_rng(1000 + seed)
     a = _mixed_content(rng, int(rng.integers(200_000, 900_000)))
