@@ -1,7 +1,7 @@
 """Joins an `ncu --page source --csv` SASS listing (per-instruction counters) with `nvdisasm --print-line-info` of the same
 cubin, and sums the counters per CUDA source line / per source range. Development tool.
 usage: sass_line_profile.py ncu_source.csv dis.txt kernel_substring [callee_substring ...]"""
-import csv, re, sys, collections
+import csv, re, sys, collections, os
 
 def load_ncu(path):
     rows = list(csv.reader(open(path)))
@@ -57,7 +57,7 @@ for i in range(n):
 tot = sum(v[0] for v in per_line.values())
 tots = sum(v[2] for v in per_line.values())
 print("opcode mismatches", mismatch, "total warp instructions %.3e" % tot, "samples", tots)
-src = open("/root/repo/sqeazy_b200/csrc/device/lz4_encode.cu").read().split("\n") if len(sys.argv) > 3 else []
+src = open("/root/repo/sqeazy_b200/csrc/device/" + (os.environ.get("SRC") or "lz4_encode.cu")).read().split("\n") if len(sys.argv) > 3 else []
 for ln in sorted(per_line):
     v = per_line[ln]
     if v[0] / tot > 0.004 or v[2] / max(tots, 1) > 0.004:
