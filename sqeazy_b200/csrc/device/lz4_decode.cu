@@ -384,12 +384,20 @@ __device__ __forceinline__ uint4 load_stream_piece(const uint8_t* addr, const ui
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// byte load that may be served by L1 (ld.global.ca); only for lines that no longer change, see the far-source copy
+__device__ __forceinline__ uint8_t ld_l1_u8(const uint8_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.ca.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return (uint8_t)v;
+}
+
 struct WinOut {
   uint8_t* win;        // shared ring
   uint8_t* d;          // block's output in global memory
   uint32_t flushed;    // bytes of this block already written to global (multiple of 512 until the end)
   uint32_t dcap;       // decoded size the block table promises: nothing is ever written to global beyond it
   bool aligned;        // d is 16-byte aligned
+  bool line_aligned;   // d is 128-byte aligned: the flushed part of the block ends on a cache line boundary
   bool overflow;
   int lane;
   // writes every complete 512-byte chunk below `op` to global memory
@@ -647,8 +655,15 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
           // far source inside this block: it ends at least 1199 bytes in front of the match (offset > kNear, mlen <= 273)
           // while everything up to 1023 bytes in front of it was flushed after the previous batch, so it is read back
           // from global memory (L2) without any window bookkeeping
+          // The flushed part ends on a 512-byte boundary of the block: with a 128-byte aligned block a cache line is either
+          // final or untouched when it is first read, so the reads may stay in L1 — an encoder that points at the first
+          // occurrence of a pattern (lz4_encode.cu) reads the same early lines of the block over and over.
           const uint8_t* from = O.d + (mo - offset);
-          for (uint32_t k = lane; k < mlen; k += 32u) SQYB_W(mo + k) = __ldcg(from + k);
+          if (O.line_aligned) {
+            for (uint32_t k = lane; k < mlen; k += 32u) SQYB_W(mo + k) = ld_l1_u8(from + k);
+          } else {
+            for (uint32_t k = lane; k < mlen; k += 32u) SQYB_W(mo + k) = __ldcg(from + k);
+          }
         } else if (!do_match(mo, offset, mlen)) {   // reaches in front of a linked block
           return op;
         }
@@ -960,6 +975,7 @@ __global__ void __launch_bounds__(kWinWarps * 32, 5) lz4_decode_kernel(const uin
       O.flushed = 0;
       O.dcap = dsize;
       O.aligned = (((uintptr_t)d) & 15) == 0;
+      O.line_aligned = (((uintptr_t)d) & 127) == 0;
       O.overflow = false;
       O.lane = lane;
       const unsigned long long before = link != kNoLink ? doff : 0ull;
