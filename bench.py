@@ -580,24 +580,27 @@ def run_sharded(ctx, wname, steps):
                 b = sq.encode(pipeline, vol, nthreads=16, out=blob_buf)     # warm-up: arenas, NCCL communicators
                 sq.decode(b, nthreads=16, out=out)
                 te = td = 0.0
+                info = None
                 for _ in range(steps):
                     t0 = time.perf_counter()
                     b = sq.encode(pipeline, vol, nthreads=16, out=blob_buf)
                     t1 = time.perf_counter()
+                    info = sq.last_shard_info()          # of the encode: the decode has no collective
+                    t1b = time.perf_counter()
                     sq.decode(b, nthreads=16, out=out)
                     t2 = time.perf_counter()
                     te += t1 - t0
-                    td += t2 - t1
-                info = sq.last_shard_info()
+                    td += t2 - t1b
                 rows[len(devs)] = {"value": vol.nbytes * steps / (te + td) / 1e9, "encode_ms": te / steps * 1e3, "decode_ms": td / steps * 1e3,
                                    "gpus_used_by_the_call": max(info["gpus"], 1), "nccl_histogram_allreduce": info["nccl"],
+                                   "nccl_allreduces_so_far": sq.nccl_allreduces(),
                                    "blob_bytes": int(b.size), "checksum": int(out[::4097].astype(np.uint64).sum())}
             one, many = rows[1], rows[ctx.world]
             res = {"workload": wname, "pipeline": pipeline, "unit": "GB/s", "value": many["value"], "gpus": ctx.world,
                    "one_gpu_value": one["value"], "speedup_over_one_gpu": many["value"] / one["value"],
                    "encode_ms": many["encode_ms"], "decode_ms": many["decode_ms"], "one_gpu_encode_ms": one["encode_ms"],
                    "one_gpu_decode_ms": one["decode_ms"], "gpus_used_by_the_call": many["gpus_used_by_the_call"],
-                   "nccl_histogram_allreduce": many["nccl_histogram_allreduce"],
+                   "nccl_histogram_allreduce": many["nccl_histogram_allreduce"], "nccl_allreduces_in_library": many["nccl_allreduces_so_far"],
                    "same_blob_size_and_voxels_as_one_gpu": many["blob_bytes"] == one["blob_bytes"] and many["checksum"] == one["checksum"],
                    "api": "SQY_PipelineEncode_UI16 + SQY_Decode_UI16, one pinned host stack, z-slabs over all GPUs inside the library"}
             del h_vol, h_out, h_blob
