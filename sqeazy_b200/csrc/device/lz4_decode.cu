@@ -638,16 +638,24 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
           if (offset >= mlen || offset >= 32u) {
             // a 32-byte step never reads a byte it writes; later steps may read what earlier ones wrote
             if ((uint32_t)lane < mlen) SQYB_W(mo + lane) = SQYB_W(base + lane);
+#pragma unroll 1
             for (uint32_t k = lane + 32u; k < mlen + lane; k += 32u) {   // (same trip count on every lane)
               __syncwarp();
               if (k < mlen) SQYB_W(mo + k) = SQYB_W(base + k);
             }
           } else if ((offset & (offset - 1u)) == 0u) {
             // period 1, 2, 4, 8, 16: every byte comes from the pattern in front of the match
+            // (first step peeled, the rest not unrolled: most matches have at most 32 bytes, and an unrolled loop pays its
+            //  remainder logic on every one of them)
             const uint32_t om = offset - 1u;
-            for (uint32_t k = lane; k < mlen; k += 32u) SQYB_W(mo + k) = SQYB_W(base + (k & om));
+            if ((uint32_t)lane < mlen) SQYB_W(mo + lane) = SQYB_W(base + (lane & om));
+            if (mlen > 32u) {
+#pragma unroll 1
+              for (uint32_t k = lane + 32u; k < mlen; k += 32u) SQYB_W(mo + k) = SQYB_W(base + (k & om));
+            }
           } else {
             const float inv = __frcp_rn((float)offset);
+#pragma unroll 1
             for (uint32_t k = lane; k < mlen; k += 32u)   // k < 512: the quotient is exact
               SQYB_W(mo + k) = SQYB_W(base + (k - offset * (uint32_t)__float2int_rz(((float)k + 0.5f) * inv)));
           }
@@ -660,8 +668,13 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
           // occurrence of a pattern (lz4_encode.cu) reads the same early lines of the block over and over.
           const uint8_t* from = O.d + (mo - offset);
           if (O.line_aligned) {
-            for (uint32_t k = lane; k < mlen; k += 32u) SQYB_W(mo + k) = ld_l1_u8(from + k);
+            if ((uint32_t)lane < mlen) SQYB_W(mo + lane) = ld_l1_u8(from + lane);
+            if (mlen > 32u) {
+#pragma unroll 1
+              for (uint32_t k = lane + 32u; k < mlen; k += 32u) SQYB_W(mo + k) = ld_l1_u8(from + k);
+            }
           } else {
+#pragma unroll 1
             for (uint32_t k = lane; k < mlen; k += 32u) SQYB_W(mo + k) = __ldcg(from + k);
           }
         } else if (!do_match(mo, offset, mlen)) {   // reaches in front of a linked block
