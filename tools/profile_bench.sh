@@ -3,7 +3,7 @@
 # `--set full` capture of the dominant kernel. Outputs land in gpurun_out/ (copy the summaries into profiles/).
 set -u
 W=${1:-cfg2}
-CMD="python bench.py --workload $W --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+CMD="python bench.py --workload $W --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-per-config"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_bench_$W.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_bench_$W.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$W.csv $CMD > gpurun_out/ncu_launches_$W.log 2>&1

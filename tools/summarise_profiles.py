@@ -29,7 +29,7 @@ for r in rows[hi + 1:]:
     n[name] += 1
 tot = sum(t.values())
 with open(os.path.join(out, f"{tag}_{w}_launch_shares.txt"), "w") as f:
-    f.write(f"ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --workload {w} --steps 2 --warmup 3 --no-e2e --no-cpu-baseline\n")
+    f.write(f"ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --workload {w} --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-per-config\n")
     f.write("kernel, launches, total_us, share_of_all_kernel_time (cold-cache serialised: compare shares only; torch kernels = synthetic-volume generator)\n")
     for k in sorted(t, key=lambda k: -t[k]):
         f.write(f"{k}, {n[k]}, {t[k]:.1f}, {100 * t[k] / tot:.1f}%\n")
