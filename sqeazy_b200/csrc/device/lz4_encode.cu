@@ -47,7 +47,7 @@ constexpr int kInf = 0x7FFFFFFF;
 constexpr int kNumOff = 5;               // fixed offsets, in priority order: 1, 2, 4, 3, pitch
 constexpr int kListMax = 15104;          // positions that may look up the hash table (more: the rest goes without; sized so that
                                          // three CTAs still fit an SM — only all-noise blocks list more, and those are stored)
-constexpr int kEarlyBytes = 4096;        // early-store test after the hash waves of the first 4 KiB ...
+constexpr int kEarlyBytes = 2048;        // early-store test on the hash candidates of the first 2 KiB (tools/lz4_model2.c EARLY=: 4096, 2048 and 1024 decide alike) ...
 constexpr int kEarlyMin = 128;           // ... a block with fewer candidates than this is stored
 constexpr uint32_t kNoCand = 0xFFFFu;
 constexpr uint32_t kNoPos = 0xFFFFFFFFu;
@@ -88,6 +88,17 @@ __device__ __forceinline__ int ext_bytes(int v) {
 __device__ __forceinline__ uint32_t load4(const uint32_t* words, int byte_off) {
   const uint32_t w0 = words[byte_off >> 2], w1 = words[(byte_off >> 2) + 1];
   return __funnelshift_r(w0, w1, (byte_off & 3) * 8);
+}
+
+// one step of a byte-equality bit mask: the four bits "byte j of a == byte j of b" are shifted in at the top of e, so that
+// after the eight words of a segment word k's bits sit at 4k..4k+3. (x has a zero byte where a and b agree; bit 7 of
+// ((x & 0x7f..) + 0x7f..) | x is clear exactly in those bytes; one high-half multiply gathers the four flags — it runs in the
+// FMA pipe, next to the logic pipe that bounds this kernel. Six instructions where __vcmpeq4 + mask + multiply + shifts take nine.)
+__device__ __forceinline__ uint32_t eq4_shift_in(uint32_t e, uint32_t a, uint32_t b) {
+  const uint32_t x = a ^ b;
+  const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+  const uint32_t y = ~(t | x) & 0x80808080u;
+  return __funnelshift_r(e, __umulhi(y, 0x02040810u), 4);   // bits 7, 15, 23, 31 of y -> bits 0..3 of the high word
 }
 
 // writes the LZ4 length extension for `v` (nibble already holds 15) at p, returns bytes written
@@ -144,8 +155,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const uint32_t prev = d == 4 ? W[k] : __funnelshift_r(W[k], W[k + 1], 32 - 8 * d);   // bytes 4k-d .. 4k-d+3
-        const uint32_t eq = __vcmpeq4(W[k + 1], prev);
-        e |= (((eq & 0x08040201u) * 0x01010101u) >> 24) << (4 * k);
+        e = eq4_shift_in(e, W[k + 1], prev);
       }
       if (tid == 0) e &= ~((1u << d) - 1u);            // no source in front of the block
       S.E[q][tid] = e & tailmask;
@@ -155,8 +165,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
       if (pitch_words > 0 && 8 * tid >= pitch_words) {   // (whole segments: the pitch is a multiple of 32 bytes)
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint32_t eq = __vcmpeq4(W[k + 1], S.data[8 * tid + k - pitch_words]);
-          e |= (((eq & 0x08040201u) * 0x01010101u) >> 24) << (4 * k);
+          e = eq4_shift_in(e, W[k + 1], S.data[8 * tid + k - pitch_words]);
         }
       }
       S.E[4][tid] = e & tailmask;
@@ -230,7 +239,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
         S.list[e++] = (uint16_t)(seg_lo + j);
       }
     };
-    // a block that may turn out to be noise lists its first 4 KiB only before that is known (in noise every position
+    // a block that may turn out to be noise lists its first 2 KiB only before that is known (in noise every position
     // wants a lookup: 32 stores per thread)
     const bool test_early = !rich && n > kEarlyBytes;
     if (!test_early || tid < kEarlyBytes / 32) write_list();
@@ -274,12 +283,12 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
       }
       return nfound;
     };
-    // Early store: a block whose candidates (fixed-offset ones of the whole block + hash candidates of the first 4 KiB)
+    // Early store: a block whose candidates (fixed-offset ones of the whole block + hash candidates of the first 2 KiB)
     // are fewer than one per 32 sampled bytes is noise — camera-noise bit planes, 8-bit quantiser codes — and would
     // shrink by < 3 % (tools/lz4_model.c: such blocks have < 70 candidates and end at 0.97..1.00 of their size, everything
     // that compresses to <= 0.82 has > 600). It is stored without the rest of the list, the parse and the emission,
-    // which is also what makes its decode a plain copy. (Positions of the first 4 KiB find the same sources in a table
-    // that holds the first 4 KiB only as in the full one: a first occurrence lies in front of them.)
+    // which is also what makes its decode a plain copy. (Positions of the first 2 KiB find the same sources in a table
+    // that holds the first 2 KiB only as in the full one: a first occurrence lies in front of them.)
     int done = 0;
     if (test_early) {
       done = min(S.wave_start[kEarlyBytes / kSub], kListMax);

@@ -262,8 +262,9 @@ def test_lz4_random_blocks_are_stored(sq, cuda):
 
 
 def test_lz4_noise_blocks_are_stored_early(sq, cuda, port, ref):
-    """blocks with fewer than one match candidate per 32 sampled bytes (camera-noise bit planes, 8-bit quantiser codes of a
-    noisy stack) are stored after the hash rounds of their first 4 KiB (lz4_encode.cu: kEarlyRounds / kEarlyMin). The
+    """blocks with fewer than 128 match candidates — fixed-offset ones of the whole block + hash ones of the first 2 KiB —
+    (camera-noise bit planes, 8-bit quantiser codes of a noisy stack) are stored without a parse (lz4_encode.cu: kEarlyBytes /
+    kEarlyMin; tools/lz4_model2.c EARLY=2048 DUMP=1: noise blocks count <= 29, every compressible block of the sample sets >= 243). The
     stated price: such blocks shrink by < 3 % under the reference's liblz4, so the payload stays within 3 % of the
     reference's; compressible blocks never take that exit."""
     vol = numpy_volume((16, 512, 512), "scmos", index=8)

@@ -27,7 +27,7 @@ int main(int argc, char** argv) {
   int offs[16], noff = 0;
   for (char* t = strtok(argv[6], ","); t && noff < 16; t = strtok(NULL, ",")) offs[noff++] = atoi(t);
   int hashlog = getenv("HLOG") ? atoi(getenv("HLOG")) : 12; int listmax = getenv("LISTMAX") ? atoi(getenv("LISTMAX")) : 1<<30; int round = getenv("ROUND") ? atoi(getenv("ROUND")) : 512;
-  long nfar = 0; long out = 0, nseq = 0, nconst = 0, nstored = 0, lookups = 0, by_off[17] = {0}, bytes_off[17] = {0};
+  long nfar = 0, early_lost = 0, nearly = 0; long out = 0, nseq = 0, nconst = 0, nstored = 0, lookups = 0, by_off[17] = {0}, bytes_off[17] = {0};
   int* cand = malloc(sizeof(int) * (block + 16));
   int* tab = malloc(sizeof(int) << hashlog);
   for (long o = 0; o < total; o += block) {
@@ -108,6 +108,20 @@ int main(int argc, char** argv) {
       }
     }
     long bo = 0; int anchor = 0, pos = 0;
+    int early_p = getenv("EARLY") ? atoi(getenv("EARLY")) : 0, early_min = getenv("EARLYMIN") ? atoi(getenv("EARLYMIN")) : 128, early_store = 0;
+    if (early_p && n > early_p) {
+      int cnt = 0;
+      for (int i = 0; i + 12 <= n; ++i) {
+        int c = cand[i]; if (c < 0) continue;
+        int isfixed = 0; for (int q = 0; q < noff; ++q) if (i - c == offs[q]) isfixed = 1;
+        if (isfixed) { cnt++; continue; }
+        if (i >= early_p) continue;
+        int cut_hi = ((i / cut) + 1) * cut, lim = n - 5 < cut_hi ? n - 5 : cut_hi, l = 0;
+        while (l < 5 && i + l < lim && d[i + l] == d[c + l]) l++;
+        if (l >= 5) cnt++;
+      }
+      early_store = cnt < early_min;
+    }
     while (pos < n) {
       int c = cand[pos];
       if (c < 0) { pos++; continue; }
@@ -127,10 +141,11 @@ int main(int argc, char** argv) {
     }
     int lit = n - anchor;
     bo += 1 + ext_bytes(lit) + lit;
+    if (early_store) { if (bo < n) early_lost += n - bo; nearly++; bo = n; }
     if (bo >= n) { bo = n; nstored++; }
     out += 4 + bo;
   }
-  printf("far matches %ld  ", nfar);
+  printf("far matches %ld  early-stored %ld (lost %ld B)  ", nfar, nearly, early_lost);
   printf("%s block=%d cut=%d hash=%d min=%d: %ld -> %ld ratio %.3f seqs %ld const %ld stored %ld lookups %.1f%%\n", argv[1], block, cut, use_hash, minmatch,
          total, out, (double)total / out, nseq, nconst, nstored, 100.0 * lookups / total);
   for (int q = 0; q <= noff; ++q) printf("   off %d: %ld matches, %ld bytes\n", q < noff ? offs[q] : -1, by_off[q], bytes_off[q]);
