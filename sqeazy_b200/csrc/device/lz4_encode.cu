@@ -14,18 +14,19 @@
 //             sample scattered differently) — one bit per position, 32 positions per thread
 //   phase A1: fixed-offset candidates (>= 5 equal bytes) and their 2-bit length codes by shifts / ANDs on the masks
 //   phase A2: the positions without such a candidate (a few per cent of a sparse plane) are COMPACTED into a list and
-//             looked up in a shared-memory hash table of earlier positions, one wave per 1 KiB sub-block: the table
-//             holds the sub-blocks in front (atomicMax inserts behind a barrier => deterministic), all 512 threads
-//             work on list entries instead of 16 warps each meeting 32 barriers for a handful of lookups
+//             looked up in ONE shared-memory hash table that holds the FIRST listed position of the block per hash:
+//             all 512 threads insert their entries with atomicMin (=> deterministic), one barrier, all 512 threads look
+//             theirs up — two sweeps over the list (the version before ran 16 waves of 2 barriers, one per 1 KiB sub-block)
 //   phase B : every THREAD parses its own 32-byte segment greedily with bit operations only; the length of a run
 //             (fixed-offset match) is read off the masks in O(1): ones to the end of the segment, whole segments by
 //             a per-warp "all ones" bit set, the rest from one more mask word. Hash matches are extended the same way
 //             where both sides sit in runs, 4 bytes at a time where not. A match may overshoot into later segments
 //             of the warp's 1 KiB sub-block, whose entry points move until the warp's parse is stable
-//   phase C : warp scans chain literal carries and encoded sizes (segments without a match hand their
-//             literals to the next sequence)
-//   phase D : every thread emits its own sequences; trailing literals are copied by the thread that owns
-//             the bytes into the sequence that owns them
+//   phase C : the selected matches of all segments are compacted into one list in stream order (position | length, offset)
+//   phase D : from here on a SEQUENCE has a thread: literal count, size, output offset (block-wide scan), token, length bytes,
+//             offset and the literals (runs of more than 32 bytes are queued and copied by whole warps) follow from a list
+//             entry and its predecessor — evenly spread over the 512 threads, where a thread that sized and emitted the
+//             sequences of its own segment kept 4-12 of 32 lanes busy
 //   hand-off: size word into the index frame + compressed bytes into a per-block staging slot (no CTA waits for
 //             another); lz4_tile_sums_kernel + lz4_block_offsets_kernel prefix-sum the sizes over many CTAs and
 //             lz4_scatter_kernel moves every block to its final offset (replaces remove_blanks)
@@ -51,6 +52,7 @@ constexpr int kEarlyBytes = 2048;        // early-store test on the hash candida
 constexpr int kEarlyMin = 128;           // ... a block with fewer candidates than this is stored
 constexpr uint32_t kNoCand = 0xFFFFu;
 constexpr uint32_t kNoPos = 0xFFFFFFFFu;
+constexpr int kLitSelf = 32;             // literal runs up to this length are copied by their sequence's thread
 
 static_assert(kSegs == kThreads, "one segment per thread");
 static_assert(kSub == 1024 && kSegs / kWarps == 32, "a warp's 32 segments are one sub-block = one hash wave");
@@ -63,17 +65,16 @@ struct __align__(16) EncSmem {
   };
   union {
     uint32_t htab[1 << kHashLog];        // phase A2 only: FIRST listed position of the block with this hash (kNoPos: none)
-    struct {
-      int seg_litbase[kSegs];            // phase D: dest(p) = seg_litbase + p for the literal run ending at the segment's first match
-      uint16_t lead[kNumOff][kSegs];     // phase B: ones of E[q] from the first position of segment t on, to the end of the warp's sub-block at most
-    };
+    uint16_t lead[kNumOff][kSegs];       // phase B: ones of E[q] from the first position of segment t on, to the end of the warp's sub-block at most
+                                         // phases C, D: the block's sequences, position | length << 14
   };
-  uint32_t E[kNumOff][kSegs + 4];        // E[q][t] bit j: data[32t+j] == data[32t+j-off(q)]
+  uint32_t E[kNumOff][kSegs + 4];        // E[q][t] bit j: data[32t+j] == data[32t+j-off(q)]; phases C, D: the sequences' offsets (uint16)
   uint32_t segHM[kSegs];                 // per segment: positions with a hash candidate (>= 5 bytes)
   uint32_t full[kNumOff][kWarps];        // per warp: segments whose E[q] word is all ones
   int wave_start[kWarps + 1];            // list index of every sub-block's first entry
-  int w_T[kWarps], w_has[kWarps], w_carry_in[kWarps], w_size[kWarps], w_off[kWarps], w_first[kWarps], w_next[kWarps];
-  int final_off, final_lit, total;
+  int w_size[kWarps], w_off[kWarps];     // per-warp totals of the scans
+  int total;
+  int nlong;                             // phase D: queued long literal runs
   int early;                             // candidates seen by the early-store test
 };
 
@@ -411,145 +412,134 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
       if (!__any_sync(0xffffffffu, need)) break;
     }
 
-    // ---------------- phase C: sizes, literal carries, output offsets ----------------
-    const int seg_end = max(0, min(32, n - seg_lo));   // valid positions of this segment
-    if (entry > seg_end) entry = seg_end;
-    int nm = 0, rest = 0, F = 0, p = entry;
+    // ---------------- phase C: the selected matches of the block, compacted in stream order ----------------
+    // Phases A and B give every 32-byte segment a thread; the sequences they select are spread unevenly (none inside a run,
+    // five or six around the isolated bytes of a sparse plane), and a thread that sizes and emits the sequences of its own
+    // segment one after the other keeps 4-12 of the 32 lanes busy. From here on a SEQUENCE has a thread: the matches are
+    // written to a list (position | length, offset), everything else — literal counts, sizes, output offsets, tokens,
+    // literal copies — follows from a list entry and its predecessor, evenly spread over the 512 threads.
+    const int nm = __popc(Sel);
+    int sincl = nm;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, sincl, d);
+      if (lane >= d) sincl += t;
+    }
+    if (lane == 31) S.w_size[warp] = sincl;
+    __syncthreads();                                   // every warp is through phase B as well: S.E and S.lead are free
+    int sbase = sincl - nm, nseq = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const int c = S.w_size[w];
+      nseq += c;
+      if (w < warp) sbase += c;
+    }
+    uint32_t* seq_pl = S.htab;                                           // position | length << 14
+    uint16_t* seq_off = reinterpret_cast<uint16_t*>(&S.E[0][0]);         // match offset
+    static_assert(sizeof(S.htab) >= 4 * (kB / 5 + 2) && sizeof(S.E) >= 2 * (kB / 5 + 2), "room for every sequence of a block");
     {
       uint32_t m = Sel;
       unsigned long long q = lens;
+      int k = sbase;
       while (m) {
         const int j = __ffs(m) - 1;
         m &= m - 1;
         const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
         int len = 5 + code;
         if (code == 3) { len = (int)(q & 0x7FF); q >>= 11; }
-        const int lit = j - p;
-        if (nm == 0) { F = lit; rest += 3 + ext_bytes(len - 4); }
-        else rest += 3 + ext_bytes(lit) + lit + ext_bytes(len - 4);
-        nm++;
-        p = j + len;
+        const int i = seg_lo + j;
+        uint32_t off;
+        if ((Ms >> j) & 1u) {
+          const uint32_t qq = ((D0 >> j) & 1u) | (((D1 >> j) & 1u) << 1) | (((D2 >> j) & 1u) << 2);
+          off = qq == 0 ? 1u : (qq == 1 ? 2u : (qq == 2 ? 4u : (qq == 3 ? 3u : 4u * (uint32_t)pitch_words)));
+        } else {
+          off = (uint32_t)(i - (int)(S.list[mybase + __popc(wants & ((1u << j) - 1u))] & 0x3FFFu));
+        }
+        seq_pl[k] = (uint32_t)i | ((uint32_t)len << 14);
+        seq_off[k] = (uint16_t)off;
+        ++k;
       }
     }
-    const int T = p < seg_end ? seg_end - p : 0;   // trailing literals, owned by a later sequence
-    const int has = nm > 0;
-    // carry scan: f_l(x) = has ? T : x + T ; combine(a,b) = (b.has ? b.T : a.T + b.T, a.has | b.has)
-    int sT = T, sH = has;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int tT = __shfl_up_sync(0xffffffffu, sT, d), tH = __shfl_up_sync(0xffffffffu, sH, d);
-      if (lane >= d) { sT = sH ? sT : tT + sT; sH |= tH; }
-    }
-    int eT = __shfl_up_sync(0xffffffffu, sT, 1), eH = __shfl_up_sync(0xffffffffu, sH, 1);   // exclusive
-    if (lane == 0) { eT = 0; eH = 0; }
-    // next segment (after this one) that owns a match
-    int nx = has ? tid : kInf;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_down_sync(0xffffffffu, nx, d);
-      if (lane + d < 32) nx = min(nx, t);
-    }
-    int nxt = __shfl_down_sync(0xffffffffu, nx, 1);
-    if (lane == 31) nxt = kInf;
-    if (lane == 31) { S.w_T[warp] = sT; S.w_has[warp] = sH; }
-    if (lane == 0) S.w_first[warp] = nx;
-    __syncthreads();
-    if (tid == 0) {
-      int x = 0;
-      for (int w = 0; w < kWarps; ++w) { S.w_carry_in[w] = x; x = S.w_has[w] ? S.w_T[w] : x + S.w_T[w]; }
-      S.final_lit = x;
-      int nn = kInf;
-      for (int w = kWarps - 1; w >= 0; --w) { S.w_next[w] = nn; nn = min(nn, S.w_first[w]); }
-    }
-    __syncthreads();
-    const int C = eH ? eT : S.w_carry_in[warp] + eT;   // literals carried into this segment's first sequence
-    if (nxt == kInf) nxt = S.w_next[warp];
-    const int size = has ? ext_bytes(C + F) + C + F + rest : 0;
-    int incl = size;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
-    }
-    if (lane == 31) S.w_size[warp] = incl;
-    // offsets of the selected matches, fetched before `out` starts to overwrite `cand`
-    uint32_t offs[4] = {0, 0, 0, 0};
+    if (tid == 0) S.nlong = 0;
+    __syncthreads();                                   // the list is complete; S.list (candidates) is free from here on
+
+    // sequences [s0, s1) of this thread; entry nseq stands for the block's final literal run
+    const int per = (nseq + kThreads) / kThreads;      // ceil((nseq + 1) / kThreads)
+    const int s0 = min(tid * per, nseq + 1), s1 = min(s0 + per, nseq + 1);
+    int mysize = 0;
     {
-      uint32_t m = Sel;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (m) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          const int i = seg_lo + j;
-          uint32_t off;
-          if ((Ms >> j) & 1u) {
-            const uint32_t q = ((D0 >> j) & 1u) | (((D1 >> j) & 1u) << 1) | (((D2 >> j) & 1u) << 2);
-            off = q == 0 ? 1u : (q == 1 ? 2u : (q == 2 ? 4u : (q == 3 ? 3u : 4u * (uint32_t)pitch_words)));
-          } else {
-            off = (uint32_t)(i - (int)(S.list[mybase + __popc(wants & ((1u << j) - 1u))] & 0x3FFFu));
-          }
-          offs[k >> 1] |= off << (16 * (k & 1));
+      int prev_end = 0;
+      if (s0 > 0 && s0 <= nseq) { const uint32_t pp = seq_pl[s0 - 1]; prev_end = (int)(pp & 0x3FFFu) + (int)(pp >> 14); }
+      for (int sq = s0; sq < s1; ++sq) {
+        if (sq < nseq) {
+          const uint32_t pl = seq_pl[sq];
+          const int pos = (int)(pl & 0x3FFFu), len = (int)(pl >> 14), lit = pos - prev_end;
+          mysize += 3 + ext_bytes(lit) + lit + ext_bytes(len - 4);
+          prev_end = pos + len;
+        } else {
+          const int lit = n - prev_end;
+          mysize += 1 + ext_bytes(lit) + lit;
         }
       }
     }
-    __syncthreads();
-    if (tid == 0) {
-      int off = 0;
-      for (int w = 0; w < kWarps; ++w) { S.w_off[w] = off; off += S.w_size[w]; }
-      S.final_off = off;
-      S.total = off + 1 + ext_bytes(S.final_lit) + S.final_lit;
+    int oincl = mysize;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, oincl, d);
+      if (lane >= d) oincl += t;
     }
+    if (lane == 31) S.w_off[warp] = oincl;
     __syncthreads();
-    csize = S.total;
-    if (csize >= n) {
+    int o = oincl - mysize;
+    csize = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const int c = S.w_off[w];
+      csize += c;
+      if (w < warp) o += c;
+    }
+    if (csize >= n || nseq == 0) {
       stored = true;
     } else {
-      // ---------------- phase D: emission ----------------
-      const int final_litbase = S.final_off + 1 + ext_bytes(S.final_lit) - (n - S.final_lit);
-      if (has) {
-        int o = S.w_off[warp] + incl - size;
-        uint32_t m = Sel;
-        unsigned long long q = lens;
-        int pp = entry;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (m) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            const int code = ((C0 >> j) & 1) | (((C1 >> j) & 1) << 1);
-            int len = 5 + code;
-            if (code == 3) { len = (int)(q & 0x7FF); q >>= 11; }
-            const int own = j - pp;                    // literals of this sequence inside this segment
-            const int lit = k == 0 ? C + own : own;
-            const int el = ext_bytes(lit);
-            const int ml = len - 4;
-            out8[o] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (ml < 15 ? ml : 15));
-            if (lit >= 15) put_ext(out8 + o + 1, lit);
-            int d = o + 1 + el + (lit - own);          // where this segment's own literals go
-            if (k == 0) S.seg_litbase[tid] = o + 1 + el - (seg_lo + entry - C);
-            for (int t = 0; t < own; ++t) out8[d + t] = data8[seg_lo + pp + t];
-            d += own;
-            const uint32_t off = (offs[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-            out8[d] = (uint8_t)(off & 0xff);
-            out8[d + 1] = (uint8_t)(off >> 8);
-            if (ml >= 15) put_ext(out8 + d + 2, ml);
-            o = d + 2 + ext_bytes(ml);
-            pp = j + len;
-          }
+      // ---------------- phase D: emission, a thread per sequence ----------------
+      // Literal runs of up to kLitSelf bytes are copied by the sequence's thread, longer ones (noise between runs) are queued
+      // and copied by whole warps afterwards.
+      uint32_t* longrec = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(S.list) + sizeof(S.out));   // behind `out`
+      static_assert(sizeof(S.list) >= sizeof(S.out) + 8 * (kB / (kLitSelf + 1) + 2), "room for the long literal runs");
+      int prev_end = 0;
+      if (s0 > 0 && s0 <= nseq) { const uint32_t pp = seq_pl[s0 - 1]; prev_end = (int)(pp & 0x3FFFu) + (int)(pp >> 14); }
+      for (int sq = s0; sq < s1; ++sq) {
+        const bool fin = sq >= nseq;
+        int pos = n, len = 4;
+        if (!fin) { const uint32_t pl = seq_pl[sq]; pos = (int)(pl & 0x3FFFu); len = (int)(pl >> 14); }
+        const int lit = pos - prev_end, ml = len - 4;
+        out8[o] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (fin ? 0 : (ml < 15 ? ml : 15)));
+        int d = o + 1;
+        if (lit >= 15) d += put_ext(out8 + d, lit);
+        if (lit <= kLitSelf) {
+          for (int t = 0; t < lit; ++t) out8[d + t] = data8[prev_end + t];
+        } else {
+          const int r = atomicAdd(&S.nlong, 1);          // (the order of the queue does not reach the output)
+          longrec[2 * r] = (uint32_t)prev_end | ((uint32_t)lit << 14);
+          longrec[2 * r + 1] = (uint32_t)d;
         }
+        d += lit;
+        if (!fin) {
+          const uint32_t off = seq_off[sq];
+          out8[d] = (uint8_t)(off & 0xff);
+          out8[d + 1] = (uint8_t)(off >> 8);
+          d += 2;
+          if (ml >= 15) d += put_ext(out8 + d, ml);
+        }
+        o = d;
+        prev_end = pos + len;
       }
       __syncthreads();
-      // trailing literals belong to the next sequence (or to the block's final literal run)
-      if (T > 0) {
-        const int lb = nxt == kInf ? final_litbase : S.seg_litbase[nxt];
-        for (int t = 0; t < T; ++t) out8[lb + seg_lo + p + t] = data8[seg_lo + p + t];
-      }
-      if (tid == 0) {
-        const int L = S.final_lit;
-        uint8_t* fp = out8 + S.final_off;
-        fp[0] = (uint8_t)((L < 15 ? L : 15) << 4);
-        if (L >= 15) put_ext(fp + 1, L);
+      const int nlong = S.nlong;
+      for (int r = warp; r < nlong; r += kWarps) {
+        const uint32_t r0 = longrec[2 * r], dst = longrec[2 * r + 1];
+        const int from = (int)(r0 & 0x3FFFu), cnt = (int)(r0 >> 14);
+        for (int t = lane; t < cnt; t += 32) out8[dst + t] = data8[from + t];
       }
     }
   }
