@@ -65,7 +65,8 @@ struct __align__(16) EncSmem {
   };
   union {
     uint32_t htab[1 << kHashLog];        // phase A2 only: FIRST listed position of the block with this hash (kNoPos: none)
-    uint16_t lead[kNumOff][kSegs];       // phase B: ones of E[q] from the first position of segment t on, to the end of the warp's sub-block at most
+    uint16_t lead[kNumOff][kSegs + 2];   // phase B: ones of E[q] from the first position of segment t on, to the end of the warp's sub-block at
+                                         // most; 0 for the first segment of a sub-block (what a run of the sub-block in front continues with)
                                          // phases C, D: the block's sequences, position | length << 14
   };
   uint32_t E[kNumOff][kSegs + 4];        // E[q][t] bit j: data[32t+j] == data[32t+j-off(q)]; phases C, D: the sequences' offsets (uint16)
@@ -102,6 +103,20 @@ __device__ __forceinline__ uint32_t eq4_shift_in(uint32_t e, uint32_t a, uint32_
   return __funnelshift_r(e, __umulhi(y, 0x02040810u), 4);   // bits 7, 15, 23, 31 of y -> bits 0..3 of the high word
 }
 
+// per-warp totals of a block-wide scan (one int per warp in shared memory, complete behind a barrier) -> what the warps in
+// front of this one add up to, and the grand total: a 16-lane shuffle scan instead of sixteen loads and adds per thread
+__device__ __forceinline__ void warp_totals(const int* totals, int warp, int lane, int& before, int& all) {
+  int v = lane < kWarps ? totals[lane] : 0;
+#pragma unroll
+  for (int d = 1; d < kWarps; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += t;
+  }
+  all = __shfl_sync(0xffffffffu, v, kWarps - 1);
+  const int prev = __shfl_sync(0xffffffffu, v, (warp + 31) & 31);
+  before = warp ? prev : 0;
+}
+
 // writes the LZ4 length extension for `v` (nibble already holds 15) at p, returns bytes written
 __device__ __forceinline__ int put_ext(uint8_t* p, int v) {
   int r = v - 15, k = 0;
@@ -116,9 +131,8 @@ __device__ __forceinline__ int put_ext(uint8_t* p, int v) {
 __device__ __forceinline__ int run_ones(const EncSmem& S, int q, int x) {
   const int t = x >> 5, b = x & 31;
   const uint32_t z = ~(S.E[q][t] >> b);          // zeros where the run goes on; the shifted-in bits end it at the segment border
-  const int r = z ? __ffs(z) - 1 : 32;           // (z == 0 only for b == 0 and a full word)
-  if (r < 32 - b || (t & 31) == 31) return min(r, 32 - b);
-  return 32 - b + (int)S.lead[q][t + 1];
+  const int r = z ? __ffs(z) - 1 : 32;           // (z == 0 only for b == 0 and a full word); r <= 32 - b
+  return r == 32 - b ? r + (int)S.lead[q][t + 1] : r;   // (the entry of a sub-block's first segment is 0: runs end there)
 }
 
 // The general path of a block (phases A0..D on the bytes in S.data), kept out of line: the closed-form path of all-equal
@@ -226,11 +240,11 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
     // (the barrier carries the one bit the early-store test needs first: a warp that is already rich in fixed-offset
     //  candidates — every compressible bit-plane block — settles it for the CTA at no cost)
     const int rich = __syncthreads_or(ncand_short >= kEarlyMin);
-    int wbase = 0;
-    for (int w = 0; w < warp; ++w) wbase += S.w_size[w];
+    int wbase, wall;
+    warp_totals(S.w_size, warp, lane, wbase, wall);
     mybase = wbase + incl - cnt;
     if (lane == 0) S.wave_start[warp] = wbase;
-    if (tid == kThreads - 1) S.wave_start[kWarps] = wbase + incl;
+    if (tid == 0) S.wave_start[kWarps] = wall;
     auto write_list = [&]() {
       uint32_t m = wants;
       int e = mybase;
@@ -319,7 +333,8 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
       const uint32_t nf = ~(S.full[q][warp] >> lane);          // zeros: full segments from this one on (shifted-in bits: the warp ends)
       const int k = min(nf ? __ffs(nf) - 1 : 32, 32 - lane);   // full segments in a row, this one included
       const int tail = __shfl_sync(0xffffffffu, lead, (lane + k) & 31);   // leading ones of the first segment that is not full
-      S.lead[q][tid] = (uint16_t)(32 * k + (lane + k < 32 ? tail : 0));
+      S.lead[q][tid] = lane ? (uint16_t)(32 * k + (lane + k < 32 ? tail : 0)) : (uint16_t)0;
+      if (tid == 0) S.lead[q][kSegs] = 0;
     }
   }
   const uint32_t HM = S.segHM[tid];
@@ -427,13 +442,9 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
     }
     if (lane == 31) S.w_size[warp] = sincl;
     __syncthreads();                                   // every warp is through phase B as well: S.E and S.lead are free
-    int sbase = sincl - nm, nseq = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      const int c = S.w_size[w];
-      nseq += c;
-      if (w < warp) sbase += c;
-    }
+    int sbase, nseq;
+    warp_totals(S.w_size, warp, lane, sbase, nseq);
+    sbase += sincl - nm;
     uint32_t* seq_pl = S.htab;                                           // position | length << 14
     uint16_t* seq_off = reinterpret_cast<uint16_t*>(&S.E[0][0]);         // match offset
     static_assert(sizeof(S.htab) >= 4 * (kB / 5 + 2) && sizeof(S.E) >= 2 * (kB / 5 + 2), "room for every sequence of a block");
@@ -490,14 +501,9 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
     }
     if (lane == 31) S.w_off[warp] = oincl;
     __syncthreads();
-    int o = oincl - mysize;
-    csize = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      const int c = S.w_off[w];
-      csize += c;
-      if (w < warp) o += c;
-    }
+    int o;
+    warp_totals(S.w_off, warp, lane, o, csize);
+    o += oincl - mysize;
     if (csize >= n || nseq == 0) {
       stored = true;
     } else {
