@@ -194,6 +194,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
   uint32_t wants = 0;                                        // positions that look up the hash table
   {
     uint32_t L6 = 0, L7 = 0, L8 = 0;
+    uint32_t tail4 = 0;                                  // positions inside a byte run with exactly four equal bytes ahead
 #pragma unroll
     for (int q = 0; q < kNumOff; ++q) {
       // matches never cross the warp's 1 KiB sub-block: the last segment sees no successor
@@ -201,6 +202,16 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
       const unsigned long long e = (unsigned long long)own | ((unsigned long long)(lane == 31 ? 0u : S.E[q][tid + 1]) << 32);
       const unsigned long long r5 = e & (e >> 1) & (e >> 2) & (e >> 3) & (e >> 4);
       const unsigned long long r6 = r5 & (e >> 5), r7 = r6 & (e >> 6), r8 = r7 & (e >> 7);
+      if (q == 0) {
+        // Inside a run of equal bytes, the position with exactly four of them ahead never pays for a lookup: a match from
+        // there would have to carry the run's last four bytes AND what follows it, and the parse only lands there when a
+        // hash match ends on that very byte (tools/lz4_model2.c NOINTERIOR=1 NIQ=1 KEEPTAIL=3: 12 % fewer lookups on
+        // background-removed planes — the phase that dominates their sparse planes — at the same size; the three positions
+        // behind it are worth 0.5 % of the size each and keep looking up)
+        const uint32_t r4only = (uint32_t)(e & (e >> 1) & (e >> 2) & (e >> 3) & ~r5);
+        const uint32_t before = (own << 1) | (lane ? S.E[0][tid - 1] >> 31 : 0u);   // the byte in front continues the run too
+        tail4 = r4only & before;
+      }
       const uint32_t sel = (uint32_t)r5 & ~Ms;         // at least 5 bytes and no better-ranked offset yet
       Ms |= sel;
       L6 |= sel & (uint32_t)r6;
@@ -217,7 +228,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
     Ms &= valid;
     C0 = (L6 ^ L7 ^ L8) & Ms;                          // code = number of the planes L6,L7,L8 that are set: 5,6,7,>=8 bytes
     C1 = L7 & Ms;
-    wants = ~Ms & valid;
+    wants = ~Ms & valid & ~tail4;
     S.segHM[tid] = 0;
   }
   const int ncand_short = __reduce_add_sync(0xffffffffu, __popc(Ms));   // this warp's candidates so far (warp-uniform)
@@ -277,12 +288,19 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
       int nfound = 0;
       for (int e = from + tid; e < to; e += kThreads) {
         const int i = (int)S.list[e];
-        const uint32_t v = load4(S.data, i);
+        // eight bytes at i and at the candidate from three aligned words each
+        const uint32_t* wi = S.data + (i >> 2);
+        const uint32_t shi = (i & 3) * 8;
+        const uint32_t i0 = wi[0], i1 = wi[1], i2 = wi[2];
+        const uint32_t v = __funnelshift_r(i0, i1, shi);
         const uint32_t c = S.htab[(v * 2654435761u) >> (32 - kHashLog)];
         uint32_t res = kNoCand;
-        if (c < (uint32_t)i && load4(S.data, (int)c) == v) {
+        const uint32_t* wc = S.data + ((c & (kB - 1)) >> 2);
+        const uint32_t shc = (c & 3) * 8;
+        const uint32_t c0 = wc[0], c1 = wc[1];
+        if (c < (uint32_t)i && __funnelshift_r(c0, c1, shc) == v) {
           const int maxlen = min((i & ~(kSub - 1)) + kSub, n - kLz4LastLiterals) - i;
-          const uint32_t x = load4(S.data, i + 4) ^ load4(S.data, (int)c + 4);
+          const uint32_t x = __funnelshift_r(i1, i2, shi) ^ __funnelshift_r(c1, wc[2], shc);
           int len = 4 + (x ? ((__ffs(x) - 1) >> 3) : 4);
           if (len > maxlen) len = maxlen;
           // 4-byte matches save one byte and cost a sequence on both ends of the codec: dropping them keeps the

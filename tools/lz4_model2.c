@@ -9,6 +9,9 @@
  *   RH=8 RLOG=10 PROBES=16 for blocks that list <= 4096 positions, RH=10 RLOG=12 PROBES=4 for the others: 4.9x fewer far
  *   matches than FIRST=1, decode of cfg2 6.27 -> 5.92 ms, but the probe loops cost the encoder 7.44 -> 8.07 ms: rejected,
  *   FIRST=1 is the shipped policy),
+ *   NOINTERIOR=1 NIQ=n KEEPTAIL=k (positions inside a run of the first n offsets do not look up unless fewer than k bytes
+ *   of the run lie ahead: NIQ=1 KEEPTAIL=3 is shipped — the position with exactly four run bytes ahead — 12 % fewer lookups
+ *   on background-removed planes at the same size; KEEPTAIL=2 / 1 / 0: -26 / -39 / -51 % lookups for +0.5 / 1.3 / 2.2 % size),
  *   FARMIN=n NEAR=n (minimum length of matches further than NEAR bytes away); prints the number of far matches
  *   (distance > 1472 = what the decoder's output ring does not hold) in front of the result line */
 #include <stdint.h>
@@ -27,7 +30,7 @@ int main(int argc, char** argv) {
   int offs[16], noff = 0;
   for (char* t = strtok(argv[6], ","); t && noff < 16; t = strtok(NULL, ",")) offs[noff++] = atoi(t);
   int hashlog = getenv("HLOG") ? atoi(getenv("HLOG")) : 12; int listmax = getenv("LISTMAX") ? atoi(getenv("LISTMAX")) : 1<<30; int round = getenv("ROUND") ? atoi(getenv("ROUND")) : 512;
-  long nfar = 0, early_lost = 0, nearly = 0; long out = 0, nseq = 0, nconst = 0, nstored = 0, lookups = 0, by_off[17] = {0}, bytes_off[17] = {0};
+  long nskip = 0; long nfar = 0, early_lost = 0, nearly = 0; long out = 0, nseq = 0, nconst = 0, nstored = 0, lookups = 0, by_off[17] = {0}, bytes_off[17] = {0};
   int* cand = malloc(sizeof(int) * (block + 16));
   int* tab = malloc(sizeof(int) << hashlog);
   for (long o = 0; o < total; o += block) {
@@ -81,6 +84,17 @@ int main(int argc, char** argv) {
           if (i < dd) continue;
           while (l < minmatch && i + l < lim && d[i + l] == d[i + l - dd]) l++;
           if (l >= minmatch) cand[i] = i - dd;
+        }
+        if (cand[i] < 0 && use_hash && getenv("NOINTERIOR")) {
+          /* interior of a fixed-offset run of >= 5: some q with d[i]==d[i-dd] and the run containing i has length >= 5 */
+          int interior = 0;
+          for (int q = 0; q < (getenv("NIQ") ? atoi(getenv("NIQ")) : noff) && !interior; ++q) {
+            int dd = offs[q]; if (i < dd || d[i] != d[i - dd]) continue;
+            int a = i; int sub_lo = (i / cut) * cut; while (a - 1 >= dd && a - 1 >= sub_lo && d[a - 1] == d[a - 1 - dd]) a--;
+            int b2 = i; int cut_hi2 = ((i / cut) + 1) * cut, lim2 = n - 5 < cut_hi2 ? n - 5 : cut_hi2; while (b2 + 1 < lim2 && d[b2 + 1] == d[b2 + 1 - dd]) b2++;
+            if (b2 - a + 1 >= 5 && a < i) { int keep = getenv("KEEPTAIL") ? atoi(getenv("KEEPTAIL")) : 0; /* b2 = last position of the run */ if (b2 - i >= keep) interior = 1; }
+          }
+          if (interior) { nskip++; continue; }
         }
         if (cand[i] < 0 && use_hash && (sub ? !(i & 1) : listed++ < listmax)) {
           uint32_t v = ld4(d + i), h = (v * 2654435761u) >> (32 - hashlog);
@@ -145,6 +159,7 @@ int main(int argc, char** argv) {
     if (bo >= n) { bo = n; nstored++; }
     out += 4 + bo;
   }
+  printf("interior skipped %.1f%%  ", 100.0 * nskip / total);
   printf("far matches %ld  early-stored %ld (lost %ld B)  ", nfar, nearly, early_lost);
   printf("%s block=%d cut=%d hash=%d min=%d: %ld -> %ld ratio %.3f seqs %ld const %ld stored %ld lookups %.1f%%\n", argv[1], block, cut, use_hash, minmatch,
          total, out, (double)total / out, nseq, nconst, nstored, 100.0 * lookups / total);
