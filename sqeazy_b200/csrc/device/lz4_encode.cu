@@ -384,13 +384,25 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
     while (true) {                     // cascade rounds
       if (need) {
         // thread-serial parse: bit operations, the masks and (for hash matches) a few words of the block
+        // (a repair parse — the entry point moved — runs only until it meets a match the parse before it had selected: from
+        //  there on everything is what it was, lengths included)
+        const uint32_t oldSel = Sel;
+        const unsigned long long oldLens = lens;
         int pos = entry, nlong = 0;
+        bool spliced = false;
         Sel = 0;
         lens = 0;
         while (pos < 32) {
           const uint32_t mm = M & (0xffffffffu << pos);
           if (!mm) break;
           const int j = __ffs(mm) - 1;
+          if ((oldSel >> j) & 1u) {
+            const int dropped = __popc(oldSel & C0 & C1 & ((1u << j) - 1u));   // long matches of the old parse in front of j
+            Sel |= oldSel & (0xffffffffu << j);
+            lens |= (oldLens >> (11 * dropped)) << (11 * nlong);
+            spliced = true;
+            break;
+          }
           const int i = seg_lo + j, maxlen = limit - i;
           int code, len;
           if ((Ms >> j) & 1u) {
@@ -429,7 +441,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
           Sel |= 1u << j;
           pos = j + len;
         }
-        exit_abs = seg_lo + (pos > 32 ? pos : 32);
+        if (!spliced) exit_abs = seg_lo + (pos > 32 ? pos : 32);
       }
       int incl = exit_abs;
 #pragma unroll
