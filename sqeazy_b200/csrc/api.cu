@@ -215,7 +215,12 @@ uint32_t lz4_pitch_hint(const Pipeline& pl, const std::vector<uint64_t>& shape) 
     const uint64_t bits = X * (uint64_t)pl.head.back().w;                                                 // bits of one row in one plane
     if (bits % 8 == 0) pitch = bits / 8;
   } else if (pl.sink.kind == StageKind::Lz4 && pl.head.empty()) pitch = X * (uint64_t)pl.elem;           // raw voxels
-  return pitch <= 8192 ? (uint32_t)pitch : 0u;
+  uint32_t hint = pitch <= 8192 ? (uint32_t)pitch : 0u;
+  // bit planes behind a background removal hold no noise planes: every warp of the encoder starts at once (kernels.h)
+  if (pl.sink.kind == StageKind::Lz4)
+    for (const Stage& s : pl.head)
+      if (s.kind == StageKind::RemoveBackground || s.kind == StageKind::RmEstBkrd) hint |= kLz4HintNoNoise;
+  return hint;
 }
 
 uint64_t shape_product(const std::vector<uint64_t>& shape) {
@@ -1171,7 +1176,10 @@ int sqyx_lz4_encode_ex(const void* d_src, long nbytes, void* d_dst, long dst_cap
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   void* ws = nullptr;
   if (A->get(kSlotWs, k_lz4_encode_workspace_bytes((uint64_t)nbytes), &ws)) return 1;
-  CKK(k_lz4_encode(static_cast<const uint8_t*>(d_src), (uint64_t)nbytes, static_cast<uint8_t*>(d_dst), ws, pitch_bytes > 0 && pitch_bytes <= 8192 ? (uint32_t)pitch_bytes : 0u, st));
+  // (pitch_bytes may carry kLz4HintNoNoise, kernels.h)
+  const long pitch = pitch_bytes & ~(long)kLz4HintNoNoise;
+  const uint32_t hint = (pitch > 0 && pitch <= 8192 ? (uint32_t)pitch : 0u) | (uint32_t)(pitch_bytes & (long)kLz4HintNoNoise);
+  CKK(k_lz4_encode(static_cast<const uint8_t*>(d_src), (uint64_t)nbytes, static_cast<uint8_t*>(d_dst), ws, hint, st));
   unsigned long long hres[4] = {0, 0, 0, 0};
   CK(cudaMemcpyAsync(hres, ws, 32, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

@@ -55,6 +55,11 @@ size_t k_lz4_encode_workspace_bytes(uint64_t raw_bytes);
 // pitch_bytes: distance in the stream between vertically adjacent voxels (a row of a bit plane: X * w / 8 bytes; a row of
 // 8-bit codes: X bytes), tried as a match offset like the short offsets 1..4; 0 (or not a multiple of 32): none. The
 // compressed bytes are a pure function of (input bytes, pitch_bytes).
+// kLz4HintNoNoise OR-ed into pitch_bytes: the caller expects no incompressible blocks (bit planes behind a background
+// removal). It changes only the order of work inside a block — without it twelve of a block's sixteen warps wait until four
+// sampled ones have settled whether the block is noise and is stored as it is, which is what makes noise cheap (8-bit
+// quantiser codes, the low planes of an unfiltered stack) and costs a compressible block a few per cent — never a byte.
+constexpr uint32_t kLz4HintNoNoise = 0x80000000u;
 int k_lz4_encode(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, void* workspace, uint32_t pitch_bytes, cudaStream_t st);
 // the same in three steps, for input that becomes available piece by piece: begin (frame prefix), any number of block
 // sets — `nsets` sets of `count` consecutive 16 KiB blocks, set j starting at block first + j * set_stride (the pieces of

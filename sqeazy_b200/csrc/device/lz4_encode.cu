@@ -72,7 +72,6 @@ struct __align__(16) EncSmem {
   uint32_t E[kNumOff][kSegs + 4];        // E[q][t] bit j: data[32t+j] == data[32t+j-off(q)]; phases C, D: the sequences' offsets (uint16)
   uint32_t segHM[kSegs];                 // per segment: positions with a hash candidate (>= 5 bytes)
   uint32_t full[kNumOff][kWarps];        // per warp: segments whose E[q] word is all ones
-  int wave_start[kWarps + 1];            // list index of every sub-block's first entry
   int w_size[kWarps], w_off[kWarps];     // per-warp totals of the scans
   int total;
   int nlong;                             // phase D: queued long literal runs
@@ -139,6 +138,7 @@ __device__ __forceinline__ int run_ones(const EncSmem& S, int q, int x) {
 // blocks — 56 % of a background-removed stack, bound by bytes in flight — then keeps the short prologue and the register
 // allocation of a kernel that does nothing else. Returns the encoded size; `stored` when the block does not shrink.
 // pitch_words: row pitch of the stack in this stream in 32-bit words (a multiple of 8), 0 = none.
+template <bool kWait>
 __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pitch_words, bool& stored_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint8_t* data8 = reinterpret_cast<uint8_t*>(S.data);
@@ -156,127 +156,132 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
   // at i with offset off(q) is then simply L consecutive ones in E_q starting at bit i — found, measured and extended
   // with shifts, ANDs and ffs on registers, never touching the bytes again.
   const int seg_lo = tid * 32;
-  {
-    uint32_t W[9];
-    W[0] = tid > 0 ? S.data[8 * tid - 1] : 0u;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) W[k + 1] = S.data[8 * tid + k];
-    const int lim = n - kLz4LastLiterals - seg_lo;     // match bytes never touch the last 5 bytes of the block
-    const uint32_t tailmask = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : (1u << lim) - 1u);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int d = q == 0 ? 1 : (q == 1 ? 2 : (q == 2 ? 4 : 3));
-      uint32_t e = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t prev = d == 4 ? W[k] : __funnelshift_r(W[k], W[k + 1], 32 - 8 * d);   // bytes 4k-d .. 4k-d+3
-        e = eq4_shift_in(e, W[k + 1], prev);
-      }
-      if (tid == 0) e &= ~((1u << d) - 1u);            // no source in front of the block
-      S.E[q][tid] = e & tailmask;
-    }
-    {
-      uint32_t e = 0;
-      if (pitch_words > 0 && 8 * tid >= pitch_words) {   // (whole segments: the pitch is a multiple of 32 bytes)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          e = eq4_shift_in(e, W[k + 1], S.data[8 * tid + k - pitch_words]);
-        }
-      }
-      S.E[4][tid] = e & tailmask;
-    }
-    if (tid < kNumOff) S.E[tid][kSegs] = 0;
-  }
-  __syncthreads();
-
-  // ---------------- phase A1: fixed-offset candidates of this thread's segment (registers only) ----------------
   uint32_t Ms = 0, D0 = 0, D1 = 0, D2 = 0, C0 = 0, C1 = 0;   // candidate mask, offset index planes, length code planes
   uint32_t wants = 0;                                        // positions that look up the hash table
-  {
-    uint32_t L6 = 0, L7 = 0, L8 = 0;
-    uint32_t tail4 = 0;                                  // positions inside a byte run with exactly four equal bytes ahead
-#pragma unroll
-    for (int q = 0; q < kNumOff; ++q) {
-      // matches never cross the warp's 1 KiB sub-block: the last segment sees no successor
-      const uint32_t own = S.E[q][tid];
-      const unsigned long long e = (unsigned long long)own | ((unsigned long long)(lane == 31 ? 0u : S.E[q][tid + 1]) << 32);
-      const unsigned long long r5 = e & (e >> 1) & (e >> 2) & (e >> 3) & (e >> 4);
-      const unsigned long long r6 = r5 & (e >> 5), r7 = r6 & (e >> 6), r8 = r7 & (e >> 7);
-      if (q == 0) {
-        // Inside a run of equal bytes, the position with exactly four of them ahead never pays for a lookup: a match from
-        // there would have to carry the run's last four bytes AND what follows it, and the parse only lands there when a
-        // hash match ends on that very byte (tools/lz4_model2.c NOINTERIOR=1 NIQ=1 KEEPTAIL=3: 12 % fewer lookups on
-        // background-removed planes — the phase that dominates their sparse planes — at the same size; the three positions
-        // behind it are worth 0.5 % of the size each and keep looking up)
-        const uint32_t r4only = (uint32_t)(e & (e >> 1) & (e >> 2) & (e >> 3) & ~r5);
-        const uint32_t before = (own << 1) | (lane ? S.E[0][tid - 1] >> 31 : 0u);   // the byte in front continues the run too
-        tail4 = r4only & before;
+  // Phases A0 and A1 of a warp's 1 KiB sub-block depend on nothing another warp computes (masks and candidates of a segment
+  // look one segment ahead and one back, inside the sub-block), so a warp runs them on its own — which lets four SAMPLED
+  // warps settle first whether the block is noise (early store, below) before the other twelve spend anything on it.
+  auto analyse = [&]() {
+    {
+      uint32_t W[9];
+      W[0] = tid > 0 ? S.data[8 * tid - 1] : 0u;
+  #pragma unroll
+      for (int k = 0; k < 8; ++k) W[k + 1] = S.data[8 * tid + k];
+      const int lim = n - kLz4LastLiterals - seg_lo;     // match bytes never touch the last 5 bytes of the block
+      const uint32_t tailmask = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : (1u << lim) - 1u);
+  #pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int d = q == 0 ? 1 : (q == 1 ? 2 : (q == 2 ? 4 : 3));
+        uint32_t e = 0;
+  #pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t prev = d == 4 ? W[k] : __funnelshift_r(W[k], W[k + 1], 32 - 8 * d);   // bytes 4k-d .. 4k-d+3
+          e = eq4_shift_in(e, W[k + 1], prev);
+        }
+        if (tid == 0) e &= ~((1u << d) - 1u);            // no source in front of the block
+        S.E[q][tid] = e & tailmask;
       }
-      const uint32_t sel = (uint32_t)r5 & ~Ms;         // at least 5 bytes and no better-ranked offset yet
-      Ms |= sel;
-      L6 |= sel & (uint32_t)r6;
-      L7 |= sel & (uint32_t)r7;
-      L8 |= sel & (uint32_t)r8;
-      if (q & 1) D0 |= sel;
-      if (q & 2) D1 |= sel;
-      if (q & 4) D2 |= sel;
-      const uint32_t fullset = __ballot_sync(0xffffffffu, own == 0xffffffffu);
-      if (lane == 0) S.full[q][warp] = fullset;
+      {
+        uint32_t e = 0;
+        if (pitch_words > 0 && 8 * tid >= pitch_words) {   // (whole segments: the pitch is a multiple of 32 bytes)
+  #pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            e = eq4_shift_in(e, W[k + 1], S.data[8 * tid + k - pitch_words]);
+          }
+        }
+        S.E[4][tid] = e & tailmask;
+      }
+      if (tid < kNumOff) S.E[tid][kSegs] = 0;
     }
-    const int lim = n - kLz4MFLimit + 1 - seg_lo;      // a match starts at most 12 bytes before the block end
-    const uint32_t valid = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : (1u << lim) - 1u);
-    Ms &= valid;
-    C0 = (L6 ^ L7 ^ L8) & Ms;                          // code = number of the planes L6,L7,L8 that are set: 5,6,7,>=8 bytes
-    C1 = L7 & Ms;
-    wants = ~Ms & valid & ~tail4;
-    S.segHM[tid] = 0;
-  }
-  const int ncand_short = __reduce_add_sync(0xffffffffu, __popc(Ms));   // this warp's candidates so far (warp-uniform)
+    __syncwarp();
 
-  // ---------------- phase A2: hash candidates for the positions without a fixed-offset match ----------------
-  // The wanting positions of the block are compacted, in order, into S.list (exclusive scan of the per-thread counts).
-  // Wave w = the entries of sub-block w: all threads look their entries up in a table that holds the listed positions of
-  // the sub-blocks in front (sources inside the sub-block come from the fixed offsets), then insert them with atomicMax —
-  // the last position with a hash wins whatever the thread order. An entry is overwritten by its result.
-  int mybase;
-  {
-    const int cnt = __popc(wants);
-    int incl = cnt;
+    // ---------------- phase A1: fixed-offset candidates of this thread's segment (registers only) ----------------
+    {
+      uint32_t L6 = 0, L7 = 0, L8 = 0;
+      uint32_t tail4 = 0;                                  // positions inside a byte run with exactly four equal bytes ahead
+  #pragma unroll
+      for (int q = 0; q < kNumOff; ++q) {
+        // matches never cross the warp's 1 KiB sub-block: the last segment sees no successor
+        const uint32_t own = S.E[q][tid];
+        const unsigned long long e = (unsigned long long)own | ((unsigned long long)(lane == 31 ? 0u : S.E[q][tid + 1]) << 32);
+        const unsigned long long r5 = e & (e >> 1) & (e >> 2) & (e >> 3) & (e >> 4);
+        const unsigned long long r6 = r5 & (e >> 5), r7 = r6 & (e >> 6), r8 = r7 & (e >> 7);
+        if (q == 0) {
+          // Inside a run of equal bytes, the position with exactly four of them ahead never pays for a lookup: a match from
+          // there would have to carry the run's last four bytes AND what follows it, and the parse only lands there when a
+          // hash match ends on that very byte (tools/lz4_model2.c NOINTERIOR=1 NIQ=1 KEEPTAIL=3: 12 % fewer lookups on
+          // background-removed planes — the phase that dominates their sparse planes — at the same size; the three positions
+          // behind it are worth 0.5 % of the size each and keep looking up)
+          const uint32_t r4only = (uint32_t)(e & (e >> 1) & (e >> 2) & (e >> 3) & ~r5);
+          const uint32_t before = (own << 1) | (lane ? S.E[0][tid - 1] >> 31 : 0u);   // the byte in front continues the run too
+          tail4 = r4only & before;
+        }
+        const uint32_t sel = (uint32_t)r5 & ~Ms;         // at least 5 bytes and no better-ranked offset yet
+        Ms |= sel;
+        L6 |= sel & (uint32_t)r6;
+        L7 |= sel & (uint32_t)r7;
+        L8 |= sel & (uint32_t)r8;
+        if (q & 1) D0 |= sel;
+        if (q & 2) D1 |= sel;
+        if (q & 4) D2 |= sel;
+        const uint32_t fullset = __ballot_sync(0xffffffffu, own == 0xffffffffu);
+        if (lane == 0) S.full[q][warp] = fullset;
+      }
+      const int lim = n - kLz4MFLimit + 1 - seg_lo;      // a match starts at most 12 bytes before the block end
+      const uint32_t valid = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : (1u << lim) - 1u);
+      Ms &= valid;
+      C0 = (L6 ^ L7 ^ L8) & Ms;                          // code = number of the planes L6,L7,L8 that are set: 5,6,7,>=8 bytes
+      C1 = L7 & Ms;
+      wants = ~Ms & valid & ~tail4;
+      S.segHM[tid] = 0;
+    }
+  };
+  // Four warps analyse their sub-blocks first: 0 and 1 (the first 2 KiB: what the hash test below looks at), 6 and 11.
+  const bool sampled = warp < kEarlyBytes / kSub || warp == 6 || warp == 11;
+  // kWait: the other twelve wait for the verdict; otherwise (kLz4HintNoNoise) all sixteen analyse at once. Which warps
+  // analyse first never reaches the output: the early-store test reads the sampled warps only.
+  const bool eager = kWait ? sampled : true;
+  int cnt = 0, incl = 0;               // positions of this segment that look up; inclusive scan over the warp
+  auto count_wants = [&]() {
+    cnt = __popc(wants);
+    incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += t;
     }
     if (lane == 31) S.w_size[warp] = incl;
-    // (the barrier carries the one bit the early-store test needs first: a warp that is already rich in fixed-offset
-    //  candidates — every compressible bit-plane block — settles it for the CTA at no cost)
-    const int rich = __syncthreads_or(ncand_short >= kEarlyMin);
-    int wbase, wall;
-    warp_totals(S.w_size, warp, lane, wbase, wall);
-    mybase = wbase + incl - cnt;
-    if (lane == 0) S.wave_start[warp] = wbase;
-    if (tid == 0) S.wave_start[kWarps] = wall;
-    auto write_list = [&]() {
+  };
+  if (eager) {
+    analyse();
+    count_wants();
+  }
+  const int ncand_short = sampled ? __reduce_add_sync(0xffffffffu, __popc(Ms)) : 0;   // (warp-uniform)
+  // One barrier, two answers. Lanes 0..15 of a warp vote "rich": a sampled warp that is already rich in fixed-offset
+  // candidates — every compressible bit-plane block — settles the early-store test for the CTA. Lane 16 votes "this warp has
+  // not analysed its sub-block yet" (at most twelve such votes).
+  const int votes = __syncthreads_count(lane < 16 ? ncand_short >= kEarlyMin : (lane == 16 && !eager));
+  const bool rich = votes >= 16, all_eager = (votes & 15) == 0;
+  const bool test_early = !rich && n > kEarlyBytes;
+
+  // ---------------- phase A2: hash candidates for the positions without a fixed-offset match ----------------
+  // The wanting positions of the block are compacted, in order, into S.list (exclusive scan of the per-thread counts), all
+  // of them are inserted into one hash table, then all of them are looked up. An entry is overwritten by its result.
+  int mybase;
+  {
+    auto write_list = [&](int base) {
       uint32_t m = wants;
-      int e = mybase;
+      int e = base;
       while (m && e < kListMax) {
         const int j = __ffs(m) - 1;
         m &= m - 1;
         S.list[e++] = (uint16_t)(seg_lo + j);
       }
     };
-    // a block that may turn out to be noise lists its first 2 KiB only before that is known (in noise every position
-    // wants a lookup: 32 stores per thread)
-    const bool test_early = !rich && n > kEarlyBytes;
-    if (!test_early || tid < kEarlyBytes / 32) write_list();
-    if (test_early && lane == 0 && ncand_short) atomicAdd(&S.early, ncand_short);
-    __syncthreads();
-
     // The table keeps the FIRST listed position of the block per hash (atomicMin: the same whatever the thread order),
     // filled before anything is looked up: a position finds the earliest occurrence of its four bytes — in its own
     // sub-block as well — and the whole phase is two sweeps over the list with all 512 threads instead of a wave per
     // sub-block (16 x 2 barriers, most threads idle). tools/lz4_model2.c (FIRST=1): ratio +0.1..0.5 % over the waves.
-    const int total = min(S.wave_start[kWarps], kListMax);
     auto insert = [&](int from, int to) {
       for (int e = from + tid; e < to; e += kThreads) {
         const int i = (int)S.list[e];
@@ -316,15 +321,20 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
       }
       return nfound;
     };
-    // Early store: a block whose candidates (fixed-offset ones of the whole block + hash candidates of the first 2 KiB)
-    // are fewer than one per 32 sampled bytes is noise — camera-noise bit planes, 8-bit quantiser codes — and would
-    // shrink by < 3 % (tools/lz4_model.c: such blocks have < 70 candidates and end at 0.97..1.00 of their size, everything
-    // that compresses to <= 0.82 has > 600). It is stored without the rest of the list, the parse and the emission,
-    // which is also what makes its decode a plain copy. (Positions of the first 2 KiB find the same sources in a table
-    // that holds the first 2 KiB only as in the full one: a first occurrence lies in front of them.)
+    // Early store: a block with fewer than kEarlyMin candidates — four times the fixed-offset ones of the sampled 4 KiB + the
+    // hash ones of the first 2 KiB — is noise (camera-noise bit planes, 8-bit quantiser codes) and would shrink by < 3 %
+    // (tools/lz4_model2.c EARLY=2048 SAMPLED=1 DUMP=1: noise blocks count <= 29, every compressible block of the sample sets
+    // >= 243; the sampled count decides like the full one on all of them). It is stored without the masks of the other
+    // twelve sub-blocks, the list, the parse and the emission, which is also what makes its decode a plain copy.
+    // (Positions of the first 2 KiB find the same sources in a table that holds the first 2 KiB only as in the full one: a
+    //  first occurrence lies in front of them; their list indices are final as well: the list is in position order.)
     int done = 0;
     if (test_early) {
-      done = min(S.wave_start[kEarlyBytes / kSub], kListMax);
+      if (lane == 0 && ncand_short) atomicAdd(&S.early, 4 * ncand_short);
+      static_assert(kEarlyBytes / kSub == 2, "bases of the early list: two warps");
+      if (warp < 2) write_list((warp ? S.w_size[0] : 0) + incl - cnt);
+      done = min(S.w_size[0] + S.w_size[1], kListMax);
+      __syncthreads();
       insert(0, done);
       __syncthreads();
       const int nf = __reduce_add_sync(0xffffffffu, lookup(0, done));
@@ -334,15 +344,29 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
         stored_out = true;
         return 0;
       }
-      if (tid >= kEarlyBytes / 32) write_list();
+    }
+    if (!all_eager) {
+      if (!eager) {
+        analyse();
+        count_wants();
+      }
       __syncthreads();
     }
-    insert(done, total);
-    __syncthreads();
-    lookup(done, total);
-    __syncthreads();
+    {
+      int wbase, wall;
+      warp_totals(S.w_size, warp, lane, wbase, wall);
+      mybase = wbase + incl - cnt;
+      if (!test_early || warp >= kEarlyBytes / kSub) write_list(mybase);
+      const int total = min(wall, kListMax);
+      __syncthreads();
+      insert(done, total);
+      __syncthreads();
+      lookup(done, total);
+      __syncthreads();
+    }
   }
   // ones at the start of every segment and beyond, for run_ones (htab is free now)
+  int entry0 = 0;
   {
 #pragma unroll
     for (int q = 0; q < kNumOff; ++q) {
@@ -353,6 +377,9 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
       const int tail = __shfl_sync(0xffffffffu, lead, (lane + k) & 31);   // leading ones of the first segment that is not full
       S.lead[q][tid] = lane ? (uint16_t)(32 * k + (lane + k < 32 ? tail : 0)) : (uint16_t)0;
       if (tid == 0) S.lead[q][kSegs] = 0;
+      // first guess of where the parse enters this segment (phase B), from the same words
+      const uint32_t prevtop = __shfl_up_sync(0xffffffffu, own >> 27, 1);
+      if (lane > 0 && prevtop == 31u) entry0 = max(entry0, lead);
     }
   }
   const uint32_t HM = S.segHM[tid];
@@ -372,14 +399,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
     // (its last five bytes continue one), the match that covers them runs on to the end of the ones of E_d here. A
     // segment in the middle of a long run then has nothing to parse, and half of the repair parses of the cascade
     // disappear. A wrong guess is corrected like any other moved entry point.
-    int entry = 0, exit_abs = seg_lo + 32;
-    if (lane > 0) {
-#pragma unroll
-      for (int q = 0; q < kNumOff; ++q) {
-        const uint32_t prevE = S.E[q][tid - 1], curE = S.E[q][tid];
-        if ((prevE >> 27) == 31u) entry = max(entry, curE == 0xffffffffu ? 32 : __ffs(~curE) - 1);
-      }
-    }
+    int entry = entry0, exit_abs = seg_lo + 32;
     bool need = true;
     while (true) {                     // cascade rounds
       if (need) {
@@ -583,6 +603,8 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
   return csize;
 }
 
+// kWait: see encode_general (the launch's kLz4HintNoNoise flag cleared)
+template <bool kWait>
 __global__ void __launch_bounds__(kThreads, 3)
 lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* __restrict__ dst, uint32_t nblocks,
                   uint8_t* __restrict__ staging, uint32_t* __restrict__ stats, uint32_t first, uint32_t set_stride, int pitch_words) {
@@ -663,7 +685,7 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
     __syncthreads();
     csize = S.total;
   } else {
-    csize = encode_general(S, n, pitch_words, stored);
+    csize = encode_general<kWait>(S, n, pitch_words, stored);
     if (stored) { csize = n; kind = 2; }
   }
   __syncthreads();
@@ -898,9 +920,15 @@ int k_lz4_encode_blocks(const uint8_t* src, uint64_t raw_bytes, uint8_t* dst, vo
   if (int e = enc_ws(raw_bytes, workspace, W)) return e;
   if (!count || !nsets) return 0;
   if (nsets > 65535u || (uint64_t)first + (uint64_t)(nsets - 1) * set_stride + count > W.nblocks) return -2;
-  SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
-  lz4_encode_kernel<<<dim3(count, nsets), kThreads, sizeof(EncSmem), st>>>(src, raw_bytes, dst, W.nblocks, W.staging, W.stats, first,
-                                                                            set_stride, pitch_words_of(pitch_bytes));
+  const dim3 grid(count, nsets);
+  const int pw = pitch_words_of(pitch_bytes & ~kLz4HintNoNoise);
+  if (pitch_bytes & kLz4HintNoNoise) {
+    SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
+    lz4_encode_kernel<false><<<grid, kThreads, sizeof(EncSmem), st>>>(src, raw_bytes, dst, W.nblocks, W.staging, W.stats, first, set_stride, pw);
+  } else {
+    SQYB_CUDA_OK(cudaFuncSetAttribute(lz4_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
+    lz4_encode_kernel<true><<<grid, kThreads, sizeof(EncSmem), st>>>(src, raw_bytes, dst, W.nblocks, W.staging, W.stats, first, set_stride, pw);
+  }
   SQYB_COUNT_LAUNCH(1);
   return (int)cudaGetLastError();
 }

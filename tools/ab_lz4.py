@@ -35,6 +35,7 @@ for name, x in inputs.items():
             def run():
                 if hasattr(L, "sqyx_lz4_encode_ex"):
                     pitch = 2048 if name == "quantiser codes" else 256
+                    if name in ("cfg2 planes", "zeros") and not os.environ.get("AB_NO_HINT"): pitch |= 0x80000000   # what rmestbkrd->bitswap1->lz4 passes
                     rc = L.sqyx_lz4_encode_ex(c_void_p(x.data_ptr()), c_long(x.numel()), c_void_p(outbuf.data_ptr()), c_long(outbuf.numel()), ctypes.byref(n), c_long(pitch), st)
                 else:
                     rc = L.sqyx_lz4_encode(c_void_p(x.data_ptr()), c_long(x.numel()), c_void_p(outbuf.data_ptr()), c_long(outbuf.numel()), ctypes.byref(n), st)

@@ -65,7 +65,7 @@ for ln in sorted(per_line):
 # ranges
 if len(sys.argv) > 3:
     import bisect
-    marks = [(1, "prologue"), (94, "A0 masks"), (123, "A1 short cand"), (157, "A2 hash rounds"), (225, "B parse"), (351, "C sizes"), (439, "D emit"), (491, "kernel: load"), (548, "closed form"), (577, "hand-off"), (595, "other")]
+    marks = [(1, "helpers"), (84, "ext_bytes"), (90, "load4"), (95, "eq4_shift_in (A0)"), (106, "warp_totals"), (120, "put_ext"), (128, "run_ones (B)"), (138, "prologue"), (153, "A0 masks"), (192, "A1 short cand"), (236, "A2 list+hash"), (345, "lead table"), (360, "B parse"), (460, "C compaction"), (507, "D sizes"), (540, "D emit"), (586, "kernel: load"), (637, "closed form"), (669, "hand-off"), (689, "other")]
     agg = collections.defaultdict(lambda: [0.0, 0.0])
     for ln, v in per_line.items():
         k = bisect.bisect_right([m[0] for m in marks], ln) - 1
