@@ -375,6 +375,11 @@ constexpr uint64_t kSmallStreamBytes = uint64_t(128) << 20;   // streams up to t
 constexpr uint32_t kLitOwn = 4;          // literals an owner lane copies itself
 constexpr uint32_t kBatchOut = 512;       // output bytes a batch of sequences may produce before the next flush
 constexpr uint32_t kNear = kWin - kBatchOut - 64;
+constexpr int kFarW = 8;                  // lanes that copy one short far match of a batch (four matches at a time) ...
+constexpr uint32_t kFarMax = 24;          // ... of up to this many bytes; longer ones take the whole warp
+                                          // (measured, cfg2 / plain planes / cfg1 decode in ms: off 5.81 / 6.60 / 0.76; 8 lanes, any length
+                                          //  5.81 / 5.55 / 0.60; 8 lanes, <= 16 / 24 / 32 bytes 5.39 / 5.37 / 5.40 (plain 5.49, cfg1 0.61);
+                                          //  16 lanes, <= 32: 5.38 / 5.76 / 0.66; 4 lanes: 6.23; the three steps' loads issued before the stores: 5.38 / 5.62 / 0.60)
 
 __device__ __forceinline__ uint4 load_stream_piece(const uint8_t* addr, const uint8_t* sbeg, const uint8_t* send) {
   if (addr >= sbeg && addr + 16 <= send) return __ldg(reinterpret_cast<const uint4*>(addr));
@@ -630,6 +635,40 @@ __device__ __forceinline__ uint32_t decode_block_window(const uint8_t* __restric
       // matches, in stream order (= lane order of the owners). Inside a batch no flush is needed and a match has at
       // most 273 bytes, so the near copies are plain loops over the output ring.
       uint32_t todo = last ? owners & ~(1u << hi) : owners;   // the block's final sequence has no match
+      // Far matches first, four at a time: their sources (more than kNear bytes back, inside this block) were flushed before
+      // this batch began, so they depend on nothing the batch writes and on no order among themselves — while a near match
+      // behind them may read what they produce. A group of eight lanes copies one of them (most have 5..16 bytes: one or two
+      // steps), where the loop below spends a whole warp and ~40 instructions on each. An encoder that points at the FIRST
+      // occurrence of a pattern (lz4_encode.cu) makes these the majority of the matches of a sparse bit plane.
+      {
+        const bool is_far = ((todo >> lane) & 1u) && my_off > kNear && my_off <= my_mo && my_mlen <= kFarMax;
+        uint32_t far = __ballot_sync(0xffffffffu, is_far);
+        todo &= ~far;
+        const int g = lane / kFarW;
+        const uint32_t l8 = (uint32_t)lane % kFarW;
+        while (far) {
+          int sel = -1;
+#pragma unroll
+          for (int t = 0; t < 32 / kFarW; ++t) {
+            const int i = __ffs(far) - 1;          // (-1 when the batch has no further far match)
+            if (t == g) sel = i;
+            far &= far - 1u;
+          }
+          const uint32_t mw = __shfl_sync(0xffffffffu, my_match, sel & 31), mo = __shfl_sync(0xffffffffu, my_mo, sel & 31);
+          if (sel >= 0) {
+            const uint32_t offset = mw & 0xffffu, mlen = mw >> 16;
+            const uint8_t* from = O.d + (mo - offset);
+            if (O.line_aligned) {
+#pragma unroll 1
+              for (uint32_t k = l8; k < mlen; k += kFarW) SQYB_W(mo + k) = ld_l1_u8(from + k);
+            } else {
+#pragma unroll 1
+              for (uint32_t k = l8; k < mlen; k += kFarW) SQYB_W(mo + k) = __ldcg(from + k);
+            }
+          }
+        }
+        __syncwarp();
+      }
       while (todo) {
         const int i = __ffs(todo) - 1;
         todo &= todo - 1u;

@@ -68,3 +68,23 @@ def test_pitch_hint_changes_bytes_not_voxels(sq, cuda, port):
         sizes[pitch] = int(p.numel())
     assert sizes[100] == sizes[0] and sizes[16384] == sizes[0]
     assert sizes[64] <= sizes[0], sizes     # 512-voxel rows: 64 bytes of a plane
+
+
+def test_no_noise_hint_changes_no_byte(sq, cuda, port):
+    """SQYX_LZ4_HINT_NO_NOISE (include/sqeazy_b200.h) only reorders the work inside a block: with it all sixteen warps
+    analyse at once, without it twelve wait for the early-store verdict of the four sampled ones. Noise, sparse planes and
+    streams that mix both must come out byte for byte the same either way."""
+    NO_NOISE = 0x80000000
+    rng = np.random.default_rng(5)
+    inputs = dict(_inputs(port))
+    inputs["noise"] = (rng.integers(0, 256, 3 << 20, dtype=np.uint8), 0)
+    codes = np.clip(rng.normal(40, 3, 4 << 20), 0, 255).astype(np.uint8)      # 8-bit quantiser codes of a noise floor
+    inputs["narrow noise"] = (codes, 2048)
+    mixed = np.concatenate([inputs["bit planes after rmestbkrd"][0][: 1 << 20], inputs["noise"][0][: (1 << 20) + 777],
+                            np.zeros(50_000, np.uint8), codes[: 1 << 19]])
+    inputs["mixed"] = (mixed, 64)
+    for name, (a, pitch) in inputs.items():
+        d = dev(cuda, a)
+        plain = sq.lz4_encode_device(d, pitch=pitch).cpu().numpy().copy()
+        hinted = sq.lz4_encode_device(d, pitch=pitch | NO_NOISE).cpu().numpy()
+        assert hinted.size == plain.size and np.array_equal(hinted, plain), name

@@ -25,10 +25,18 @@ if len(sys.argv) > 3 and sys.argv[3] == "quant":
     vol = planes
 else:
     sq.bitswap_encode_device(1, vol.view(-1), planes.view(-1), threshold=thr)
+pitch = 0
+if len(sys.argv) > 4:      # one bit plane only (0 = lowest), encoded the way the pipeline does it: row pitch + no-noise hint
+    k = int(sys.argv[4])
+    flat = planes.view(torch.uint8).view(-1)
+    seg = flat.numel() // 16
+    planes = flat[(15 - k) * seg:(16 - k) * seg].contiguous()
+    vol = planes
+    pitch = shape[2] // 8 | (0x80000000 if thr else 0)
 out = torch.empty_like(vol)
 payload = None
 for _ in range(reps):
-    payload = sq.lz4_encode_device(planes)
+    payload = sq.lz4_encode_device(planes, pitch=pitch)
     sq.lz4_decode_device(payload, out)
 torch.cuda.synchronize()
 assert torch.equal(out, planes)

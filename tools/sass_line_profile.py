@@ -65,7 +65,19 @@ for ln in sorted(per_line):
 # ranges
 if len(sys.argv) > 3:
     import bisect
-    marks = [(1, "helpers"), (84, "ext_bytes"), (90, "load4"), (95, "eq4_shift_in (A0)"), (106, "warp_totals"), (120, "put_ext"), (128, "run_ones (B)"), (138, "prologue"), (153, "A0 masks"), (192, "A1 short cand"), (236, "A2 list+hash"), (345, "lead table"), (360, "B parse"), (460, "C compaction"), (507, "D sizes"), (540, "D emit"), (586, "kernel: load"), (637, "closed form"), (669, "hand-off"), (689, "other")]
+    # phase boundaries of lz4_encode.cu, found by their header comments
+    pats = [("ext_bytes", "__device__ __forceinline__ int ext_bytes"), ("load4", "uint32_t load4("), ("eq4_shift_in (A0)", "uint32_t eq4_shift_in("),
+            ("warp_totals", "void warp_totals("), ("put_ext", "int put_ext("), ("run_ones (B)", "int run_ones("), ("prologue", "int encode_general("),
+            ("A0 masks", "auto analyse = "), ("A1 short cand", "phase A1: fixed-offset candidates"), ("sampling + votes", "Four warps analyse their sub-blocks first"),
+            ("A2 list+hash", "phase A2: hash candidates"), ("lead table", "ones at the start of every segment and beyond"), ("B parse", "phase B: every thread parses"),
+            ("C compaction", "phase C: the selected matches"), ("D sizes", "sequences [s0, s1) of this thread"), ("D emit", "phase D: emission"),
+            ("kernel: load", "lz4_encode_kernel(const uint8_t*"), ("closed form", "closed form: 1 literal"), ("hand-off", "hand-off: size word"), ("other", "Compaction (replaces remove_blanks")]
+    marks = [(1, "helpers")]
+    for name, pat in pats:
+        for i, l in enumerate(src):
+            if pat in l:
+                marks.append((i + 1, name)); break
+    marks.sort()
     agg = collections.defaultdict(lambda: [0.0, 0.0])
     for ln, v in per_line.items():
         k = bisect.bisect_right([m[0] for m in marks], ln) - 1
