@@ -101,7 +101,7 @@ int sqyx_lut_decode_UI16(const void* d_codes, void* d_dst, long n, const unsigne
 long sqyx_lz4_bound(long nbytes);
 int sqyx_lz4_encode(const void* d_src, long nbytes, void* d_dst, long dst_capacity, long* payload_bytes, void* stream);
 /* pitch_bytes: distance in the stream between vertically adjacent voxels (a row of a bit plane of 2048-voxel rows: 256),
- * offered to the match finder as a fixed offset beside 1..4; must be a multiple of 32, 0 = none. The pipelines pass
+ * offered to the match finder as a fixed offset beside 1; must be a multiple of 32, 0 = none. The pipelines pass
  * X * w / 8 (bit planes) or X (8-bit codes). Output bytes are a pure function of (input, pitch_bytes).
  * SQYX_LZ4_HINT_NO_NOISE OR-ed into pitch_bytes: the stream is expected to hold no incompressible 16 KiB blocks (bit planes
  * behind a background removal, as the pipelines pass it): a few per cent faster on such streams, slower on noise, and never a

@@ -53,7 +53,7 @@ int k_lut_decode(const uint8_t* in, uint16_t* out, uint64_t n, const uint16_t* l
 size_t k_lz4_encode_workspace_bytes(uint64_t raw_bytes);
 // workspace[0..8) receives the payload size (u64) when the stream has drained; [16,28) block-kind counters
 // pitch_bytes: distance in the stream between vertically adjacent voxels (a row of a bit plane: X * w / 8 bytes; a row of
-// 8-bit codes: X bytes), tried as a match offset like the short offsets 1..4; 0 (or not a multiple of 32): none. The
+// 8-bit codes: X bytes), tried as a fixed match offset like offset 1; 0 (or not a multiple of 32): none. The
 // compressed bytes are a pure function of (input bytes, pitch_bytes).
 // kLz4HintNoNoise OR-ed into pitch_bytes: the caller expects no incompressible blocks (bit planes behind a background
 // removal). It changes only the order of work inside a block — without it twelve of a block's sixteen warps wait until four

@@ -9,9 +9,9 @@
 //
 // Per block (16 KiB of input staged in shared memory by 512 threads):
 //   load    : 128-bit coalesced loads -> smem; all-equal blocks take a closed-form path
-//   phase A0: byte-equality bit masks E_q for five fixed offsets — 1, 2, 4, 3 and the row pitch of the stack in this
-//             stream (a 2048-voxel row of a bit plane is 256 bytes: what differs from the row above is what the
-//             sample scattered differently) — one bit per position, 32 positions per thread
+//   phase A0: byte-equality bit masks E_q for two fixed offsets — 1 and the row pitch of the stack in this stream (a
+//             2048-voxel row of a bit plane is 256 bytes: what differs from the row above is what the sample scattered
+//             differently) — one bit per position, 32 positions per thread
 //   phase A1: fixed-offset candidates (>= 5 equal bytes) and their 2-bit length codes by shifts / ANDs on the masks
 //   phase A2: the positions without such a candidate (a few per cent of a sparse plane) are COMPACTED into a list and
 //             looked up in ONE shared-memory hash table that holds the FIRST listed position of the block per hash:
@@ -45,7 +45,14 @@ constexpr int kSegs = kB / 32;           // 32-byte segments, one per thread
 constexpr int kPad = 256;
 constexpr int kHashLog = 12;
 constexpr int kInf = 0x7FFFFFFF;
-constexpr int kNumOff = 5;               // fixed offsets, in priority order: 1, 2, 4, 3, pitch
+constexpr int kNumShort = 1;             // short fixed offsets, in priority order out of 1, 2, 4, 3 ...
+constexpr int kNumOff = kNumShort + 1;   // ... and the row pitch. Offsets 2, 4 and 3 were tried as well until the hash table
+                                         // held the first occurrences of the whole block: since then a periodic pattern finds
+                                         // itself there, and on every stream of tools/lz4_model2.c's sample (bit, 2-bit, nibble
+                                         // and byte planes with and without background removal, raw and diff'ed voxels, 8-bit
+                                         // stacks) the three change the size by < 0.1 % either way — for 13 % of the kernel's time
+                                         // (cfg2 planes 6.04 -> 5.26 ms at -0.08 % payload, plain planes 6.23 -> 5.83 ms at +0.02 %)
+__host__ __device__ constexpr int short_offset(int q) { return q == 0 ? 1 : (q == 1 ? 2 : (q == 2 ? 4 : 3)); }
 constexpr int kListMax = 15104;          // positions that may look up the hash table (more: the rest goes without; sized so that
                                          // three CTAs still fit an SM — only all-noise blocks list more, and those are stored)
 constexpr int kEarlyBytes = 2048;        // early-store test on the hash candidates of the first 2 KiB (tools/lz4_model2.c EARLY=: 4096, 2048 and 1024 decide alike) ...
@@ -69,7 +76,8 @@ struct __align__(16) EncSmem {
                                          // most; 0 for the first segment of a sub-block (what a run of the sub-block in front continues with)
                                          // phases C, D: the block's sequences, position | length << 14
   };
-  uint32_t E[kNumOff][kSegs + 4];        // E[q][t] bit j: data[32t+j] == data[32t+j-off(q)]; phases C, D: the sequences' offsets (uint16)
+  uint32_t E[kNumOff < 4 ? 4 : kNumOff][kSegs + 4];   // (four rows at least: the phases C, D use)
+                                         // E[q][t] bit j: data[32t+j] == data[32t+j-off(q)]; phases C, D: the sequences' offsets (uint16)
   uint32_t segHM[kSegs];                 // per segment: positions with a hash candidate (>= 5 bytes)
   uint32_t full[kNumOff][kWarps];        // per warp: segments whose E[q] word is all ones
   int w_size[kWarps], w_off[kWarps];     // per-warp totals of the scans
@@ -151,8 +159,8 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
 #pragma unroll
   for (int k = 0; k < (1 << kHashLog) / kThreads; ++k) S.htab[tid + k * kThreads] = kNoPos;
   // ---------------- phase A0: byte-equality bit masks for the fixed offsets ----------------
-  // In bit-plane data runs, 2/4-byte periods and the row above carry the long matches. A thread compares its 32-byte
-  // segment with itself shifted by the offset (__vcmpeq4 on 8 words) and keeps one bit per position; a match of length L
+  // In bit-plane data byte runs and the row above carry the long matches. A thread compares its 32-byte
+  // segment with itself shifted by the offset (eq4_shift_in on 8 words) and keeps one bit per position; a match of length L
   // at i with offset off(q) is then simply L consecutive ones in E_q starting at bit i — found, measured and extended
   // with shifts, ANDs and ffs on registers, never touching the bytes again.
   const int seg_lo = tid * 32;
@@ -170,8 +178,8 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
       const int lim = n - kLz4LastLiterals - seg_lo;     // match bytes never touch the last 5 bytes of the block
       const uint32_t tailmask = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : (1u << lim) - 1u);
   #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int d = q == 0 ? 1 : (q == 1 ? 2 : (q == 2 ? 4 : 3));
+      for (int q = 0; q < kNumShort; ++q) {
+        const int d = short_offset(q);
         uint32_t e = 0;
   #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -189,7 +197,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
             e = eq4_shift_in(e, W[k + 1], S.data[8 * tid + k - pitch_words]);
           }
         }
-        S.E[4][tid] = e & tailmask;
+        S.E[kNumShort][tid] = e & tailmask;
       }
       if (tid < kNumOff) S.E[tid][kSegs] = 0;
     }
@@ -512,7 +520,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
         uint32_t off;
         if ((Ms >> j) & 1u) {
           const uint32_t qq = ((D0 >> j) & 1u) | (((D1 >> j) & 1u) << 1) | (((D2 >> j) & 1u) << 2);
-          off = qq == 0 ? 1u : (qq == 1 ? 2u : (qq == 2 ? 4u : (qq == 3 ? 3u : 4u * (uint32_t)pitch_words)));
+          off = qq == (uint32_t)kNumShort ? 4u * (uint32_t)pitch_words : (uint32_t)short_offset((int)qq);
         } else {
           off = (uint32_t)(i - (int)(S.list[mybase + __popc(wants & ((1u << j) - 1u))] & 0x3FFFu));
         }
