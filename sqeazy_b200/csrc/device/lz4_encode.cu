@@ -297,8 +297,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
         atomicMin(&S.htab[h], (uint32_t)i);
       }
     };
-    auto lookup = [&](int from, int to) -> int {
-      int nfound = 0;
+    auto lookup = [&](int from, int to) {
       for (int e = from + tid; e < to; e += kThreads) {
         const int i = (int)S.list[e];
         // eight bytes at i and at the candidate from three aligned words each
@@ -320,14 +319,12 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
           // ratio within ~1 % on bit planes, improves it on background-removed stacks and matches liblz4 on noisy
           // 8-bit codes (tools/lz4_model.c), while halving the number of sequences
           if (len >= 5) {
-            ++nfound;
             res = c | ((uint32_t)(len - 5 < 3 ? len - 5 : 3) << 14);   // code 0,1,2: exactly 5,6,7 bytes; 3: >= 8
             atomicOr(&S.segHM[i >> 5], 1u << (i & 31));
           }
         }
         S.list[e] = (uint16_t)res;       // the entry is overwritten by its result
       }
-      return nfound;
     };
     // Early store: a block with fewer than kEarlyMin candidates — four times the fixed-offset ones of the sampled 4 KiB + the
     // hash ones of the first 2 KiB — is noise (camera-noise bit planes, 8-bit quantiser codes) and would shrink by < 3 %
@@ -335,17 +332,41 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
     // >= 243; the sampled count decides like the full one on all of them). It is stored without the masks of the other
     // twelve sub-blocks, the list, the parse and the emission, which is also what makes its decode a plain copy.
     // (Positions of the first 2 KiB find the same sources in a table that holds the first 2 KiB only as in the full one: a
-    //  first occurrence lies in front of them; their list indices are final as well: the list is in position order.)
-    int done = 0;
+    //  first occurrence lies in front of them.)
     if (test_early) {
+      // The test needs no list: the 2048 positions are spread over the 512 threads as they are (four each, consecutive lanes
+      // on consecutive bytes), the segments' owners pass their `wants` masks through a free row of S.E. Nothing is kept:
+      // a block that goes on enters its first 2 KiB into the list below like the rest — the same first occurrences come out
+      // (they lie in front of the position that looks them up) — so a noise block never pays for the serial list writes of
+      // two warps (32 entries per thread) while fourteen wait.
       if (lane == 0 && ncand_short) atomicAdd(&S.early, 4 * ncand_short);
-      static_assert(kEarlyBytes / kSub == 2, "bases of the early list: two warps");
-      if (warp < 2) write_list((warp ? S.w_size[0] : 0) + incl - cnt);
-      done = min(S.w_size[0] + S.w_size[1], kListMax);
+      static_assert(kEarlyBytes / kSub == 2 && kEarlyBytes % kThreads == 0, "the first two warps own the tested positions");
+      if (warp < kEarlyBytes / kSub) S.E[2][tid] = wants;
       __syncthreads();
-      insert(0, done);
+      uint32_t mine = 0;                 // bit k: position k * kThreads + tid looks up
+#pragma unroll
+      for (int k = 0; k < kEarlyBytes / kThreads; ++k) {
+        const int i = k * kThreads + tid;
+        if ((S.E[2][i >> 5] >> (i & 31)) & 1u) {
+          mine |= 1u << k;
+          atomicMin(&S.htab[(load4(S.data, i) * 2654435761u) >> (32 - kHashLog)], (uint32_t)i);
+        }
+      }
       __syncthreads();
-      const int nf = __reduce_add_sync(0xffffffffu, lookup(0, done));
+      int nf = 0;
+#pragma unroll
+      for (int k = 0; k < kEarlyBytes / kThreads; ++k) {
+        const int i = k * kThreads + tid;
+        if ((mine >> k) & 1u) {
+          const uint32_t v = load4(S.data, i);
+          const uint32_t c = S.htab[(v * 2654435761u) >> (32 - kHashLog)];
+          // a candidate counts when it gives a match of >= 5 bytes inside the sub-block (what the lookup below keeps)
+          if (c < (uint32_t)i && load4(S.data, (int)c) == v && data8[i + 4] == data8[c + 4] &&
+              min((i & ~(kSub - 1)) + kSub, n - kLz4LastLiterals) - i >= 5)
+            ++nf;
+        }
+      }
+      nf = __reduce_add_sync(0xffffffffu, nf);
       if (lane == 0 && nf) atomicAdd(&S.early, nf);
       __syncthreads();
       if (S.early < kEarlyMin) {
@@ -364,12 +385,12 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
       int wbase, wall;
       warp_totals(S.w_size, warp, lane, wbase, wall);
       mybase = wbase + incl - cnt;
-      if (!test_early || warp >= kEarlyBytes / kSub) write_list(mybase);
+      write_list(mybase);
       const int total = min(wall, kListMax);
       __syncthreads();
-      insert(done, total);
+      insert(0, total);
       __syncthreads();
-      lookup(done, total);
+      lookup(0, total);
       __syncthreads();
     }
   }

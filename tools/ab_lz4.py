@@ -27,6 +27,15 @@ del vol
 libs = [(os.path.basename(p), ctypes.CDLL(os.path.abspath(p))) for p in sys.argv[1:]]
 outbuf = torch.empty(sq.lz4_bound(planes.numel() * 2), dtype=torch.uint8, device="cuda")
 st = c_void_p(torch.cuda.current_stream().cuda_stream)
+def checksum(buf, n):
+    """position-dependent checksum of buf[:n] (equal between two builds = the same compressed bytes)"""
+    w = buf[: n & ~7].view(torch.int64)
+    acc = 0
+    for a in range(0, w.numel(), 1 << 26):
+        c = w[a : a + (1 << 26)]
+        acc += int((c * (torch.arange(a, a + c.numel(), device=c.device, dtype=torch.int64) * 2 + 1)).sum().item())
+    acc += int(buf[n & ~7 : n].to(torch.int64).sum().item())
+    return acc & 0xFFFFFFFFFFFFFFFF
 for name, x in inputs.items():
     if only and name not in only.split(","): continue
     for rnd in range(2):
@@ -41,9 +50,10 @@ for name, x in inputs.items():
                     rc = L.sqyx_lz4_encode(c_void_p(x.data_ptr()), c_long(x.numel()), c_void_p(outbuf.data_ptr()), c_long(outbuf.numel()), ctypes.byref(n), st)
                 assert rc == 0
             run(); torch.cuda.synchronize()
+            ck = checksum(outbuf, n.value)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(5): run()
             e1.record(); e1.synchronize()
             ms = e0.elapsed_time(e1) / 5
-            print(f"{name:16s} {lname:24s} {ms:7.3f} ms  {x.numel() / ms / 1e6:7.1f} GB/s  payload {n.value}")
+            print(f"{name:16s} {lname:24s} {ms:7.3f} ms  {x.numel() / ms / 1e6:7.1f} GB/s  payload {n.value}  bytes {ck:016x}", flush=True)
