@@ -59,6 +59,7 @@ constexpr int kEarlyBytes = 2048;        // early-store test on the hash candida
 constexpr int kEarlyMin = 128;           // ... a block with fewer candidates than this is stored
 constexpr uint32_t kNoCand = 0xFFFFu;
 constexpr uint32_t kNoPos = 0xFFFFFFFFu;
+constexpr uint32_t kPrefetchAhead = 3 * kNumSMs;   // blocks between a CTA's block and the one it requests into L2 (one residency wave)
 constexpr int kLitSelf = 32;             // literal runs up to this length are copied by their sequence's thread
 
 static_assert(kSegs == kThreads, "one segment per thread");
@@ -70,14 +71,14 @@ struct __align__(16) EncSmem {
     uint16_t list[kListMax];             // phase A2: positions that look up; then, in place: candidate | code << 14 (kNoCand: none)
     uint32_t out[(kB + 64) / 4];         // phase D: encoded bytes (every list read happens before the first out write)
   };
-  union {
-    uint32_t htab[1 << kHashLog];        // phase A2 only: FIRST listed position of the block with this hash (kNoPos: none)
-    uint16_t lead[kNumOff][kSegs + 2];   // phase B: ones of E[q] from the first position of segment t on, to the end of the warp's sub-block at
-                                         // most; 0 for the first segment of a sub-block (what a run of the sub-block in front continues with)
+  uint32_t htab[1 << kHashLog];          // phase A2: FIRST listed position of the block with this hash (kNoPos: none)
                                          // phases C, D: the block's sequences, position | length << 14
-  };
-  uint32_t E[kNumOff < 4 ? 4 : kNumOff][kSegs + 4];   // (four rows at least: the phases C, D use)
-                                         // E[q][t] bit j: data[32t+j] == data[32t+j-off(q)]; phases C, D: the sequences' offsets (uint16)
+  uint32_t E[4][kSegs + 4];              // rows q < kNumOff: E[q][t] bit j: data[32t+j] == data[32t+j-off(q)]
+                                         // row 2, as uint16 lead[kNumOff][kSegs + 2] (lead_row): ones of E[q] from the first position of
+                                         //   segment t on, to the end of the warp's sub-block at most; 0 for the first segment of a
+                                         //   sub-block (what a run of the sub-block in front continues with)
+                                         // row 3: the `wants` masks of the first 2 KiB for the early-store test
+                                         // phases C, D: all four rows hold the sequences' offsets (uint16)
   uint32_t segHM[kSegs];                 // per segment: positions with a hash candidate (>= 5 bytes)
   uint32_t full[kNumOff][kWarps];        // per warp: segments whose E[q] word is all ones
   int w_size[kWarps], w_off[kWarps];     // per-warp totals of the scans
@@ -133,13 +134,17 @@ __device__ __forceinline__ int put_ext(uint8_t* p, int v) {
 }
 
 // number of consecutive ones of E[q] from position x on, inside the sub-block of x: the ones left in x's segment, then
-// what the table says about the segments behind it (S.lead: computed once per segment with ballots and a shuffle, so that
+// what the table says about the segments behind it (lead_row: computed once per segment with ballots and a shuffle, so that
 // the few lanes that measure a run do not walk the masks themselves)
+// (the table lives in row 2 of S.E, which is free until phase C: it is written before the hash table is — which it shared
+//  its memory with before — and the barrier between the two went away)
+__device__ __forceinline__ uint16_t* lead_row(EncSmem& S, int q) { return reinterpret_cast<uint16_t*>(&S.E[2][0]) + q * (kSegs + 2); }
+__device__ __forceinline__ const uint16_t* lead_row(const EncSmem& S, int q) { return reinterpret_cast<const uint16_t*>(&S.E[2][0]) + q * (kSegs + 2); }
 __device__ __forceinline__ int run_ones(const EncSmem& S, int q, int x) {
   const int t = x >> 5, b = x & 31;
   const uint32_t z = ~(S.E[q][t] >> b);          // zeros where the run goes on; the shifted-in bits end it at the segment border
   const int r = z ? __ffs(z) - 1 : 32;           // (z == 0 only for b == 0 and a full word); r <= 32 - b
-  return r == 32 - b ? r + (int)S.lead[q][t + 1] : r;   // (the entry of a sub-block's first segment is 0: runs end there)
+  return r == 32 - b ? r + (int)lead_row(S, q)[t + 1] : r;   // (the entry of a sub-block's first segment is 0: runs end there)
 }
 
 // The general path of a block (phases A0..D on the bytes in S.data), kept out of line: the closed-form path of all-equal
@@ -264,6 +269,8 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
     analyse();
     count_wants();
   }
+  // (for the early-store test below: the `wants` masks of the first 2 KiB, in a row of S.E that is free until phase C)
+  if (warp < kEarlyBytes / kSub) S.E[3][tid] = wants;
   const int ncand_short = sampled ? __reduce_add_sync(0xffffffffu, __popc(Ms)) : 0;   // (warp-uniform)
   // One barrier, two answers. Lanes 0..15 of a warp vote "rich": a sampled warp that is already rich in fixed-offset
   // candidates — every compressible bit-plane block — settles the early-store test for the CTA. Lane 16 votes "this warp has
@@ -272,6 +279,22 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
   const bool rich = votes >= 16, all_eager = (votes & 15) == 0;
   const bool test_early = !rich && n > kEarlyBytes;
 
+  int entry0 = 0;
+  auto lead_table = [&]() {
+#pragma unroll
+    for (int q = 0; q < kNumOff; ++q) {
+      const uint32_t own = S.E[q][tid];
+      const int lead = own == 0xffffffffu ? 32 : __ffs(~own) - 1;
+      const uint32_t nf = ~(S.full[q][warp] >> lane);          // zeros: full segments from this one on (shifted-in bits: the warp ends)
+      const int k = min(nf ? __ffs(nf) - 1 : 32, 32 - lane);   // full segments in a row, this one included
+      const int tail = __shfl_sync(0xffffffffu, lead, (lane + k) & 31);   // leading ones of the first segment that is not full
+      lead_row(S, q)[tid] = lane ? (uint16_t)(32 * k + (lane + k < 32 ? tail : 0)) : (uint16_t)0;
+      if (tid == 0) lead_row(S, q)[kSegs] = 0;
+      // first guess of where the parse enters this segment (phase B), from the same words
+      const uint32_t prevtop = __shfl_up_sync(0xffffffffu, own >> 27, 1);
+      if (lane > 0 && prevtop == 31u) entry0 = max(entry0, lead);
+    }
+  };
   // ---------------- phase A2: hash candidates for the positions without a fixed-offset match ----------------
   // The wanting positions of the block are compacted, in order, into S.list (exclusive scan of the per-thread counts), all
   // of them are inserted into one hash table, then all of them are looked up. An entry is overwritten by its result.
@@ -335,19 +358,17 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
     //  first occurrence lies in front of them.)
     if (test_early) {
       // The test needs no list: the 2048 positions are spread over the 512 threads as they are (four each, consecutive lanes
-      // on consecutive bytes), the segments' owners pass their `wants` masks through a free row of S.E. Nothing is kept:
+      // on consecutive bytes), the segments' owners have passed their `wants` masks through S.E[3]. Nothing is kept:
       // a block that goes on enters its first 2 KiB into the list below like the rest — the same first occurrences come out
       // (they lie in front of the position that looks them up) — so a noise block never pays for the serial list writes of
       // two warps (32 entries per thread) while fourteen wait.
       if (lane == 0 && ncand_short) atomicAdd(&S.early, 4 * ncand_short);
       static_assert(kEarlyBytes / kSub == 2 && kEarlyBytes % kThreads == 0, "the first two warps own the tested positions");
-      if (warp < kEarlyBytes / kSub) S.E[2][tid] = wants;
-      __syncthreads();
       uint32_t mine = 0;                 // bit k: position k * kThreads + tid looks up
 #pragma unroll
       for (int k = 0; k < kEarlyBytes / kThreads; ++k) {
         const int i = k * kThreads + tid;
-        if ((S.E[2][i >> 5] >> (i & 31)) & 1u) {
+        if ((S.E[3][i >> 5] >> (i & 31)) & 1u) {
           mine |= 1u << k;
           atomicMin(&S.htab[(load4(S.data, i) * 2654435761u) >> (32 - kHashLog)], (uint32_t)i);
         }
@@ -381,6 +402,8 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
       }
       __syncthreads();
     }
+    __syncwarp();                      // (S.full of this warp)
+    lead_table();
     {
       int wbase, wall;
       warp_totals(S.w_size, warp, lane, wbase, wall);
@@ -394,29 +417,9 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
       __syncthreads();
     }
   }
-  // ones at the start of every segment and beyond, for run_ones (htab is free now)
-  int entry0 = 0;
-  {
-#pragma unroll
-    for (int q = 0; q < kNumOff; ++q) {
-      const uint32_t own = S.E[q][tid];
-      const int lead = own == 0xffffffffu ? 32 : __ffs(~own) - 1;
-      const uint32_t nf = ~(S.full[q][warp] >> lane);          // zeros: full segments from this one on (shifted-in bits: the warp ends)
-      const int k = min(nf ? __ffs(nf) - 1 : 32, 32 - lane);   // full segments in a row, this one included
-      const int tail = __shfl_sync(0xffffffffu, lead, (lane + k) & 31);   // leading ones of the first segment that is not full
-      S.lead[q][tid] = lane ? (uint16_t)(32 * k + (lane + k < 32 ? tail : 0)) : (uint16_t)0;
-      if (tid == 0) S.lead[q][kSegs] = 0;
-      // first guess of where the parse enters this segment (phase B), from the same words
-      const uint32_t prevtop = __shfl_up_sync(0xffffffffu, own >> 27, 1);
-      if (lane > 0 && prevtop == 31u) entry0 = max(entry0, lead);
-    }
-  }
   const uint32_t HM = S.segHM[tid];
-  const int any_found = __syncthreads_or((Ms | HM) != 0u);
-
-  if (!any_found) {
-    stored = true;
-  } else {
+  // (no test for "no candidate at all" and no barrier here: such a block comes out of the parse with no sequence and is stored)
+  {
     // ---------------- phase B: every thread parses its own 32-byte segment greedily ----------------
     // A match may overshoot into the following segments of the same warp; their entry point moves and
     // they re-parse until the warp's parse is stable (lane k is final after at most k+1 rounds).
@@ -520,7 +523,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
       if (lane >= d) sincl += t;
     }
     if (lane == 31) S.w_size[warp] = sincl;
-    __syncthreads();                                   // every warp is through phase B as well: S.E and S.lead are free
+    __syncthreads();                                   // every warp is through phase B as well: S.E (masks and lead table) is free
     int sbase, nseq;
     warp_totals(S.w_size, warp, lane, sbase, nseq);
     sbase += sincl - nm;
@@ -696,6 +699,14 @@ lz4_encode_kernel(const uint8_t* __restrict__ src, uint64_t raw_bytes, uint8_t* 
   const uint8_t* bsrc = src + boff;
   uint8_t* data8 = reinterpret_cast<uint8_t*>(S.data);
   uint8_t* out8 = reinterpret_cast<uint8_t*>(S.out);
+  // The block that the CTA one residency wave behind this one will load is requested into L2 now: an all-equal block is
+  // bound by the bytes an SM has in flight (3 CTAs x 16 KiB), and a noise block holds its slot for the early-store test
+  // without loading anything (measured: all-zero input 1.147 -> 1.068 ms per 4 GiB, cfg2 planes 5.35 -> 5.29 ms, plain planes
+  // 5.73 -> 5.65 ms; three waves ahead: the same, ten: half of the gain).
+  if (tid < kB / 128 && blockIdx.x + kPrefetchAhead < gridDim.x) {
+    const uint64_t poff = boff + (uint64_t)kPrefetchAhead * kB + (uint64_t)tid * 128u;
+    if (poff < raw_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + poff));
+  }
 
   // ---------------- load ----------------
   bool same = true;
