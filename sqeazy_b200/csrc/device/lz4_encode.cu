@@ -598,6 +598,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
     const int per = (nseq + kThreads) / kThreads;      // ceil((nseq + 1) / kThreads)
     const int s0 = min(tid * per, nseq + 1), s1 = min(s0 + per, nseq + 1);
     int mysize = 0;
+    bool has_long = false;             // a literal run of this thread's sequences is copied by a whole warp (phase D)
     {
       int prev_end = 0;
       // (the sequence in front may be a joined piece or a head that has grown: the chain's pieces end where it ends, except
@@ -607,11 +608,15 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
         if (sq < nseq) {
           const uint32_t pl = seq_pl[sq];
           const int pos = (int)(pl & 0x3FFFu), len = (int)((pl & ~kJoined) >> 14), lit = pos - prev_end;
-          if (!(pl & kJoined)) mysize += 3 + ext_bytes(lit) + lit + ext_bytes(len - 4);
+          if (!(pl & kJoined)) {
+            mysize += 3 + ext_bytes(lit) + lit + ext_bytes(len - 4);
+            has_long = has_long || lit > kLitSelf;
+          }
           prev_end = pos + len;
         } else {
           const int lit = n - prev_end;
           mysize += 1 + ext_bytes(lit) + lit;
+          has_long = has_long || lit > kLitSelf;
         }
       }
     }
@@ -622,7 +627,7 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
       if (lane >= d) oincl += t;
     }
     if (lane == 31) S.w_off[warp] = oincl;
-    __syncthreads();
+    const int any_long = __syncthreads_or(has_long);
     int o;
     warp_totals(S.w_off, warp, lane, o, csize);
     o += oincl - mysize;
@@ -670,12 +675,14 @@ __device__ __noinline__ int encode_general(EncSmem& S, const int n, const int pi
         o = d;
         prev_end = pos + len;
       }
-      __syncthreads();
-      const int nlong = S.nlong;
-      for (int r = warp; r < nlong; r += kWarps) {
-        const uint32_t r0 = longrec[2 * r], dst = longrec[2 * r + 1];
-        const int from = (int)(r0 & 0x3FFFu), cnt = (int)(r0 >> 14);
-        for (int t = lane; t < cnt; t += 32) out8[dst + t] = data8[from + t];
+      if (any_long) {                  // (block-uniform: most blocks of a sparse plane have none and save the barrier)
+        __syncthreads();
+        const int nlong = S.nlong;
+        for (int r = warp; r < nlong; r += kWarps) {
+          const uint32_t r0 = longrec[2 * r], dst = longrec[2 * r + 1];
+          const int from = (int)(r0 & 0x3FFFu), cnt = (int)(r0 >> 14);
+          for (int t = lane; t < cnt; t += 32) out8[dst + t] = data8[from + t];
+        }
       }
     }
   }

@@ -51,6 +51,10 @@ for name, x in inputs.items():
                 assert rc == 0
             run(); torch.cuda.synchronize()
             ck = checksum(outbuf, n.value)
+            if rnd == 0:                # the stream decodes back to the input (decoder of the in-tree library)
+                back = torch.empty_like(x)
+                assert sq.lz4_decode_device(outbuf[: n.value], back) == x.numel() and torch.equal(back, x), "round trip failed"
+                del back
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(5): run()
