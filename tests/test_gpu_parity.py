@@ -150,6 +150,28 @@ def test_histogram_distributions(sq, cuda, port, kind):
     assert np.array_equal(hist.cpu().numpy().view(np.uint32), want.astype(np.uint32))
 
 
+@pytest.mark.parametrize("kind", ["uniform", "all_high", "bright_tail"])
+def test_histogram_bright_stacks(sq, cuda, port, kind):
+    """stacks with many voxels above the CTA-private bins (>= 49152): a thread that has sent more than 64 of them to global
+    atomics leaves the rest to a second sweep in shared memory (quantise.cu) — enough iterations per thread here to get there"""
+    n = (1 << 26) + 5
+    rng = np.random.default_rng(7)
+    if kind == "uniform":
+        a = rng.integers(0, 65536, size=n, dtype=np.uint16)
+    elif kind == "all_high":
+        a = rng.integers(49152, 65536, size=n, dtype=np.uint16)
+    else:                               # camera-like, the second half of the stack saturated here and there
+        a = np.clip(rng.normal(100, 3, n), 0, 65535).astype(np.uint16)
+        a[n // 2:][rng.random(n - n // 2) < 0.2] = 65535
+    hist = cuda.zeros(65536, dtype=cuda.int32, device="cuda")
+    d = dev(cuda, a)
+    sq.histogram_device(d, hist)
+    sq.histogram_device(d[3: n - 1], hist)                                        # unaligned view, accumulating
+    cuda.cuda.synchronize()
+    want = port.histogram(a).astype(np.uint64) + port.histogram(a[3: n - 1])
+    assert np.array_equal(hist.cpu().numpy().view(np.uint32), want.astype(np.uint32))
+
+
 def test_histogram_unaligned_and_accumulating(sq, cuda, port):
     a = np.random.default_rng(0).integers(0, 3000, size=(1 << 21) + 5, dtype=np.uint16)
     d = dev(cuda, a)
