@@ -21,7 +21,11 @@ small = torch_volume((256, 512, 512), "scmos")
 sp = torch.empty_like(small)
 sq.bitswap_encode_device(1, small.view(-1), sp.view(-1))
 inputs["cfg1 planes"] = sp.view(torch.uint8).view(-1)
+inputs["noise 2 GiB (all stored)"] = torch.randint(0, 256, (1 << 31,), dtype=torch.uint8, device="cuda")
 del vol
+only = os.environ.get("AB_ONLY")
+if only:
+    inputs = {k: v for k, v in inputs.items() if any(o in k for o in only.split(","))}
 libs = [(os.path.basename(p), ctypes.CDLL(os.path.abspath(p))) for p in sys.argv[1:]]
 st = c_void_p(torch.cuda.current_stream().cuda_stream)
 for name, x in inputs.items():
