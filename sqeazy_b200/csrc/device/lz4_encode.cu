@@ -88,6 +88,8 @@ struct __align__(16) EncSmem {
 };
 
 static_assert(sizeof(EncSmem) <= (228 * 1024 - 3 * 1024) / 3, "three CTAs per SM (1 KiB of each CTA's share is the system's)");
+static_assert(sizeof(uint16_t) * kNumOff * (kSegs + 2) <= sizeof(uint32_t) * (kSegs + 4), "the lead table fits row 2 of S.E");
+static_assert(kEarlyBytes / 32 <= kSegs, "the early-store test's wants masks fit row 3 of S.E");
 
 __device__ __forceinline__ int ext_bytes(int v) {
   if (v < 15) return 0;          // by far the common case: keep the division off the hot path
